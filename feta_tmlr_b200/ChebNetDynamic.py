@@ -1,0 +1,118 @@
+"""Drop-in ``ChebConvDynamic`` (reference: transformer/ChebNetDynamic.py:29-198).
+
+Same constructor, ``forward`` signature, parameter names (``bias``; ``weight`` only in
+``learn_only_filter_order_coeff`` mode) and output shape as the reference's PyG module, but the
+whole forward is ONE fused sm_100a kernel (csrc/cheb.cu) behind the C ABI, with a matching fused
+backward, over a CSR plan of the scaled Laplacian built once per mini-batch (csrc/cheb_plan.cu).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+class ChebConvDynamic(nn.Module):
+    def __init__(self, in_channels, out_channels, K, normalization='sym', bias=True,
+                 learn_only_filter_order_coeff=False, **kwargs):
+        # kwargs: MessagePassing options of the reference (aggr/flow/node_dim); only the defaults
+        # the reference uses ('add', 'source_to_target', 0) are implemented
+        aggr = kwargs.pop('aggr', 'add')
+        flow = kwargs.pop('flow', 'source_to_target')
+        node_dim = kwargs.pop('node_dim', 0)
+        if aggr != 'add' or flow != 'source_to_target' or node_dim != 0 or kwargs:
+            raise NotImplementedError("ChebConvDynamic(b200): only aggr='add', "
+                                      "flow='source_to_target', node_dim=0 are implemented")
+        super().__init__()
+        assert K > 0
+        assert normalization in [None, 'sym', 'rw'], 'Invalid normalization'
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.K = K
+        self.normalization = normalization
+        if learn_only_filter_order_coeff:
+            self.weight = nn.Parameter(torch.empty(K, in_channels, out_channels))
+        self.learn_only_filter_order_coeff = learn_only_filter_order_coeff
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self._plans = OrderedDict()      # small identity-keyed cache: one plan per mini-batch
+        self.plan_hints = None           # set by a caller that knows max_nodes on the host
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.learn_only_filter_order_coeff:          # glorot, ChebNetDynamic.py:20-23
+            stdv = math.sqrt(6.0 / (self.weight.size(-2) + self.weight.size(-1)))
+            self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.fill_(0)
+
+    def __deepcopy__(self, memo):       # plans hold device buffers tied to one batch: never cloned
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, OrderedDict() if k == '_plans' else copy.deepcopy(v, memo))
+        return new
+
+    # -- plan management -------------------------------------------------------------------
+    def get_plan(self, edge_index, batch, num_rows, num_graphs, lambda_max, hints=None):
+        """The reference recomputes ``__norm__`` (:157-160) and ``unique`` (:148) on every call;
+        here the CSR plan is cached per (edge_index, batch) identity + version."""
+        key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape),
+               None if batch is None else (batch.data_ptr(), batch._version, batch.dtype),
+               num_rows, num_graphs, float(lambda_max), None if hints is None else tuple(sorted(hints.items())))
+        hit = self._plans.get(key)
+        if hit is not None:
+            self._plans.move_to_end(key)
+            return hit
+        plan = ops.build_cheb_plan(edge_index, batch, num_rows, num_graphs, lambda_max, hints=hints)
+        plan._keep = (edge_index, batch)     # pins the storage so the identity key cannot be recycled
+        self._plans[key] = plan
+        while len(self._plans) > 4:
+            self._plans.popitem(last=False)
+        return plan
+
+    def forward(self, x, edge_index, filter_coeff, edge_weight=None, batch=None, lambda_max=None,
+                plan=None):
+        """ChebNetDynamic.py:132-189.  ``plan`` (extension): a prebuilt ``ops.ChebPlan``."""
+        if self.normalization != 'sym' and lambda_max is None:
+            raise ValueError('You need to pass `lambda_max` to `forward() in`'
+                             'case the normalization is non-symmetric.')
+        if self.normalization != 'sym':
+            raise NotImplementedError("ChebConvDynamic(b200): only normalization='sym' is implemented "
+                                      "(the reference drivers never pass another, SURVEY.md section 5)")
+        if edge_weight is not None:
+            raise NotImplementedError("ChebConvDynamic(b200): edge_weight is not implemented "
+                                      "(never passed by the reference, models.py:360)")
+        if lambda_max is None:
+            lambda_max = 2.0
+        if isinstance(lambda_max, torch.Tensor):
+            if lambda_max.numel() != 1:
+                raise NotImplementedError("ChebConvDynamic(b200): per-graph lambda_max is not implemented")
+            lambda_max = float(lambda_max)
+        if batch is None:
+            raise NameError("ChebConvDynamic.forward: `weight` is unbound when batch is None "
+                            "(ChebNetDynamic.py:146-166) -- pass `batch`")
+        if self.learn_only_filter_order_coeff:
+            # out = sum_k (c_k[g] * T_k) W_k  ==  sum_k T_k (c_k[g] W_k): same fused kernel
+            theta = filter_coeff.reshape(filter_coeff.shape[0], filter_coeff.shape[1], 1, 1) \
+                * self.weight.unsqueeze(1)
+        else:
+            theta = filter_coeff
+        if theta.dim() != 4:
+            raise ValueError("filter_coeff must be [K, G, in, out]; got %s" % (tuple(theta.shape),))
+        R = x.size(0)
+        G = theta.size(1)
+        if plan is None:
+            plan = self.get_plan(edge_index, batch, R, G, lambda_max, hints=self.plan_hints)
+        out = ops.cheb_filter(x, theta, self.bias, plan)
+        return out.squeeze()        # the reference's bmm(...).squeeze(), :167
+
+    def __repr__(self):
+        return '{}({}, {}, K={}, normalization={})'.format(
+            self.__class__.__name__, self.in_channels, self.out_channels, self.K, self.normalization)

@@ -1,0 +1,369 @@
+// A6: kernel-biased attention core, fp32-exact CUDA-core path (see include/feta_b200.h).
+//
+// Replaces the un-fused bmm -> masked_fill -> max -> exp -> *pe -> /clamp(sum) -> bmm chain of the
+// (missing) DiffTransformerEncoderLayer that transformer/models.py:4 imports; contract from
+// models.py:166-167.  One launch computes S, the kernel-biased normalisation, writes the
+// attention matrix the caller needs (models.py:173 consumes it) and O = P V per head, with K/V
+// of the (graph, head) staged once in shared memory.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace feta {
+
+constexpr int kAttnThreads = 256;
+constexpr int kAttnWarps = kAttnThreads / 32;
+constexpr int kRowsPerCta = 32;  // forward: query rows per CTA
+
+// n_eff = 1 + index of the last un-masked position of graph b (0 if all masked)
+__device__ __forceinline__ int block_n_eff(const uint8_t* __restrict__ mk, int nmax, int* s_neff) {
+  if (threadIdx.x == 0) *s_neff = 0;
+  __syncthreads();
+  int loc = 0;
+  for (int j = threadIdx.x; j < nmax; j += blockDim.x)
+    if (mk[j] == 0) loc = j + 1;
+  if (loc > 0) atomicMax(s_neff, loc);
+  __syncthreads();
+  return *s_neff;
+}
+
+template <int DH>
+__device__ __forceinline__ float slice_reduce(float v) {
+  // lanes are (c = lane % DH, slice = lane / DH); sum over slices
+#pragma unroll
+  for (int o = 16; o >= DH; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ forward -------------
+template <int DH, int NCH>
+__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
+    const float* __restrict__ pe, const uint8_t* __restrict__ mask, float* __restrict__ attn,
+    float* __restrict__ o_heads, float* __restrict__ rowflag, int H, int nmax, float scale) {
+  extern __shared__ float smem[];
+  __shared__ int s_neff;
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int i0 = blockIdx.x * kRowsPerCta;
+  const uint8_t* mk = mask + (size_t)b * nmax;
+  const int n = block_n_eff(mk, nmax, &s_neff);
+  const int npad = nmax | 1;
+  float* Kt = smem;                         // [DH][npad]
+  float* Vs = Kt + (size_t)DH * npad;       // [nmax][DH]
+  float* prow = Vs + (size_t)nmax * DH;     // [warps][npad]
+  float* pen = prow + (size_t)kAttnWarps * npad;  // [nmax] 0 or -inf key penalty
+
+  const float* kb = k + (int64_t)b * sb + h * DH;
+  const float* vb = v + (int64_t)b * sb + h * DH;
+  for (int idx = threadIdx.x; idx < n * DH; idx += blockDim.x) {
+    const int j = idx / DH, c = idx - j * DH;
+    Kt[c * npad + j] = __ldg(kb + (int64_t)j * sn + c);
+    Vs[idx] = __ldg(vb + (int64_t)j * sn + c);
+  }
+  for (int j = threadIdx.x; j < nmax; j += blockDim.x) pen[j] = mk[j] ? -INFINITY : 0.0f;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pr = prow + (size_t)warp * npad;
+  for (int ii = warp; ii < kRowsPerCta; ii += kAttnWarps) {
+    const int i = i0 + ii;
+    if (i >= nmax) break;
+    float* arow = attn + (((size_t)b * H + h) * nmax + i) * nmax;
+    float* orow = o_heads + (((size_t)b * nmax + i) * H + h) * DH;
+    if (mk[i]) {  // padded query: defined as zero (never consumed by the model)
+      for (int j = lane; j < nmax; j += 32) arow[j] = 0.0f;
+      if (lane < DH) orow[lane] = 0.0f;
+      if (DH > 32 && lane + 32 < DH) orow[lane + 32] = 0.0f;
+      if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = 0.0f;
+      continue;
+    }
+    float qr[DH];
+    const float* qp = q + (int64_t)i * sn + (int64_t)b * sb + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) qr[c] = __ldg(qp + c) * scale;  // q * scaling before the product
+    float s[NCH];
+    float m = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int j = lane + 32 * ch;
+      float a = -INFINITY;
+      if (j < n) {
+        a = 0.0f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) a = fmaf(qr[c], Kt[c * npad + j], a);
+        a += pen[j];
+      }
+      s[ch] = a;
+      m = fmaxf(m, a);
+    }
+    m = warp_max(m);
+    float sum = 0.0f;
+    const float* perow = pe ? pe + ((size_t)b * nmax + i) * nmax : nullptr;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int j = lane + 32 * ch;
+      float e = 0.0f;
+      if (j < n && s[ch] != -INFINITY) {
+        e = expf(s[ch] - m);
+        if (perow) e *= __ldg(perow + j);
+      }
+      s[ch] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float denom = fmaxf(sum, 1e-6f);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int j = lane + 32 * ch;
+      const float p = s[ch] / denom;
+      if (j < nmax) arow[j] = p;
+      if (j < n) pr[j] = p;
+    }
+    if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = sum > 1e-6f ? 1.0f : 0.0f;
+    __syncwarp();
+    if (DH <= 32) {
+      constexpr int NS = DH <= 32 ? 32 / DH : 1;
+      const int c = lane % DH, js = lane / DH;
+      float o = 0.0f;
+      for (int j = js; j < n; j += NS) o = fmaf(pr[j], Vs[j * DH + c], o);
+      o = slice_reduce<(DH <= 32 ? DH : 32)>(o);
+      if (js == 0) orow[c] = o;
+    } else {
+      float o0 = 0.0f, o1 = 0.0f;
+      for (int j = 0; j < n; ++j) {
+        const float p = pr[j];
+        o0 = fmaf(p, Vs[j * DH + lane], o0);
+        o1 = fmaf(p, Vs[j * DH + lane + 32], o1);
+      }
+      orow[lane] = o0;
+      orow[lane + 32] = o1;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ backward ------------
+// One CTA per (graph, head).  Rows are processed in rounds of 8 (one per warp): phase A builds
+// dS_i and dQ_i for the warp's row, phase B lets every thread fold the round's 8 rows into the
+// (j, c) entries of dK / dV it owns -- deterministic, no atomics.
+template <int DH, int NCH>
+__global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
+    const uint8_t* __restrict__ mask, const float* __restrict__ attn, const float* __restrict__ rowflag,
+    const float* __restrict__ d_o, const float* __restrict__ d_attn, float* __restrict__ dq, float* __restrict__ dk,
+    float* __restrict__ dv, int64_t dsn, int64_t dsb, int H, int nmax, float scale) {
+  extern __shared__ float smem[];
+  __shared__ int s_neff;
+  __shared__ int s_valid[kAttnWarps];
+  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+  const uint8_t* mk = mask + (size_t)b * nmax;
+  const int n = block_n_eff(mk, nmax, &s_neff);
+  const int npad = nmax | 1;
+  float* Vt = smem;                              // [DH][npad]
+  float* Ks = Vt + (size_t)DH * npad;            // [nmax][DH]
+  float* Qs = Ks + (size_t)nmax * DH;            // [nmax][DH]
+  float* dOs = Qs + (size_t)nmax * DH;           // [nmax][DH]
+  float* dKs = dOs + (size_t)nmax * DH;          // [nmax][DH]
+  float* dVs = dKs + (size_t)nmax * DH;          // [nmax][DH]
+  float* Pb = dVs + (size_t)nmax * DH;           // [warps][npad]
+  float* dSb = Pb + (size_t)kAttnWarps * npad;   // [warps][npad]
+
+  const int64_t base_in = (int64_t)b * sb + h * DH;
+  for (int idx = threadIdx.x; idx < nmax * DH; idx += blockDim.x) {
+    const int j = idx / DH, c = idx - j * DH;
+    float kk = 0.f, vv = 0.f, qq = 0.f, dd = 0.f;
+    if (j < n) {
+      kk = __ldg(k + base_in + (int64_t)j * sn + c);
+      vv = __ldg(v + base_in + (int64_t)j * sn + c);
+      qq = __ldg(q + base_in + (int64_t)j * sn + c);
+      dd = __ldg(d_o + (((size_t)b * nmax + j) * H + h) * DH + c);
+    }
+    Vt[c * npad + j] = vv;
+    Ks[idx] = kk;
+    Qs[idx] = qq;
+    dOs[idx] = dd;
+    dKs[idx] = 0.0f;
+    dVs[idx] = 0.0f;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pr = Pb + (size_t)warp * npad;
+  float* ds = dSb + (size_t)warp * npad;
+  for (int base = 0; base < n; base += kAttnWarps) {
+    const int i = base + warp;
+    const bool valid = (i < n) && (mk[i] == 0);
+    if (lane == 0) s_valid[warp] = valid;
+    if (valid) {
+      // ---- phase A
+      float dor[DH];
+#pragma unroll
+      for (int c = 0; c < DH; ++c) dor[c] = dOs[i * DH + c];
+      const float* arow = attn + (((size_t)b * H + h) * nmax + i) * nmax;
+      const float* garow = d_attn ? d_attn + (((size_t)b * H + h) * nmax + i) * nmax : nullptr;
+      float p[NCH], dp[NCH];
+      float delta = 0.0f;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int j = lane + 32 * ch;
+        float pv = 0.0f, dpv = 0.0f;
+        if (j < n) {
+          pv = __ldg(arow + j);
+#pragma unroll
+          for (int c = 0; c < DH; ++c) dpv = fmaf(dor[c], Vt[c * npad + j], dpv);
+          if (garow) dpv += __ldg(garow + j);
+        }
+        p[ch] = pv;
+        dp[ch] = dpv;
+        delta = fmaf(pv, dpv, delta);
+      }
+      delta = warp_sum(delta) * __ldg(rowflag + ((size_t)b * H + h) * nmax + i);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int j = lane + 32 * ch;
+        if (j < n) {
+          pr[j] = p[ch];
+          ds[j] = p[ch] * (dp[ch] - delta);
+        }
+      }
+      __syncwarp();
+      float* dqrow = dq + (int64_t)i * dsn + (int64_t)b * dsb + h * DH;
+      if (DH <= 32) {
+        constexpr int NS = DH <= 32 ? 32 / DH : 1;
+        const int c = lane % DH, js = lane / DH;
+        float a = 0.0f;
+        for (int j = js; j < n; j += NS) a = fmaf(ds[j], Ks[j * DH + c], a);
+        a = slice_reduce<(DH <= 32 ? DH : 32)>(a);
+        if (js == 0) dqrow[c] = a * scale;
+      } else {
+        float a0 = 0.0f, a1 = 0.0f;
+        for (int j = 0; j < n; ++j) {
+          a0 = fmaf(ds[j], Ks[j * DH + lane], a0);
+          a1 = fmaf(ds[j], Ks[j * DH + lane + 32], a1);
+        }
+        dqrow[lane] = a0 * scale;
+        dqrow[lane + 32] = a1 * scale;
+      }
+    }
+    __syncthreads();
+    // ---- phase B
+    for (int idx = threadIdx.x; idx < n * DH; idx += blockDim.x) {
+      const int j = idx / DH, c = idx - j * DH;
+      float ak = dKs[idx], av = dVs[idx];
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) {
+        if (s_valid[w]) {
+          const int iw = base + w;
+          ak = fmaf(dSb[w * npad + j], Qs[iw * DH + c], ak);
+          av = fmaf(Pb[w * npad + j], dOs[iw * DH + c], av);
+        }
+      }
+      dKs[idx] = ak;
+      dVs[idx] = av;
+    }
+    __syncthreads();
+  }
+  // write dK, dV for every position (zeros for padding) and dQ = 0 for padded queries
+  for (int idx = threadIdx.x; idx < nmax * DH; idx += blockDim.x) {
+    const int j = idx / DH, c = idx - j * DH;
+    const int64_t o = (int64_t)j * dsn + (int64_t)b * dsb + h * DH + c;
+    const bool real = (j < n) && (mk[j] == 0);
+    dk[o] = real ? dKs[idx] * scale : 0.0f;
+    dv[o] = real ? dVs[idx] : 0.0f;
+    if (!real) dq[o] = 0.0f;
+  }
+}
+
+static size_t attn_fwd_smem(int dh, int nmax) {
+  const int npad = nmax | 1;
+  return ((size_t)dh * npad + (size_t)nmax * dh + (size_t)kAttnWarps * npad + nmax) * sizeof(float);
+}
+static size_t attn_bwd_smem(int dh, int nmax) {
+  const int npad = nmax | 1;
+  return ((size_t)dh * npad + 5 * (size_t)nmax * dh + 2 * (size_t)kAttnWarps * npad) * sizeof(float);
+}
+
+template <int DH, int NCH>
+static int launch_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
+                           const uint8_t* mask, float* attn, float* o_heads, float* rowflag, int B, int H, int nmax,
+                           float scale, cudaStream_t st) {
+  const size_t smem = attn_fwd_smem(DH, nmax);
+  FETA_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)ceil_div(nmax, kRowsPerCta), (unsigned)(B * H));
+  attn_fwd_kernel<DH, NCH><<<grid, kAttnThreads, smem, st>>>(q, k, v, sn, sb, pe, mask, attn, o_heads, rowflag, H,
+                                                             nmax, scale);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+template <int DH, int NCH>
+static int launch_attn_bwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
+                           const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o,
+                           const float* d_attn, float* dq, float* dk, float* dv, int64_t dsn, int64_t dsb, int B,
+                           int H, int nmax, float scale, cudaStream_t st) {
+  const size_t smem = attn_bwd_smem(DH, nmax);
+  FETA_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_bwd_kernel<DH, NCH><<<(unsigned)(B * H), kAttnThreads, smem, st>>>(q, k, v, sn, sb, mask, attn, rowflag, d_o,
+                                                                          d_attn, dq, dk, dv, dsn, dsb, H, nmax,
+                                                                          scale);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+
+#define FETA_ATTN_NCH(DH_, CALLNAME, ...)                                   \
+  if (nmax <= 32) return CALLNAME<DH_, 1>(__VA_ARGS__);                     \
+  if (nmax <= 64) return CALLNAME<DH_, 2>(__VA_ARGS__);                     \
+  if (nmax <= 128) return CALLNAME<DH_, 4>(__VA_ARGS__);                    \
+  if (nmax <= 256) return CALLNAME<DH_, 8>(__VA_ARGS__);                    \
+  if (nmax <= 512) return CALLNAME<DH_, 16>(__VA_ARGS__);                   \
+  return CALLNAME<DH_, 32>(__VA_ARGS__);
+
+#define FETA_ATTN_DISPATCH(CALLNAME, ...)                                   \
+  switch (dh) {                                                             \
+    case 4: { FETA_ATTN_NCH(4, CALLNAME, __VA_ARGS__) }                     \
+    case 8: { FETA_ATTN_NCH(8, CALLNAME, __VA_ARGS__) }                     \
+    case 16: { FETA_ATTN_NCH(16, CALLNAME, __VA_ARGS__) }                   \
+    case 32: { FETA_ATTN_NCH(32, CALLNAME, __VA_ARGS__) }                   \
+    case 64: { FETA_ATTN_NCH(64, CALLNAME, __VA_ARGS__) }                   \
+    default: break;                                                         \
+  }
+
+}  // namespace feta
+
+using namespace feta;
+
+extern "C" int feta_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
+                             const uint8_t* mask, float* attn, float* o_heads, float* rowflag, int B, int H, int nmax,
+                             int dh, float scale, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && dh >= 1, "attn_fwd: bad sizes");
+  if (B == 0 || nmax == 0) return FETA_OK;
+  FETA_REQUIRE(q && k && v && mask && attn && o_heads && rowflag, "attn_fwd: NULL pointer argument");
+  if (nmax > 1024 || attn_fwd_smem(dh, nmax) > 220 * 1024) {
+    set_last_error("attn_fwd: nmax=%d dh=%d exceeds the shared-memory tile (nmax <= 1024, %zu B smem)", nmax, dh,
+                   attn_fwd_smem(dh, nmax));
+    return FETA_EUNSUPPORTED;
+  }
+  FETA_ATTN_DISPATCH(launch_attn_fwd, q, k, v, sn, sb, pe, mask, attn, o_heads, rowflag, B, H, nmax, scale, st);
+  set_last_error("attn_fwd: head dim %d not in {4,8,16,32,64}", dh);
+  return FETA_EUNSUPPORTED;
+}
+
+extern "C" int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
+                             const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o_heads,
+                             const float* d_attn, float* dq, float* dk, float* dv, int64_t dsn, int64_t dsb, int B,
+                             int H, int nmax, int dh, float scale, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && dh >= 1, "attn_bwd: bad sizes");
+  if (B == 0 || nmax == 0) return FETA_OK;
+  FETA_REQUIRE(q && k && v && mask && attn && rowflag && d_o_heads && dq && dk && dv,
+               "attn_bwd: NULL pointer argument");
+  if (nmax > 1024 || attn_bwd_smem(dh, nmax) > 220 * 1024) {
+    set_last_error("attn_bwd: nmax=%d dh=%d exceeds the shared-memory tile (%zu B smem)", nmax, dh,
+                   attn_bwd_smem(dh, nmax));
+    return FETA_EUNSUPPORTED;
+  }
+  FETA_ATTN_DISPATCH(launch_attn_bwd, q, k, v, sn, sb, mask, attn, rowflag, d_o_heads, d_attn, dq, dk, dv, dsn, dsb, B,
+                     H, nmax, scale, st);
+  set_last_error("attn_bwd: head dim %d not in {4,8,16,32,64}", dh);
+  return FETA_EUNSUPPORTED;
+}

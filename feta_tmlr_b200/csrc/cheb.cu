@@ -1,0 +1,689 @@
+// A1/A3: fused ChebConvDynamic forward / backward (see include/feta_b200.h).
+//
+// Replaces ChebConvDynamic.forward (transformer/ChebNetDynamic.py:132-189): the reference
+// materialises a per-node filter [K,R,F,F] (:148-149), runs K batched 1xF.FxF bmm's and K-1 PyG
+// propagate calls (gather -> message tensor -> atomic scatter-add).  Here one launch does the
+// whole recursion: a CTA owns a *chunk* of consecutive whole graphs (block-diagonal L_hat =>
+// the chunk is closed under neighbours), keeps T_{k-1}/T_k of the chunk in shared memory,
+// one thread per row gathers its CSR neighbours with float4 loads, and the per-graph filter
+// is applied in registers as the epilogue of every order (out += T_k . Theta_k[g]).
+//
+// HBM traffic per launch = x + out + CSR + Theta (each read/written once); everything else
+// lives in shared memory / registers.
+#include "common.cuh"
+
+namespace feta {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// First row of the first graph whose start row is >= p (chunk boundaries; no search needed
+// because row_graph gives the graph of row p).
+__device__ __forceinline__ int chunk_boundary(int64_t p, int64_t R, const int32_t* __restrict__ graph_ptr,
+                                              const int32_t* __restrict__ row_graph) {
+  if (p >= R) return (int)R;
+  const int g = row_graph[p];
+  const int s = graph_ptr[g];
+  return (s == (int)p) ? (int)p : graph_ptr[g + 1];
+}
+
+// device-side plan guard (see feta_cheb_fwd in include/feta_b200.h)
+__device__ __forceinline__ bool plan_guard_ok(int32_t* meta, int64_t G, int max_nodes) {
+  if (meta == nullptr) return true;
+  const bool ok = meta[FETA_META_SORTED] == 1 && meta[FETA_META_BLOCKDIAG] == 1 &&
+                  meta[FETA_META_NUM_GRAPHS] == (int32_t)G && meta[FETA_META_MAX_NODES] <= max_nodes &&
+                  meta[FETA_META_BAD_INDEX] == 0;
+  if (!ok && threadIdx.x == 0) meta[FETA_META_GUARD] = 1;
+  return ok;
+}
+
+// coalesced copy of a [n, F] row-major global slab into shared memory with row stride LD
+template <int F>
+__device__ __forceinline__ void slab_to_smem(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  constexpr int LD = F + 4, Q = F / 4;
+  for (int i = threadIdx.x; i < n * Q; i += blockDim.x) {
+    const int row = i / Q, q = i - row * Q;
+    st4(dst + row * LD + 4 * q, ldg4(src + (size_t)i * 4));
+  }
+}
+template <int F>
+__device__ __forceinline__ void smem_to_slab(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  constexpr int LD = F + 4, Q = F / 4;
+  for (int i = threadIdx.x; i < n * Q; i += blockDim.x) {
+    const int row = i / Q, q = i - row * Q;
+    st4(dst + (size_t)i * 4, ld4(src + row * LD + 4 * q));
+  }
+}
+
+// t[F] = sum_e vals[e] * buf[colidx[e] - r0]
+template <int F>
+__device__ __forceinline__ void gather_row(float (&t)[F], const float* __restrict__ buf, int r0,
+                                           const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                                           int e0, int e1) {
+  constexpr int LD = F + 4;
+#pragma unroll
+  for (int i = 0; i < F; ++i) t[i] = 0.0f;
+  for (int e = e0; e < e1; ++e) {
+    const int c = __ldg(colidx + e) - r0;
+    const float w = __ldg(vals + e);
+    const float* row = buf + c * LD;
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      const float4 a = ld4(row + 4 * q);
+      t[4 * q + 0] = fmaf(w, a.x, t[4 * q + 0]);
+      t[4 * q + 1] = fmaf(w, a.y, t[4 * q + 1]);
+      t[4 * q + 2] = fmaf(w, a.z, t[4 * q + 2]);
+      t[4 * q + 3] = fmaf(w, a.w, t[4 * q + 3]);
+    }
+  }
+}
+
+// acc[j] += sum_i t[i] * th[i*F + j]     (th: one graph's Theta_k, row-major [F, F], global/L1)
+template <int F>
+__device__ __forceinline__ void apply_theta(float (&acc)[F], const float (&t)[F], const float* __restrict__ th) {
+#pragma unroll
+  for (int i = 0; i < F; ++i) {
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      const float4 w = ldg4(th + i * F + 4 * q);
+      acc[4 * q + 0] = fmaf(t[i], w.x, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(t[i], w.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(t[i], w.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(t[i], w.w, acc[4 * q + 3]);
+    }
+  }
+}
+
+// d[i] = sum_j dout[j] * th[i*F + j]     (transpose application for the backward)
+template <int F>
+__device__ __forceinline__ void apply_theta_t(float (&d)[F], const float (&g)[F], const float* __restrict__ th) {
+#pragma unroll
+  for (int i = 0; i < F; ++i) {
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      const float4 w = ldg4(th + i * F + 4 * q);
+      s = fmaf(g[4 * q + 0], w.x, s);
+      s = fmaf(g[4 * q + 1], w.y, s);
+      s = fmaf(g[4 * q + 2], w.z, s);
+      s = fmaf(g[4 * q + 3], w.w, s);
+    }
+    d[i] = s;
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void load_row(float (&t)[F], const float* __restrict__ row) {
+#pragma unroll
+  for (int q = 0; q < F / 4; ++q) {
+    const float4 a = ld4(row + 4 * q);
+    t[4 * q + 0] = a.x, t[4 * q + 1] = a.y, t[4 * q + 2] = a.z, t[4 * q + 3] = a.w;
+  }
+}
+template <int F>
+__device__ __forceinline__ void store_row(float* __restrict__ row, const float (&t)[F]) {
+#pragma unroll
+  for (int q = 0; q < F / 4; ++q) st4(row + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
+}
+
+template <int F>
+constexpr int fused_max_threads() {
+  return F <= 8 ? 1024 : 512;
+}
+
+// ------------------------------------------------------------------ forward -------------
+template <int F>
+__global__ void __launch_bounds__(fused_max_threads<F>()) cheb_fwd_fused_kernel(
+    const float* __restrict__ x, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+    const float* __restrict__ vals, const int32_t* __restrict__ graph_ptr, const int32_t* __restrict__ row_graph,
+    const float* __restrict__ theta, int64_t sk, int64_t sg, const float* __restrict__ bias,
+    float* __restrict__ out, int64_t R, int K, int C, int cap, int32_t* meta, int64_t G, int max_nodes) {
+  constexpr int LD = F + 4;
+  extern __shared__ float4 smem_f4[];
+  if (!plan_guard_ok(meta, G, max_nodes)) return;
+  float* buf0 = reinterpret_cast<float*>(smem_f4);
+  float* buf1 = buf0 + (size_t)cap * LD;
+
+  const int64_t p0 = (int64_t)blockIdx.x * C;
+  const int r0 = chunk_boundary(p0, R, graph_ptr, row_graph);
+  const int r1 = chunk_boundary(p0 + C, R, graph_ptr, row_graph);
+  const int n = r1 - r0;
+  if (n <= 0) return;
+
+  slab_to_smem<F>(buf0, x + (size_t)r0 * F, n);
+  __syncthreads();
+
+  const int lr = threadIdx.x;
+  const bool active = lr < n;
+  const int r = r0 + lr;
+  int e0 = 0, e1 = 0;
+  const float* th = theta;
+  float acc[F], t[F];
+#pragma unroll
+  for (int i = 0; i < F; ++i) acc[i] = 0.0f;
+  if (active) {
+    e0 = rowptr[r];
+    e1 = rowptr[r + 1];
+    th = theta + (int64_t)row_graph[r] * sg;
+    load_row<F>(t, buf0 + lr * LD);
+    apply_theta<F>(acc, t, th);  // k = 0, ChebNetDynamic.py:167
+  }
+  float* cur = buf0;
+  float* nxt = buf1;
+  for (int k = 1; k < K; ++k) {
+    if (active) {
+      gather_row<F>(t, cur, r0, colidx, vals, e0, e1);  // propagate, :171 / :178
+      if (k >= 2) {                                      // Tx_2 = 2 * Tx_2 - Tx_0, :179
+        float old[F];
+        load_row<F>(old, nxt + lr * LD);  // own row of T_{k-2}; nobody else reads it any more
+#pragma unroll
+        for (int i = 0; i < F; ++i) t[i] = fmaf(2.0f, t[i], -old[i]);
+      }
+      if (k + 1 < K) store_row<F>(nxt + lr * LD, t);
+      apply_theta<F>(acc, t, th + (int64_t)k * sk);  // :175 / :183
+    }
+    __syncthreads();
+    float* s = cur;
+    cur = nxt;
+    nxt = s;
+  }
+  // epilogue: + bias (:186-187), stage through shared memory for coalesced stores
+  if (active) {
+    if (bias != nullptr) {
+#pragma unroll
+      for (int i = 0; i < F; ++i) acc[i] += __ldg(bias + i);
+    }
+    store_row<F>(nxt + lr * LD, acc);  // nxt: last read two barriers ago
+  }
+  __syncthreads();
+  smem_to_slab<F>(out + (size_t)r0 * F, nxt, n);
+}
+
+// ------------------------------------------------------------------ backward: dx --------
+// Clenshaw-style reverse recursion: G_k = dOut.Theta_k^T + c_k L^T G_{k+1} - G_{k+2},
+// c_k = 2 (k >= 1) or 1 (k = 0); dx = G_0.  L^T comes from the SOURCE-grouped CSR.
+template <int F>
+__global__ void __launch_bounds__(fused_max_threads<F>()) cheb_bwd_dx_fused_kernel(
+    const float* __restrict__ dout, const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ colidx_t,
+    const float* __restrict__ vals_t, const int32_t* __restrict__ graph_ptr,
+    const int32_t* __restrict__ row_graph, const float* __restrict__ theta, int64_t sk, int64_t sg,
+    float* __restrict__ dx, int64_t R, int K, int C, int cap, int32_t* meta, int64_t G, int max_nodes) {
+  constexpr int LD = F + 4;
+  extern __shared__ float4 smem_f4[];
+  if (!plan_guard_ok(meta, G, max_nodes)) return;
+  float* buf0 = reinterpret_cast<float*>(smem_f4);
+  float* buf1 = buf0 + (size_t)cap * LD;
+
+  const int64_t p0 = (int64_t)blockIdx.x * C;
+  const int r0 = chunk_boundary(p0, R, graph_ptr, row_graph);
+  const int r1 = chunk_boundary(p0 + C, R, graph_ptr, row_graph);
+  const int n = r1 - r0;
+  if (n <= 0) return;
+
+  slab_to_smem<F>(buf0, dout + (size_t)r0 * F, n);
+  __syncthreads();
+  const int lr = threadIdx.x;
+  const bool active = lr < n;
+  const int r = r0 + lr;
+  int e0 = 0, e1 = 0;
+  const float* th = theta;
+  float d[F], g[F], t[F];
+  if (active) {
+    e0 = rowptr_t[r];
+    e1 = rowptr_t[r + 1];
+    th = theta + (int64_t)row_graph[r] * sg;
+    load_row<F>(d, buf0 + lr * LD);
+  }
+  __syncthreads();  // buf0 is recycled below
+  float* cur = buf0;  // holds G_{k+1}
+  float* nxt = buf1;  // holds G_{k+2}, receives G_k
+  for (int k = K - 1; k >= 0; --k) {
+    if (active) {
+      apply_theta_t<F>(g, d, th + (int64_t)k * sk);
+      if (k + 1 <= K - 1) {
+        gather_row<F>(t, cur, r0, colidx_t, vals_t, e0, e1);
+        const float c = (k == 0) ? 1.0f : 2.0f;
+#pragma unroll
+        for (int i = 0; i < F; ++i) g[i] = fmaf(c, t[i], g[i]);
+      }
+      if (k + 2 <= K - 1) {
+        load_row<F>(t, nxt + lr * LD);
+#pragma unroll
+        for (int i = 0; i < F; ++i) g[i] -= t[i];
+      }
+      store_row<F>(nxt + lr * LD, g);
+    }
+    __syncthreads();
+    float* s = cur;
+    cur = nxt;
+    nxt = s;
+  }
+  smem_to_slab<F>(dx + (size_t)r0 * F, cur, n);  // cur == G_0 after the final swap
+}
+
+// ------------------------------------------------------------------ backward: dTheta ----
+// Recomputes T_k (forward recursion) and reduces dTheta_k[g] = sum_{r in g} T_k[r]^T dOut[r]
+// inside the CTA (deterministic, no atomics: whole graphs never straddle CTAs).
+template <int F>
+__device__ __forceinline__ void dtheta_reduce(const float* __restrict__ Tk, const float* __restrict__ sD,
+                                              float4* __restrict__ partial, int lo, int hi,
+                                              float* __restrict__ dst /* [F,F] for this (k,g) */) {
+  constexpr int LD = F + 4, NG = F * F / 4, Q = F / 4;
+  const int T = blockDim.x;
+  const int S = T >= NG ? T / NG : 1;
+  for (int item = threadIdx.x; item < S * NG; item += T) {
+    const int s = item / NG, o = item - s * NG;
+    const int i = o / Q, q = o - i * Q;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int row = lo + s; row < hi; row += S) {
+      const float tv = Tk[row * LD + i];
+      const float4 dv = ld4(sD + row * LD + 4 * q);
+      a.x = fmaf(tv, dv.x, a.x), a.y = fmaf(tv, dv.y, a.y), a.z = fmaf(tv, dv.z, a.z), a.w = fmaf(tv, dv.w, a.w);
+    }
+    partial[item] = a;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < NG; o += T) {
+    float4 a = partial[o];
+    for (int s = 1; s < S; ++s) {
+      const float4 b = partial[s * NG + o];
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
+    st4(dst + 4 * o, a);
+  }
+  __syncthreads();
+}
+
+template <int F>
+__global__ void __launch_bounds__(fused_max_threads<F>()) cheb_bwd_dtheta_fused_kernel(
+    const float* __restrict__ x, const float* __restrict__ dout, const int32_t* __restrict__ rowptr,
+    const int32_t* __restrict__ colidx, const float* __restrict__ vals, const int32_t* __restrict__ graph_ptr,
+    const int32_t* __restrict__ row_graph, float* __restrict__ dtheta, int64_t sk, int64_t sg, int64_t R, int K,
+    int C, int cap, int32_t* meta, int64_t G, int max_nodes) {
+  constexpr int LD = F + 4, NG = F * F / 4;
+  extern __shared__ float4 smem_f4[];
+  if (!plan_guard_ok(meta, G, max_nodes)) return;
+  float* buf0 = reinterpret_cast<float*>(smem_f4);
+  float* buf1 = buf0 + (size_t)cap * LD;
+  float* sD = buf1 + (size_t)cap * LD;
+  float4* partial = reinterpret_cast<float4*>(sD + (size_t)cap * LD);
+
+  const int64_t p0 = (int64_t)blockIdx.x * C;
+  const int r0 = chunk_boundary(p0, R, graph_ptr, row_graph);
+  const int r1 = chunk_boundary(p0 + C, R, graph_ptr, row_graph);
+  const int n = r1 - r0;
+  if (n <= 0) return;
+  const int g_lo = row_graph[r0], g_hi = row_graph[r1 - 1] + 1;
+
+  slab_to_smem<F>(buf0, x + (size_t)r0 * F, n);
+  slab_to_smem<F>(sD, dout + (size_t)r0 * F, n);
+  __syncthreads();
+
+  const int lr = threadIdx.x;
+  const bool active = lr < n;
+  const int r = r0 + lr;
+  int e0 = 0, e1 = 0;
+  if (active) {
+    e0 = rowptr[r];
+    e1 = rowptr[r + 1];
+  }
+  float* cur = buf0;
+  float* nxt = buf1;
+  for (int k = 0; k < K; ++k) {
+    if (k >= 1) {
+      if (active) {
+        float t[F];
+        gather_row<F>(t, cur, r0, colidx, vals, e0, e1);
+        if (k >= 2) {
+          float old[F];
+          load_row<F>(old, nxt + lr * LD);
+#pragma unroll
+          for (int i = 0; i < F; ++i) t[i] = fmaf(2.0f, t[i], -old[i]);
+        }
+        store_row<F>(nxt + lr * LD, t);
+      }
+      __syncthreads();
+      float* s = cur;
+      cur = nxt;
+      nxt = s;
+    }
+    for (int g = g_lo; g < g_hi; ++g) {
+      const int lo = graph_ptr[g] - r0, hi = graph_ptr[g + 1] - r0;
+      dtheta_reduce<F>(cur, sD, partial, lo, hi, dtheta + (int64_t)k * sk + (int64_t)g * sg);
+    }
+  }
+  (void)NG;
+}
+
+// ------------------------------------------------------------------ un-fused fallback ---
+// Any F, any graph size, edges may cross graph boundaries.  One launch per Chebyshev order.
+__global__ void spmm_axpby_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                  const float* __restrict__ vals, const float* __restrict__ tin,
+                                  const float* __restrict__ tprev, float* __restrict__ tout, int64_t R, int F,
+                                  float alpha, float beta) {
+  const int64_t total = R * F;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / F;
+    const int f = (int)(idx - r * F);
+    float s = 0.0f;
+    for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) s = fmaf(vals[e], tin[(int64_t)colidx[e] * F + f], s);
+    s *= alpha;
+    if (tprev != nullptr) s -= beta * tprev[idx];
+    tout[idx] = s;
+  }
+}
+
+// out[r, j] (+)= sum_i t[r, i] * theta[g(r)][i, j]   (transpose: out[r, i] = sum_j t[r, j] theta[i, j])
+__global__ void theta_apply_kernel(const float* __restrict__ t, const float* __restrict__ theta_k, int64_t sg,
+                                   const int32_t* __restrict__ row_graph, const float* __restrict__ bias,
+                                   float* __restrict__ out, int64_t R, int64_t G, int fin, int fout,
+                                   int accumulate, int transpose) {
+  const int nout = transpose ? fin : fout;
+  const int nin = transpose ? fout : fin;
+  const int64_t total = R * nout;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / nout;
+    const int j = (int)(idx - r * nout);
+    const int g = row_graph[r];
+    if (g >= G) continue;  // more runs in `batch` than graphs in theta: caller raises on the meta words
+    const float* th = theta_k + (int64_t)g * sg;
+    float s = 0.0f;
+    if (!transpose) {
+      for (int i = 0; i < nin; ++i) s = fmaf(t[r * fin + i], th[i * fout + j], s);
+    } else {
+      for (int i = 0; i < nin; ++i) s = fmaf(t[r * fout + i], th[j * fout + i], s);
+    }
+    if (bias != nullptr) s += bias[j];
+    out[idx] = accumulate ? out[idx] + s : s;
+  }
+}
+
+__global__ void dtheta_graph_kernel(const float* __restrict__ t, const float* __restrict__ dout,
+                                    const int32_t* __restrict__ graph_ptr, float* __restrict__ dtheta_k,
+                                    int64_t sg, int fin, int fout) {
+  const int g = blockIdx.x;
+  const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+  for (int o = threadIdx.x; o < fin * fout; o += blockDim.x) {
+    const int i = o / fout, j = o - i * fout;
+    float s = 0.0f;
+    for (int r = lo; r < hi; ++r) s = fmaf(t[(int64_t)r * fin + i], dout[(int64_t)r * fout + j], s);
+    dtheta_k[(int64_t)g * sg + o] = s;
+  }
+}
+
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], y[i]);
+}
+
+// deterministic two-stage column sum: partial[b, c] then out[c]
+__global__ void colsum_partial_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ partial) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.0f;
+    for (int64_t r = blockIdx.x; r < R; r += gridDim.x) s += x[r * C + c];
+    partial[(int64_t)blockIdx.x * C + c] = s;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int b = 0; b < nblk; ++b) s += partial[(int64_t)b * C + c];
+    out[c] = s;
+  }
+}
+
+constexpr int kColsumBlocks = 256;
+
+static inline unsigned grid1d(int64_t n, int threads = 256) {
+  int64_t b = ceil_div(n > 0 ? n : 1, threads);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (unsigned)(b < cap ? b : cap);
+}
+
+struct FusedCfg {
+  bool ok;
+  int C, cap, threads;
+  size_t smem;
+};
+
+// chunk quantum C and capacity (rows a chunk can hold) for the fused kernels
+static FusedCfg fused_config(int F, int max_nodes, int nbuf, bool with_partial) {
+  FusedCfg c{false, 0, 0, 0, 0};
+  if (!(F == 4 || F == 8 || F == 16 || F == 32)) return c;
+  if (max_nodes < 1) max_nodes = 1;
+  const int maxT = F <= 8 ? 1024 : 512;
+  int C = (max_nodes + 31) / 32 * 32;
+  if (C < 64) C = 64;
+  if (C > 256) C = 256;
+  while (C > 32 && C + max_nodes - 1 > maxT) C -= 32;
+  int cap = (C + max_nodes - 1 + 31) / 32 * 32;
+  if (cap > maxT) return c;
+  size_t smem = (size_t)nbuf * cap * (F + 4) * sizeof(float);
+  if (with_partial) {
+    const int NG = F * F / 4;
+    smem += (size_t)(cap > NG ? cap : NG) * 16;
+  }
+  if (smem > 220 * 1024) return c;
+  c.ok = true, c.C = C, c.cap = cap, c.threads = cap, c.smem = smem;
+  return c;
+}
+
+template <int F>
+static int launch_fwd(const FusedCfg& cfg, const float* x, const int32_t* rowptr, const int32_t* colidx,
+                      const float* vals, const int32_t* graph_ptr, const int32_t* row_graph, const float* theta,
+                      int64_t sk, int64_t sg, const float* bias, float* out, int64_t R, int K, int32_t* meta, int64_t G,
+                      int max_nodes, cudaStream_t st) {
+  FETA_CUDA(cudaFuncSetAttribute(cheb_fwd_fused_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)cfg.smem));
+  const unsigned grid = (unsigned)ceil_div(R, cfg.C);
+  cheb_fwd_fused_kernel<F><<<grid, cfg.threads, cfg.smem, st>>>(x, rowptr, colidx, vals, graph_ptr, row_graph,
+                                                                theta, sk, sg, bias, out, R, K, cfg.C, cfg.cap, meta, G,
+                                                                max_nodes);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+template <int F>
+static int launch_bwd_dx(const FusedCfg& cfg, const float* dout, const int32_t* rowptr_t, const int32_t* colidx_t,
+                         const float* vals_t, const int32_t* graph_ptr, const int32_t* row_graph,
+                         const float* theta, int64_t sk, int64_t sg, float* dx, int64_t R, int K,
+                         int32_t* meta, int64_t G, int max_nodes, cudaStream_t st) {
+  FETA_CUDA(cudaFuncSetAttribute(cheb_bwd_dx_fused_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)cfg.smem));
+  const unsigned grid = (unsigned)ceil_div(R, cfg.C);
+  cheb_bwd_dx_fused_kernel<F><<<grid, cfg.threads, cfg.smem, st>>>(dout, rowptr_t, colidx_t, vals_t, graph_ptr,
+                                                                   row_graph, theta, sk, sg, dx, R, K, cfg.C,
+                                                                   cfg.cap, meta, G, max_nodes);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+template <int F>
+static int launch_bwd_dtheta(const FusedCfg& cfg, const float* x, const float* dout, const int32_t* rowptr,
+                             const int32_t* colidx, const float* vals, const int32_t* graph_ptr,
+                             const int32_t* row_graph, float* dtheta, int64_t sk, int64_t sg, int64_t R, int K,
+                             int32_t* meta, int64_t G, int max_nodes, cudaStream_t st) {
+  FETA_CUDA(cudaFuncSetAttribute(cheb_bwd_dtheta_fused_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)cfg.smem));
+  const unsigned grid = (unsigned)ceil_div(R, cfg.C);
+  cheb_bwd_dtheta_fused_kernel<F><<<grid, cfg.threads, cfg.smem, st>>>(x, dout, rowptr, colidx, vals, graph_ptr,
+                                                                       row_graph, dtheta, sk, sg, R, K, cfg.C,
+                                                                       cfg.cap, meta, G, max_nodes);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+
+#define FETA_DISPATCH_F(F_, ...)                            \
+  switch (F_) {                                             \
+    case 4: { constexpr int FF = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int FF = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int FF = 16; __VA_ARGS__; } break; \
+    case 32: { constexpr int FF = 32; __VA_ARGS__; } break; \
+    default: break;                                         \
+  }
+
+}  // namespace feta
+
+using namespace feta;
+
+extern "C" size_t feta_cheb_workspace_bytes(int64_t R, int fin, int fout, int K) {
+  (void)K;
+  const int fm = fin > fout ? fin : fout;
+  size_t per = align_up((size_t)(R > 0 ? R : 1) * fm * sizeof(float), 256);
+  return 4 * per + align_up((size_t)kColsumBlocks * fm * sizeof(float), 256) + 1024;
+}
+
+static int check_common(const float* x, const int32_t* rowptr, const int32_t* graph_ptr, const int32_t* row_graph,
+                        const float* theta, int64_t R, int64_t G, int K, int fin, int fout) {
+  FETA_REQUIRE(R >= 0 && G >= 1 && K >= 1 && fin >= 1 && fout >= 1, "cheb: bad sizes R=%lld G=%lld K=%d F=%d/%d",
+               (long long)R, (long long)G, K, fin, fout);
+  FETA_REQUIRE(x && rowptr && graph_ptr && row_graph && theta, "cheb: NULL pointer argument");
+  return FETA_OK;
+}
+
+extern "C" int feta_cheb_fwd(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                             const int32_t* graph_ptr, const int32_t* row_graph, int32_t* plan_meta,
+                             const float* theta, int64_t sk,
+                             int64_t sg, const float* bias, float* out, int64_t R, int64_t G, int K, int fin, int fout,
+                             int max_nodes, int block_diagonal, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (R == 0) return FETA_OK;
+  int rc = check_common(x, rowptr, graph_ptr, row_graph, theta, R, G, K, fin, fout);
+  if (rc) return rc;
+  FETA_REQUIRE(out != nullptr, "cheb_fwd: out is NULL");
+  const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)theta % 16 == 0) &&
+                       (sk % 4 == 0) && (sg % 4 == 0);
+  FusedCfg cfg = fused_config(fin, max_nodes, 2, false);
+  if (fin == fout && block_diagonal && aligned && cfg.ok) {
+    FETA_DISPATCH_F(fin, return launch_fwd<FF>(cfg, x, rowptr, colidx, vals, graph_ptr, row_graph, theta, sk, sg,
+                                               bias, out, R, K, plan_meta, G, max_nodes, st));
+  }
+  // un-fused path
+  if (workspace == nullptr || workspace_bytes < feta_cheb_workspace_bytes(R, fin, fout, K)) {
+    set_last_error("cheb_fwd: fallback path needs %zu workspace bytes, got %zu",
+                   feta_cheb_workspace_bytes(R, fin, fout, K), workspace_bytes);
+    return FETA_EWORKSPACE;
+  }
+  Arena ar(workspace, workspace_bytes);
+  float* tb[3] = {ar.take<float>(R * fin), ar.take<float>(R * fin), ar.take<float>(R * fin)};
+  const float* tcur = x;
+  const float* tprev = nullptr;
+  theta_apply_kernel<<<grid1d(R * fout), 256, 0, st>>>(x, theta, sg, row_graph, bias, out, R, G, fin, fout, 0, 0);
+  FETA_LAUNCH_CHECK();
+  for (int k = 1; k < K; ++k) {
+    float* tn = tb[k % 3];
+    spmm_axpby_kernel<<<grid1d(R * fin), 256, 0, st>>>(rowptr, colidx, vals, tcur, k >= 2 ? tprev : nullptr, tn, R,
+                                                       fin, k >= 2 ? 2.0f : 1.0f, 1.0f);
+    FETA_LAUNCH_CHECK();
+    theta_apply_kernel<<<grid1d(R * fout), 256, 0, st>>>(tn, theta + (int64_t)k * sk, sg, row_graph, nullptr, out, R,
+                                                         G, fin, fout, 1, 0);
+    FETA_LAUNCH_CHECK();
+    tprev = tcur;
+    tcur = tn;
+  }
+  return FETA_OK;
+}
+
+extern "C" int feta_cheb_bwd(const float* dout, const float* x, const int32_t* rowptr, const int32_t* colidx,
+                             const float* vals, const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t,
+                             const int32_t* graph_ptr, const int32_t* row_graph, int32_t* plan_meta,
+                             const float* theta, int64_t sk,
+                             int64_t sg, float* dx, float* dtheta, float* dbias, int64_t R, int64_t G, int K, int fin,
+                             int fout, int max_nodes, int block_diagonal, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc = check_common(x, rowptr, graph_ptr, row_graph, theta, R > 0 ? R : 0, G, K, fin, fout);
+  if (rc) return rc;
+  FETA_REQUIRE(dout != nullptr || R == 0, "cheb_bwd: dout is NULL");
+  FETA_REQUIRE(!dx || (rowptr_t && (colidx_t || R == 0)), "cheb_bwd: dx requested without transposed CSR");
+  if (workspace == nullptr || workspace_bytes < feta_cheb_workspace_bytes(R, fin, fout, K)) {
+    set_last_error("cheb_bwd: needs %zu workspace bytes, got %zu", feta_cheb_workspace_bytes(R, fin, fout, K),
+                   workspace_bytes);
+    return FETA_EWORKSPACE;
+  }
+  Arena ar(workspace, workspace_bytes);
+  const int fm = fin > fout ? fin : fout;
+  float* wb[4] = {ar.take<float>((R > 0 ? R : 1) * fm), ar.take<float>((R > 0 ? R : 1) * fm),
+                  ar.take<float>((R > 0 ? R : 1) * fm), ar.take<float>((R > 0 ? R : 1) * fm)};
+  float* partial = ar.take<float>((size_t)kColsumBlocks * fm);
+  FETA_REQUIRE(partial != nullptr, "cheb_bwd: workspace carve failed");
+
+  if (dbias != nullptr) {
+    const int nblk = (int)(R < kColsumBlocks ? (R > 0 ? R : 1) : kColsumBlocks);
+    colsum_partial_kernel<<<nblk, 64, 0, st>>>(dout, R, fout, partial);
+    FETA_LAUNCH_CHECK();
+    colsum_final_kernel<<<1, 64, 0, st>>>(partial, R > 0 ? nblk : 0, fout, dbias);
+    FETA_LAUNCH_CHECK();
+  }
+  if (R == 0) {
+    return FETA_OK;
+  }
+  const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)dout % 16 == 0) && ((uintptr_t)theta % 16 == 0) &&
+                       (sk % 4 == 0) && (sg % 4 == 0) && (!dx || (uintptr_t)dx % 16 == 0) &&
+                       (!dtheta || (uintptr_t)dtheta % 16 == 0);
+  const bool fusable = fin == fout && block_diagonal && aligned;
+  if (dx != nullptr) {
+    FusedCfg cfg = fused_config(fin, max_nodes, 2, false);
+    bool done = false;
+    if (fusable && cfg.ok) {
+      FETA_DISPATCH_F(fin, {
+        rc = launch_bwd_dx<FF>(cfg, dout, rowptr_t, colidx_t, vals_t, graph_ptr, row_graph, theta, sk, sg, dx, R, K,
+                               plan_meta, G, max_nodes, st);
+        done = true;
+      });
+      if (rc) return rc;
+    }
+    if (!done) {
+      // G_k = D_k + c_k L^T G_{k+1} - G_{k+2};  buffers rotate over wb[0..2], D_k in wb[3]
+      float* gk1 = nullptr;  // G_{k+1}
+      float* gk2 = nullptr;  // G_{k+2}
+      for (int k = K - 1; k >= 0; --k) {
+        float* gk = (k == 0) ? dx : wb[k % 3];
+        theta_apply_kernel<<<grid1d(R * fin), 256, 0, st>>>(dout, theta + (int64_t)k * sk, sg, row_graph, nullptr, gk,
+                                                            R, G, fin, fout, 0, 1);
+        FETA_LAUNCH_CHECK();
+        if (gk1 != nullptr) {
+          spmm_axpby_kernel<<<grid1d(R * fin), 256, 0, st>>>(rowptr_t, colidx_t, vals_t, gk1, gk2, wb[3], R, fin,
+                                                             k == 0 ? 1.0f : 2.0f, 1.0f);
+          FETA_LAUNCH_CHECK();
+          axpy_kernel<<<grid1d(R * fin), 256, 0, st>>>(gk, wb[3], 1.0f, R * fin);
+          FETA_LAUNCH_CHECK();
+        }
+        gk2 = gk1;
+        gk1 = gk;
+      }
+    }
+  }
+  if (dtheta != nullptr) {
+    FusedCfg cfg = fused_config(fin, max_nodes, 3, true);
+    bool done = false;
+    if (fusable && cfg.ok) {
+      FETA_DISPATCH_F(fin, {
+        rc = launch_bwd_dtheta<FF>(cfg, x, dout, rowptr, colidx, vals, graph_ptr, row_graph, dtheta, sk, sg, R, K,
+                                   plan_meta, G, max_nodes, st);
+        done = true;
+      });
+      if (rc) return rc;
+    }
+    if (!done) {
+      const float* tcur = x;
+      const float* tprev = nullptr;
+      for (int k = 0; k < K; ++k) {
+        if (k >= 1) {
+          float* tn = wb[k % 3];
+          spmm_axpby_kernel<<<grid1d(R * fin), 256, 0, st>>>(rowptr, colidx, vals, tcur, k >= 2 ? tprev : nullptr, tn,
+                                                             R, fin, k >= 2 ? 2.0f : 1.0f, 1.0f);
+          FETA_LAUNCH_CHECK();
+          tprev = tcur;
+          tcur = tn;
+        }
+        dtheta_graph_kernel<<<(unsigned)G, 256, 0, st>>>(tcur, dout, graph_ptr, dtheta + (int64_t)k * sk, sg, fin,
+                                                         fout);
+        FETA_LAUNCH_CHECK();
+      }
+    }
+  }
+  return FETA_OK;
+}

@@ -1,0 +1,144 @@
+// A7: GPU batch builder (see include/feta_b200.h).
+//
+// Replaces the per-graph / per-node Python loops of GraphDataset_{v2,sbm,ogb}.collate_fn
+// (transformer/data.py:161-225, :277-344, :394-460) for a dataset that has been packed onto the
+// device once: node features, local edge lists, dense per-graph PE blocks and degree vectors
+// concatenated with prefix-sum pointers.  Pure integer/index work + copies; outputs are
+// bit-identical to the reference's host collate.
+#include "common.cuh"
+
+namespace feta {
+
+constexpr int kColThreads = 256;
+
+static inline unsigned col_grid(int64_t n) {
+  int64_t b = ceil_div(n > 0 ? n : 1, kColThreads);
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  return (unsigned)(b < cap ? b : cap);
+}
+
+// largest b with ptr[b] <= i   (ptr is [B+1], non-decreasing, ptr[B] > i)
+__device__ __forceinline__ int owner_of(const int64_t* __restrict__ ptr, int B, int64_t i) {
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (ptr[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kColThreads) collate_nodes_kernel(const int64_t* __restrict__ out_node_ptr,
+                                                                   int64_t* __restrict__ batch_indices,
+                                                                   int64_t* __restrict__ feature_indices, int B,
+                                                                   int64_t N) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = owner_of(out_node_ptr, B, i);
+    batch_indices[i] = b;                        // data.py:220
+    feature_indices[2 * i] = b;                  // data.py:218
+    feature_indices[2 * i + 1] = i - out_node_ptr[b];
+  }
+}
+
+__global__ void __launch_bounds__(kColThreads) collate_mask_kernel(const int64_t* __restrict__ out_node_ptr,
+                                                                  uint8_t* __restrict__ mask, int B, int nmax) {
+  const int64_t total = (int64_t)B * nmax;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / nmax), n = (int)(idx - (int64_t)b * nmax);
+    mask[idx] = n >= (out_node_ptr[b + 1] - out_node_ptr[b]);  // data.py:210  mask[i, g_len:] = True
+  }
+}
+
+__global__ void __launch_bounds__(kColThreads) collate_edges_kernel(
+    const int64_t* __restrict__ graph_ids, const int64_t* __restrict__ ds_edge_ptr,
+    const int64_t* __restrict__ ds_edge_index, int64_t ds_E, const int64_t* __restrict__ out_node_ptr,
+    const int64_t* __restrict__ out_edge_ptr, int64_t* __restrict__ edge_indices, int B, int64_t E) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = owner_of(out_edge_ptr, B, e);
+    const int64_t src = ds_edge_ptr[graph_ids[b]] + (e - out_edge_ptr[b]);
+    const int64_t off = out_node_ptr[b];         // data.py:219  g.edge_index + node_offset
+    edge_indices[e] = ds_edge_index[src] + off;
+    edge_indices[E + e] = ds_edge_index[ds_E + src] + off;
+  }
+}
+
+__global__ void __launch_bounds__(kColThreads) collate_pad_rows_kernel(const int64_t* __restrict__ graph_ids,
+                                                                      const int64_t* __restrict__ ds_node_ptr,
+                                                                      const float* __restrict__ src,
+                                                                      float* __restrict__ dst, int B, int nmax, int C) {
+  const int64_t total = (int64_t)B * nmax * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t bn = idx / C;
+    const int b = (int)(bn / nmax), n = (int)(bn - (int64_t)b * nmax);
+    const int64_t gid = graph_ids[b];
+    const int64_t lo = ds_node_ptr[gid], len = ds_node_ptr[gid + 1] - lo;
+    dst[idx] = n < len ? src[(lo + n) * C + c] : 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(kColThreads) collate_pad_pe_kernel(const int64_t* __restrict__ graph_ids,
+                                                                    const int64_t* __restrict__ ds_node_ptr,
+                                                                    const int64_t* __restrict__ ds_pe_ptr,
+                                                                    const float* __restrict__ pe_src,
+                                                                    float* __restrict__ pe_dst, int B, int nmax) {
+  const int64_t total = (int64_t)B * nmax * nmax;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % nmax);
+    const int64_t bi = idx / nmax;
+    const int b = (int)(bi / nmax), i = (int)(bi - (int64_t)b * nmax);
+    const int64_t gid = graph_ids[b];
+    const int64_t len = ds_node_ptr[gid + 1] - ds_node_ptr[gid];
+    pe_dst[idx] = (i < len && j < len) ? pe_src[ds_pe_ptr[gid] + (int64_t)i * len + j] : 0.0f;
+  }
+}
+
+}  // namespace feta
+
+using namespace feta;
+
+extern "C" int feta_collate_indices(const int64_t* graph_ids, const int64_t* ds_node_ptr, const int64_t* ds_edge_ptr,
+                                    const int64_t* ds_edge_index, int64_t ds_E, const int64_t* out_node_ptr,
+                                    const int64_t* out_edge_ptr, uint8_t* mask, int64_t* edge_indices,
+                                    int64_t* batch_indices, int64_t* feature_indices, int B, int nmax, int64_t N,
+                                    int64_t E, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  (void)ds_node_ptr;
+  FETA_REQUIRE(B >= 1 && nmax >= 1 && N >= 0 && E >= 0, "collate_indices: bad sizes");
+  FETA_REQUIRE(graph_ids && ds_edge_ptr && out_node_ptr && out_edge_ptr && mask, "collate_indices: NULL pointer");
+  collate_mask_kernel<<<col_grid((int64_t)B * nmax), kColThreads, 0, st>>>(out_node_ptr, mask, B, nmax);
+  FETA_LAUNCH_CHECK();
+  if (N > 0) {
+    FETA_REQUIRE(batch_indices && feature_indices, "collate_indices: NULL node outputs");
+    collate_nodes_kernel<<<col_grid(N), kColThreads, 0, st>>>(out_node_ptr, batch_indices, feature_indices, B, N);
+    FETA_LAUNCH_CHECK();
+  }
+  if (E > 0) {
+    FETA_REQUIRE(edge_indices && ds_edge_index, "collate_indices: NULL edge pointers");
+    collate_edges_kernel<<<col_grid(E), kColThreads, 0, st>>>(graph_ids, ds_edge_ptr, ds_edge_index, ds_E,
+                                                              out_node_ptr, out_edge_ptr, edge_indices, B, E);
+    FETA_LAUNCH_CHECK();
+  }
+  return FETA_OK;
+}
+
+extern "C" int feta_collate_pad_rows(const int64_t* graph_ids, const int64_t* ds_node_ptr, const float* src, float* dst,
+                                     int B, int nmax, int C, void* stream_) {
+  FETA_REQUIRE(graph_ids && ds_node_ptr && src && dst && B >= 1 && nmax >= 1 && C >= 1, "collate_pad_rows: bad argument");
+  collate_pad_rows_kernel<<<col_grid((int64_t)B * nmax * C), kColThreads, 0, (cudaStream_t)stream_>>>(
+      graph_ids, ds_node_ptr, src, dst, B, nmax, C);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+
+extern "C" int feta_collate_pad_pe(const int64_t* graph_ids, const int64_t* ds_node_ptr, const int64_t* ds_pe_ptr,
+                                   const float* pe_src, float* pe_dst, int B, int nmax, void* stream_) {
+  FETA_REQUIRE(graph_ids && ds_node_ptr && ds_pe_ptr && pe_src && pe_dst && B >= 1 && nmax >= 1,
+               "collate_pad_pe: bad argument");
+  collate_pad_pe_kernel<<<col_grid((int64_t)B * nmax * nmax), kColThreads, 0, (cudaStream_t)stream_>>>(
+      graph_ids, ds_node_ptr, ds_pe_ptr, pe_src, pe_dst, B, nmax);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}

@@ -1,0 +1,106 @@
+"""Drop-in ``DiffTransformerEncoderLayer`` -- the kernel-biased attention layer.
+
+The reference imports this class from ``transformer/layers.py`` (transformer/models.py:4) but its
+source is absent from the tree, so the contract is the call site
+(models.py:166-167, :92-93, :505-506) plus the upstream GraphiT semantics the reference credits
+(README.md:129).  Parameter names follow ``nn.TransformerEncoderLayer`` so reference checkpoints
+load: ``self_attn.in_proj_weight``, ``self_attn.out_proj.weight``, ``linear1/2``, ``norm1/2``.
+
+The attention core -- S = scale*QK^T, key-padding mask, exp(S - rowmax) * pe, renormalise with a
+1e-6 clamp, O = P V, per head -- is ONE fused sm_100a kernel (csrc/attention.cu) that also emits
+the per-head attention matrix and per-head outputs the FeTA encoder consumes.  Projections, FFN
+and norms are plain library GEMMs / PyTorch.
+"""
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class DiffMultiheadAttention(nn.Module):
+    def __init__(self, embed_dim, num_heads, dropout=0.0, bias=False, share_qk=False):
+        super().__init__()
+        if embed_dim % num_heads != 0:
+            raise ValueError("embed_dim must be divisible by num_heads")
+        self.embed_dim, self.num_heads = embed_dim, num_heads
+        self.head_dim = embed_dim // num_heads
+        self.dropout = dropout
+        self.share_qk = share_qk
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        if bias:
+            self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        else:
+            self.register_parameter('in_proj_bias', None)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        if bias:
+            nn.init.constant_(self.out_proj.bias, 0.0)
+
+    def forward(self, src, pe=None, key_padding_mask=None):
+        """src [Nmax, B, d] -> (out [Nmax, B, d], attn [B, H, Nmax, Nmax], heads [B, Nmax, H, dh])."""
+        if self.dropout > 0.0 and self.training:
+            raise NotImplementedError("DiffTransformerEncoderLayer(b200): attention-weight dropout > 0 is "
+                                      "not implemented in the fused kernel (all reference drivers "
+                                      "default to --dropout 0.0)")
+        N, B, E = src.shape
+        qkv = F.linear(src, self.in_proj_weight, self.in_proj_bias)          # library GEMM
+        attn, heads = ops.diff_attention(qkv, pe, key_padding_mask, self.num_heads,
+                                         float(self.head_dim) ** -0.5, self.share_qk)
+        o = heads.view(B, N, E).transpose(0, 1)                              # concat heads, seq-first
+        return self.out_proj(o), attn, heads
+
+
+class DiffTransformerEncoderLayer(nn.Module):
+    """ctor contract models.py:505-506: ``(d_model, nb_heads, dim_feedforward, dropout, batch_norm=)``;
+    call contract models.py:166-167 / :92-93."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu",
+                 batch_norm=False, attn_bias=False, share_qk=False):
+        super().__init__()
+        self.self_attn = DiffMultiheadAttention(d_model, nhead, dropout=dropout, bias=attn_bias,
+                                                share_qk=share_qk)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.batch_norm = batch_norm
+        if batch_norm:
+            self.norm1 = nn.BatchNorm1d(d_model)
+            self.norm2 = nn.BatchNorm1d(d_model)
+        else:
+            self.norm1 = nn.LayerNorm(d_model)
+            self.norm2 = nn.LayerNorm(d_model)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        if activation != "relu":
+            raise NotImplementedError("only relu")
+        self.scaling = None
+
+    def forward(self, src, pe=None, degree=None, src_mask=None, src_key_padding_mask=None,
+                need_heads=False):
+        if src_mask is not None:
+            raise NotImplementedError("src_mask (attn_mask) is never passed by the reference "
+                                      "(models.py:166) and is not implemented")
+        src2, attn, heads = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask)
+        if degree is not None:
+            src2 = degree.transpose(0, 1).contiguous().unsqueeze(-1) * src2
+        else:
+            if pe is None:
+                raise ValueError("DiffTransformerEncoderLayer needs `degree` or `pe`")
+            if self.scaling is None:
+                self.scaling = 1. / pe.diagonal(dim1=1, dim2=2).max().item()
+            src2 = (self.scaling * pe.diagonal(dim1=1, dim2=2)).transpose(0, 1) \
+                .contiguous().unsqueeze(-1) * src2
+        src = src + self.dropout1(src2)
+        if self.batch_norm:
+            bsz = src.shape[1]
+            src = src.reshape(-1, src.shape[-1])
+        src = self.norm1(src)
+        src2 = self.linear2(self.dropout(F.relu(self.linear1(src))))
+        src = src + self.dropout2(src2)
+        src = self.norm2(src)
+        if self.batch_norm:
+            src = src.view(-1, bsz, src.shape[-1])
+        if need_heads:
+            return src, attn, heads
+        return src, attn

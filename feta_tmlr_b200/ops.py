@@ -1,0 +1,520 @@
+"""PyTorch-facing operators over the C ABI of libfeta_b200.so.
+
+PyTorch owns memory, streams and autograd bookkeeping; every computation is a call through
+``include/feta_b200.h`` with raw device pointers on the current CUDA stream.  There is no CPU
+path: CPU tensors raise.  Reference call sites are cited per op.
+"""
+import torch
+
+from . import _lib
+from ._lib import check
+
+META_NNZ, META_NUM_GRAPHS, META_SORTED, META_BLOCKDIAG, META_MAX_NODES, META_MAX_DEG, \
+    META_BAD_INDEX, META_GUARD, META_WORDS = 0, 1, 2, 3, 4, 5, 6, 7, 8
+
+_DT = {torch.int64: 0, torch.int32: 1, torch.float32: 2, torch.float64: 3}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("feta_tmlr_b200 ops run on CUDA tensors only (sm_100a); there is no "
+                               "CPU fallback -- got a %s tensor" % t.device)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError("feta_tmlr_b200 kernels are fp32; got %s" % t.dtype)
+    return t.contiguous()
+
+
+# =====================================================================================
+# A2: Laplacian CSR plan
+# =====================================================================================
+class ChebPlan(object):
+    """Device-resident CSR of L_hat (+ its transpose) and the graph segmentation of one
+    mini-batch -- what ``ChebConvDynamic.__norm__`` (ChebNetDynamic.py:108-130) and the
+    ``torch.unique`` of :148 recompute on every call in the reference."""
+
+    __slots__ = ("rowptr", "colidx", "vals", "rowptr_t", "colidx_t", "vals_t", "graph_ptr",
+                 "row_graph", "meta", "num_rows", "num_edges", "num_graphs", "max_nodes",
+                 "block_diagonal", "validated", "_keep")
+
+    def meta_host(self):
+        """Synchronises; returns the 8 meta words as a python list."""
+        return self.meta.cpu().tolist()
+
+    def validate(self):
+        """Synchronising check of the device-side flags; raises like the reference would
+        (or where the reference would silently mis-assign filters)."""
+        m = self.meta_host()
+        if m[META_BAD_INDEX]:
+            raise IndexError("ChebConvDynamic: edge_index holds a node id outside [0, %d)" % self.num_rows)
+        if self.num_rows > 0 and m[META_NUM_GRAPHS] != self.num_graphs:
+            raise RuntimeError(
+                "ChebConvDynamic: `batch` holds %d graphs but filter_coeff has %d "
+                "(repeat_interleave size mismatch, ChebNetDynamic.py:149)" % (m[META_NUM_GRAPHS], self.num_graphs))
+        if not m[META_SORTED]:
+            raise ValueError("ChebConvDynamic: `batch` must be sorted (nodes of a graph contiguous)")
+        if m[META_GUARD]:
+            raise RuntimeError("ChebConvDynamic: a fused kernel refused to run because the host-side "
+                               "plan hints (max_nodes=%d, block_diagonal) did not hold: meta=%s"
+                               % (self.max_nodes, m))
+        self.validated = True
+        return m
+
+
+def build_cheb_plan(edge_index, batch, num_rows, num_graphs, lambda_max=2.0, hints=None):
+    """Build the plan on the current stream.
+
+    ``hints`` -- optional dict ``{'max_nodes': int, 'block_diagonal': bool}`` supplied by a caller
+    that already knows them on the host (e.g. the padded width Nmax of the mini-batch).  With
+    hints no device->host synchronisation happens; the fused kernels verify the hints on the
+    device (FETA_META_GUARD).  Without hints the meta words are read back once (one sync),
+    which is still one sync fewer than the reference's ``.cpu()`` at models.py:246.
+    """
+    _need_cuda(edge_index, batch)
+    lib = _lib.load()
+    dev = edge_index.device
+    if edge_index.dtype != torch.int64:
+        edge_index = edge_index.long()
+    edge_index = edge_index.contiguous()
+    E = int(edge_index.shape[1])
+    R, G = int(num_rows), int(num_graphs)
+    if batch is not None:
+        if batch.dtype not in _DT:
+            raise TypeError("batch dtype %s not supported" % batch.dtype)
+        batch = batch.contiguous()
+        if batch.numel() != R:
+            raise ValueError("batch has %d entries for %d rows" % (batch.numel(), R))
+    p = ChebPlan()
+    i32 = dict(dtype=torch.int32, device=dev)
+    p.rowptr = torch.empty(R + 1, **i32)
+    p.rowptr_t = torch.empty(R + 1, **i32)
+    p.colidx = torch.empty(max(E, 1), **i32)
+    p.colidx_t = torch.empty(max(E, 1), **i32)
+    p.vals = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+    p.vals_t = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+    p.graph_ptr = torch.empty(G + 1, **i32)
+    p.row_graph = torch.empty(max(R, 1), **i32)
+    p.meta = torch.empty(META_WORDS, **i32)
+    ws_bytes = lib.feta_cheb_plan_workspace_bytes(R, E)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.feta_cheb_plan_build(
+        _ptr(edge_index), E, _ptr(batch), _DT[batch.dtype] if batch is not None else 0, R, G,
+        float(lambda_max), _ptr(p.rowptr), _ptr(p.colidx), _ptr(p.vals), _ptr(p.rowptr_t),
+        _ptr(p.colidx_t), _ptr(p.vals_t), _ptr(p.graph_ptr), _ptr(p.row_graph), _ptr(p.meta),
+        _ptr(ws), ws_bytes, _stream()), "feta_cheb_plan_build")
+    p.num_rows, p.num_edges, p.num_graphs = R, E, G
+    p._keep = None
+    p.validated = False
+    if hints is not None:
+        p.max_nodes = int(hints.get("max_nodes", 0))
+        p.block_diagonal = bool(hints.get("block_diagonal", True))
+    else:
+        p.max_nodes, p.block_diagonal = 0, True
+        m = p.validate()
+        p.max_nodes = int(m[META_MAX_NODES])
+        p.block_diagonal = bool(m[META_BLOCKDIAG])
+    return p
+
+
+# =====================================================================================
+# A1/A3: fused Chebyshev filter
+# =====================================================================================
+def _theta_layout(theta):
+    """theta [K, G, Fin, Fout] with a contiguous inner [Fin, Fout] block -> (tensor, sk, sg)."""
+    K, G, fi, fo = theta.shape
+    ok = theta.stride(3) == 1 and theta.stride(2) == fo and theta.stride(0) % 4 == 0 \
+        and theta.stride(1) % 4 == 0 and theta.data_ptr() % 16 == 0
+    if G == 1 and ok:
+        pass
+    if not ok:
+        theta = theta.contiguous()
+    return theta, theta.stride(0), theta.stride(1)
+
+
+class ChebFilterFn(torch.autograd.Function):
+    """out = sum_k T_k(x) . theta[k, g(row)] + bias   (ChebNetDynamic.py:162-187)."""
+
+    @staticmethod
+    def forward(ctx, x, theta, bias, plan):
+        _need_cuda(x, theta, bias)
+        lib = _lib.load()
+        x = _f32c(x)
+        if theta.dtype != torch.float32:
+            raise TypeError("filter_coeff must be fp32")
+        theta, sk, sg = _theta_layout(theta)
+        K, G, fin, fout = theta.shape
+        R = x.shape[0]
+        if x.shape[1] != fin:
+            raise ValueError("x has %d channels, filter expects %d" % (x.shape[1], fin))
+        if G != plan.num_graphs or R != plan.num_rows:
+            raise ValueError("plan was built for R=%d G=%d, got R=%d G=%d"
+                             % (plan.num_rows, plan.num_graphs, R, G))
+        out = torch.empty((R, fout), dtype=torch.float32, device=x.device)
+        ws_bytes = lib.feta_cheb_workspace_bytes(R, fin, fout, K)
+        fused = fin == fout and fin in (4, 8, 16, 32) and plan.block_diagonal
+        ws = None if fused else torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        biasc = None if bias is None else _f32c(bias)
+        rc = lib.feta_cheb_fwd(_ptr(x), _ptr(plan.rowptr), _ptr(plan.colidx), _ptr(plan.vals),
+                               _ptr(plan.graph_ptr), _ptr(plan.row_graph), _ptr(plan.meta), _ptr(theta),
+                               sk, sg, _ptr(biasc), _ptr(out), R, G, K, fin, fout, plan.max_nodes,
+                               int(plan.block_diagonal), _ptr(ws), ws_bytes if ws is not None else 0,
+                               _stream())
+        if rc == -3 and ws is None:     # graph too large for the fused tile: un-fused path
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            rc = lib.feta_cheb_fwd(_ptr(x), _ptr(plan.rowptr), _ptr(plan.colidx), _ptr(plan.vals),
+                                   _ptr(plan.graph_ptr), _ptr(plan.row_graph), _ptr(plan.meta),
+                                   _ptr(theta), sk, sg, _ptr(biasc), _ptr(out), R, G, K, fin, fout,
+                                   plan.max_nodes, int(plan.block_diagonal), _ptr(ws), ws_bytes, _stream())
+        check(rc, "feta_cheb_fwd")
+        ctx.save_for_backward(x, theta)
+        ctx.plan = plan
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, theta = ctx.saved_tensors
+        plan = ctx.plan
+        K, G, fin, fout = theta.shape
+        R = x.shape[0]
+        dout = _f32c(dout)
+        need_x, need_t, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], \
+            ctx.needs_input_grad[2] and ctx.has_bias
+        dx = torch.empty_like(x) if need_x else None
+        dtheta = torch.empty_strided(theta.shape, theta.stride(), dtype=torch.float32,
+                                     device=x.device) if need_t else None
+        dbias = torch.empty(fout, dtype=torch.float32, device=x.device) if need_b else None
+        ws_bytes = lib.feta_cheb_workspace_bytes(R, fin, fout, K)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        check(lib.feta_cheb_bwd(_ptr(dout), _ptr(x), _ptr(plan.rowptr), _ptr(plan.colidx), _ptr(plan.vals),
+                                _ptr(plan.rowptr_t), _ptr(plan.colidx_t), _ptr(plan.vals_t),
+                                _ptr(plan.graph_ptr), _ptr(plan.row_graph), _ptr(plan.meta), _ptr(theta),
+                                theta.stride(0), theta.stride(1), _ptr(dx), _ptr(dtheta), _ptr(dbias), R, G,
+                                K, fin, fout, plan.max_nodes, int(plan.block_diagonal), _ptr(ws), ws_bytes,
+                                _stream()), "feta_cheb_bwd")
+        return dx, dtheta, dbias, None
+
+
+def cheb_filter(x, theta, bias, plan):
+    return ChebFilterFn.apply(x, theta, bias, plan)
+
+
+# =====================================================================================
+# A6: kernel-biased attention core
+# =====================================================================================
+def _mask_u8(mask, B, nmax, device):
+    if mask is None:
+        return torch.zeros((B, nmax), dtype=torch.uint8, device=device)
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    return (mask != 0).to(torch.uint8).contiguous()
+
+
+class DiffAttentionFn(torch.autograd.Function):
+    """(attn [B,H,N,N], o_heads [B,N,H,dh]) = kernel-biased attention of qkv [N,B,3d].
+
+    The attention core of the layer models.py:166-167 calls."""
+
+    @staticmethod
+    def forward(ctx, qkv, pe, mask_u8, num_heads, scale, share_qk):
+        _need_cuda(qkv, pe, mask_u8)
+        lib = _lib.load()
+        qkv = _f32c(qkv)
+        N, B, d3 = qkv.shape
+        d = d3 // 3
+        H = num_heads
+        dh = d // H
+        pec = None if pe is None else _f32c(pe)
+        if pec is not None and tuple(pec.shape) != (B, N, N):
+            raise ValueError("pe must be [B, Nmax, Nmax] = %s, got %s" % ((B, N, N), tuple(pec.shape)))
+        attn = torch.empty((B, H, N, N), dtype=torch.float32, device=qkv.device)
+        o_heads = torch.empty((B, N, H, dh), dtype=torch.float32, device=qkv.device)
+        rowflag = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
+        base = qkv.data_ptr()
+        qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
+        check(lib.feta_attn_fwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(attn), _ptr(o_heads),
+                                _ptr(rowflag), B, H, N, dh, float(scale), _stream()), "feta_attn_fwd")
+        ctx.save_for_backward(qkv, mask_u8, attn, rowflag)
+        ctx.cfg = (H, float(scale), bool(share_qk))
+        ctx.mark_non_differentiable(rowflag)
+        return attn, o_heads, rowflag
+
+    @staticmethod
+    def backward(ctx, d_attn, d_o_heads, _unused):
+        lib = _lib.load()
+        qkv, mask_u8, attn, rowflag = ctx.saved_tensors
+        H, scale, share_qk = ctx.cfg
+        N, B, d3 = qkv.shape
+        d = d3 // 3
+        dh = d // H
+        if d_o_heads is None:
+            d_o_heads = torch.zeros((B, N, H, dh), dtype=torch.float32, device=qkv.device)
+        d_o_heads = _f32c(d_o_heads)
+        d_attn_c = None if d_attn is None else _f32c(d_attn)
+        dqkv = torch.empty_like(qkv)
+        base = qkv.data_ptr()
+        qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
+        db = dqkv.data_ptr()
+        check(lib.feta_attn_bwd(qp, kp, vp, B * d3, d3, _ptr(mask_u8), _ptr(attn), _ptr(rowflag),
+                                _ptr(d_o_heads), _ptr(d_attn_c), db, db + d * 4, db + 2 * d * 4, B * d3, d3,
+                                B, H, N, dh, scale, _stream()), "feta_attn_bwd")
+        if share_qk:
+            dqkv[..., :d] += dqkv[..., d:2 * d]
+            dqkv[..., d:2 * d] = 0
+        return dqkv, None, None, None, None, None
+
+
+def diff_attention(qkv, pe, key_padding_mask, num_heads, scale, share_qk=False):
+    N, B, _ = qkv.shape
+    mask_u8 = _mask_u8(key_padding_mask, B, N, qkv.device)
+    attn, o_heads, _ = DiffAttentionFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk)
+    return attn, o_heads
+
+
+# =====================================================================================
+# A4: filter-coefficient path
+# =====================================================================================
+def coeff_scalar(attn, key_padding_mask, node_ptr, num_nodes):
+    """s [H*N]: the per-node scalar the all-ones GCN of models.py:280-282 reduces to.
+    Not differentiable (the reference detaches the attention, models.py:282)."""
+    _need_cuda(attn, node_ptr)
+    lib = _lib.load()
+    attn = _f32c(attn.detach())
+    B, H, nmax, _ = attn.shape
+    mask_u8 = _mask_u8(key_padding_mask, B, nmax, attn.device)
+    s = torch.empty(H * int(num_nodes), dtype=torch.float32, device=attn.device)
+    check(lib.feta_coeff_scalar(_ptr(attn), _ptr(mask_u8), _ptr(node_ptr), _ptr(s), B, H, nmax,
+                                int(num_nodes), _stream()), "feta_coeff_scalar")
+    return s
+
+
+_POOL_BWD_BLOCKS = 148
+
+
+class CoeffPoolFn(torch.autograd.Function):
+    """pooled[g] = mean_{j in g} tanh(s_j * wbar + gbias)   (models.py:282-283 with x == 1)."""
+
+    @staticmethod
+    def forward(ctx, s, graph_ptr, wbar, gbias):
+        _need_cuda(s, graph_ptr, wbar, gbias)
+        lib = _lib.load()
+        s, wbar, gbias = _f32c(s), _f32c(wbar), _f32c(gbias)
+        G = graph_ptr.numel() - 1
+        C = wbar.numel()
+        pooled = torch.empty((G, C), dtype=torch.float32, device=s.device)
+        check(lib.feta_coeff_pool_fwd(_ptr(s), _ptr(graph_ptr), _ptr(wbar), _ptr(gbias), _ptr(pooled), G, C,
+                                      _stream()), "feta_coeff_pool_fwd")
+        ctx.save_for_backward(s, graph_ptr, wbar, gbias)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, d_pooled):
+        lib = _lib.load()
+        s, graph_ptr, wbar, gbias = ctx.saved_tensors
+        G = graph_ptr.numel() - 1
+        C = wbar.numel()
+        d_pooled = _f32c(d_pooled)
+        nblk = max(1, min(_POOL_BWD_BLOCKS, G))
+        partial = torch.empty((nblk, 2, C), dtype=torch.float32, device=s.device)
+        d_w = torch.empty(C, dtype=torch.float32, device=s.device)
+        d_b = torch.empty(C, dtype=torch.float32, device=s.device)
+        check(lib.feta_coeff_pool_bwd(_ptr(s), _ptr(graph_ptr), _ptr(wbar), _ptr(gbias), _ptr(d_pooled),
+                                      _ptr(d_w), _ptr(d_b), _ptr(partial), nblk, G, C, _stream()),
+              "feta_coeff_pool_bwd")
+        return None, None, d_w, d_b
+
+
+def coeff_pool(s, graph_ptr, wbar, gbias):
+    return CoeffPoolFn.apply(s, graph_ptr, wbar, gbias)
+
+
+# =====================================================================================
+# A5: pack / unpack / pool
+# =====================================================================================
+def _fi64(feature_indices):
+    if feature_indices.dtype != torch.int64:
+        feature_indices = feature_indices.long()
+    return feature_indices.contiguous()
+
+
+class PackHeadsFn(torch.autograd.Function):
+    """x[h*N + i] = o_heads[fi[i,0], fi[i,1], h]   (models.py:177-185 + :347)."""
+
+    @staticmethod
+    def forward(ctx, o_heads, fi):
+        _need_cuda(o_heads, fi)
+        lib = _lib.load()
+        o_heads = _f32c(o_heads)
+        B, nmax, H, dh = o_heads.shape
+        N = fi.shape[0]
+        x = torch.empty((H * N, dh), dtype=torch.float32, device=o_heads.device)
+        check(lib.feta_pack_heads(_ptr(o_heads), _ptr(fi), _ptr(x), N, B, nmax, H, dh, _stream()),
+              "feta_pack_heads")
+        ctx.save_for_backward(fi)
+        ctx.shape = (B, nmax, H, dh)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        lib = _lib.load()
+        (fi,) = ctx.saved_tensors
+        B, nmax, H, dh = ctx.shape
+        dx = _f32c(dx)
+        d_o = torch.empty(ctx.shape, dtype=torch.float32, device=dx.device)
+        check(lib.feta_pack_heads_bwd(_ptr(dx), _ptr(fi), _ptr(d_o), fi.shape[0], B, nmax, H, dh, _stream()),
+              "feta_pack_heads_bwd")
+        return d_o, None
+
+
+class UnpackHeadsFn(torch.autograd.Function):
+    """out[fi[i,1], fi[i,0], h*dh:(h+1)*dh] = y[h*N + i], zeros elsewhere (models.py:200-202)."""
+
+    @staticmethod
+    def forward(ctx, y, fi, B, nmax, H):
+        _need_cuda(y, fi)
+        lib = _lib.load()
+        y = _f32c(y)
+        dh = y.shape[1]
+        N = fi.shape[0]
+        out = torch.empty((nmax, B, H * dh), dtype=torch.float32, device=y.device)
+        check(lib.feta_unpack_heads(_ptr(y), _ptr(fi), _ptr(out), N, B, nmax, H, dh, _stream()),
+              "feta_unpack_heads")
+        ctx.save_for_backward(fi)
+        ctx.cfg = (B, nmax, H, dh)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        (fi,) = ctx.saved_tensors
+        B, nmax, H, dh = ctx.cfg
+        d_out = _f32c(d_out)
+        N = fi.shape[0]
+        dy = torch.empty((H * N, dh), dtype=torch.float32, device=d_out.device)
+        check(lib.feta_unpack_heads_bwd(_ptr(d_out), _ptr(fi), _ptr(dy), N, B, nmax, H, dh, _stream()),
+              "feta_unpack_heads_bwd")
+        return dy, None, None, None, None
+
+
+def pack_heads(o_heads, feature_indices):
+    return PackHeadsFn.apply(o_heads, _fi64(feature_indices))
+
+
+def unpack_heads(y, feature_indices, B, nmax, H):
+    return UnpackHeadsFn.apply(y, _fi64(feature_indices), B, nmax, H)
+
+
+class SegmentMeanFn(torch.autograd.Function):
+    """PyG global_mean_pool over sorted segments (models.py:283)."""
+
+    @staticmethod
+    def forward(ctx, x, graph_ptr):
+        _need_cuda(x, graph_ptr)
+        lib = _lib.load()
+        x = _f32c(x)
+        G, C = graph_ptr.numel() - 1, x.shape[1]
+        out = torch.empty((G, C), dtype=torch.float32, device=x.device)
+        check(lib.feta_segment_mean_fwd(_ptr(x), _ptr(graph_ptr), _ptr(out), G, C, _stream()),
+              "feta_segment_mean_fwd")
+        ctx.save_for_backward(graph_ptr)
+        ctx.rows = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        (graph_ptr,) = ctx.saved_tensors
+        d_out = _f32c(d_out)
+        G, C = d_out.shape
+        dx = torch.zeros((ctx.rows, C), dtype=torch.float32, device=d_out.device)
+        check(lib.feta_segment_mean_bwd(_ptr(d_out), _ptr(graph_ptr), _ptr(dx), G, C, _stream()),
+              "feta_segment_mean_bwd")
+        return dx, None
+
+
+def segment_mean(x, graph_ptr):
+    return SegmentMeanFn.apply(x, graph_ptr)
+
+
+class MaskedMeanFn(torch.autograd.Function):
+    """GlobalAvg1D (models.py:586-595) over x [B, Nmax, C] (any batch/node strides)."""
+
+    @staticmethod
+    def forward(ctx, x, mask_u8):
+        _need_cuda(x, mask_u8)
+        lib = _lib.load()
+        if x.dtype != torch.float32:
+            raise TypeError("fp32 only")
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        B, nmax, C = x.shape
+        out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+        check(lib.feta_masked_mean_fwd(_ptr(x), x.stride(0), x.stride(1), _ptr(mask_u8), _ptr(out), B, nmax, C,
+                                       _stream()), "feta_masked_mean_fwd")
+        ctx.save_for_backward(mask_u8)
+        ctx.shape = (B, nmax, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        (mask_u8,) = ctx.saved_tensors
+        B, nmax, C = ctx.shape
+        d_out = _f32c(d_out)
+        dx = torch.empty((B, nmax, C), dtype=torch.float32, device=d_out.device)
+        check(lib.feta_masked_mean_bwd(_ptr(d_out), _ptr(mask_u8), _ptr(dx), B, nmax, C, _stream()),
+              "feta_masked_mean_bwd")
+        return dx, None
+
+
+def masked_mean(x, mask):
+    B, nmax, _ = x.shape
+    return MaskedMeanFn.apply(x, _mask_u8(mask, B, nmax, x.device))
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """packed[i] = padded[fi[i,0], fi[i,1]]  (models.py:347, :1070-1071); padded [B, Nmax, C] view."""
+
+    @staticmethod
+    def forward(ctx, padded, fi):
+        _need_cuda(padded, fi)
+        lib = _lib.load()
+        if padded.dtype != torch.float32:
+            raise TypeError("fp32 only")
+        if padded.stride(2) != 1:
+            padded = padded.contiguous()
+        B, nmax, C = padded.shape
+        N = fi.shape[0]
+        packed = torch.empty((N, C), dtype=torch.float32, device=padded.device)
+        check(lib.feta_gather_rows(_ptr(padded), padded.stride(0), padded.stride(1), _ptr(fi), _ptr(packed), N, C,
+                                   _stream()), "feta_gather_rows")
+        ctx.save_for_backward(fi)
+        ctx.shape = (B, nmax, C)
+        return packed
+
+    @staticmethod
+    def backward(ctx, d_packed):
+        lib = _lib.load()
+        (fi,) = ctx.saved_tensors
+        B, nmax, C = ctx.shape
+        d_packed = _f32c(d_packed)
+        d_padded = torch.zeros((B, nmax, C), dtype=torch.float32, device=d_packed.device)
+        check(lib.feta_scatter_rows(_ptr(d_packed), _ptr(fi), _ptr(d_padded), nmax * C, C, fi.shape[0], C,
+                                    _stream()), "feta_scatter_rows")
+        return d_padded, None
+
+
+def gather_rows(padded, feature_indices):
+    return GatherRowsFn.apply(padded, _fi64(feature_indices))

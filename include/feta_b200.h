@@ -1,0 +1,221 @@
+/*
+ * feta_b200.h -- C ABI of libfeta_b200.so: B200 (sm_100a) kernels for the FeTA
+ * spectral hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain C, no C++/torch types; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host;
+ *   - the caller owns every buffer, including workspaces; the library keeps no
+ *     state and allocates nothing;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     hidden synchronisation, so every call is CUDA-graph capturable;
+ *   - returns 0 on success, a negative FETA_E* code otherwise; never throws,
+ *     never exits; feta_last_error_string() describes the last failure on the
+ *     calling thread;
+ *   - floating point is fp32; index inputs that come from the reference's
+ *     callers are int64 as PyTorch/PyG produce them, library-built index
+ *     arrays (CSR, graph_ptr) are int32.
+ *
+ * Each declaration cites the reference interface it replaces
+ * (paths relative to the ansonb/FeTA_TMLR tree).
+ */
+#ifndef FETA_B200_H_
+#define FETA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FETA_OK 0
+#define FETA_EINVAL (-1)     /* bad argument (null pointer, unsupported size) */
+#define FETA_ECUDA (-2)      /* a CUDA runtime call / launch failed */
+#define FETA_EWORKSPACE (-3) /* workspace too small */
+#define FETA_EUNSUPPORTED (-4)
+
+/* dtype tags for `batch` (models.py:179-182 hands ChebConvDynamic a FLOAT batch) */
+#define FETA_DT_I64 0
+#define FETA_DT_I32 1
+#define FETA_DT_F32 2
+#define FETA_DT_F64 3
+
+/* slots of the int32 `meta` array written by feta_cheb_plan_build */
+#define FETA_META_NNZ 0        /* entries of L_hat after self-loop removal */
+#define FETA_META_NUM_GRAPHS 1 /* runs of equal values found in `batch` */
+#define FETA_META_SORTED 2     /* 1 iff batch is non-decreasing */
+#define FETA_META_BLOCKDIAG 3  /* 1 iff every edge stays inside its graph's row range */
+#define FETA_META_MAX_NODES 4  /* largest graph (rows) */
+#define FETA_META_MAX_DEG 5    /* longest CSR row (either orientation) */
+#define FETA_META_BAD_INDEX 6  /* 1 iff an edge endpoint was outside [0, R) (edge dropped) */
+#define FETA_META_GUARD 7      /* set to 1 by feta_cheb_fwd/bwd when they refused to run (see below) */
+#define FETA_META_WORDS 8
+
+int feta_version(void);
+const char* feta_last_error_string(void);
+/* number of kernels this library has launched from the calling process (bench.py's
+ * gpu_launches claim is read from here) */
+int64_t feta_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * A2  ChebConvDynamic.__norm__  (transformer/ChebNetDynamic.py:108-130; PyG-1.7
+ *     remove_self_loops -> get_laplacian('sym') -> 2w/lambda_max -> add_self_loops(-1))
+ *     + the `torch.unique(batch, return_counts=True)` segmenting of :148.
+ *
+ * Builds, once per mini-batch, the CSR of L_hat = -(2/lambda_max) D^-1/2 A D^-1/2 grouped by
+ * TARGET (rowptr/colidx/vals: row t lists its sources, in input edge order) and the same
+ * matrix grouped by SOURCE (the *_t arrays, used by the backward pass).  The +1/-1 self-loop
+ * pair of the reference cancels and is not stored.  graph_ptr[g]..graph_ptr[g+1] is the row
+ * range of the g-th run of equal `batch` values; row_graph[r] is that run index.
+ * Pass batch == NULL for a single graph covering all rows.
+ * --------------------------------------------------------------------------------------- */
+size_t feta_cheb_plan_workspace_bytes(int64_t num_rows, int64_t num_edges);
+int feta_cheb_plan_build(const int64_t* edge_index /* [2, E] */, int64_t num_edges,
+                         const void* batch /* [R] or NULL */, int batch_dtype, int64_t num_rows,
+                         int64_t num_graphs /* capacity of graph_ptr - 1 */, float lambda_max,
+                         int32_t* rowptr /* [R+1] */, int32_t* colidx /* [E] */, float* vals /* [E] */,
+                         int32_t* rowptr_t /* [R+1] */, int32_t* colidx_t /* [E] */, float* vals_t /* [E] */,
+                         int32_t* graph_ptr /* [G+1] */, int32_t* row_graph /* [R] */,
+                         int32_t* meta /* [FETA_META_WORDS] */, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A1/A3  ChebConvDynamic.forward  (transformer/ChebNetDynamic.py:132-189, message :192-193)
+ *     out[r] = sum_k T_k[r] . Theta_k[g(r)] + bias,  T_0 = x, T_1 = L x, T_k = 2 L T_{k-1} - T_{k-2}
+ * theta is addressed as theta[k*theta_stride_k + g*theta_stride_g + i*fout + j] (elements), so
+ * the reference's permuted view of a contiguous [G, K*Fin*Fout] tensor (models.py:357) is
+ * consumed without a copy.  One fused launch when `block_diagonal` != 0, Fin == Fout in
+ * {4, 8, 16, 32} and the largest graph fits shared memory (`max_nodes`: an upper bound, from
+ * meta[FETA_META_MAX_NODES] or the caller's own knowledge); otherwise an un-fused per-order
+ * path through `workspace` (feta_cheb_workspace_bytes).
+ * `plan_meta` (may be NULL) is the meta array of feta_cheb_plan_build: when given, the fused
+ * kernels verify ON THE DEVICE that the plan is sorted, block diagonal, has exactly
+ * `num_graphs` graphs, none larger than `max_nodes`, and no bad index; if not they write
+ * nothing, set plan_meta[FETA_META_GUARD] = 1 and return -- so a caller that passed host-side
+ * hints instead of synchronising on the meta words cannot fault the GPU, and finds out at
+ * its next synchronisation point.
+ * --------------------------------------------------------------------------------------- */
+size_t feta_cheb_workspace_bytes(int64_t num_rows, int fin, int fout, int K);
+int feta_cheb_fwd(const float* x /* [R, Fin] */, const int32_t* rowptr, const int32_t* colidx,
+                  const float* vals, const int32_t* graph_ptr, const int32_t* row_graph,
+                  int32_t* plan_meta /* [FETA_META_WORDS] or NULL */,
+                  const float* theta, int64_t theta_stride_k, int64_t theta_stride_g,
+                  const float* bias /* [Fout] or NULL */, float* out /* [R, Fout] */,
+                  int64_t num_rows, int64_t num_graphs, int K, int fin, int fout, int max_nodes,
+                  int block_diagonal, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above.  dx (may be NULL) needs the SOURCE-grouped CSR (*_t); dtheta (may be
+ * NULL) recomputes T_k with the TARGET-grouped CSR.  dtheta uses the same strides as theta and
+ * is fully overwritten.  dbias [Fout] (may be NULL) is overwritten with sum_r dout[r]. */
+int feta_cheb_bwd(const float* dout /* [R, Fout] */, const float* x, const int32_t* rowptr,
+                  const int32_t* colidx, const float* vals, const int32_t* rowptr_t,
+                  const int32_t* colidx_t, const float* vals_t, const int32_t* graph_ptr,
+                  const int32_t* row_graph, int32_t* plan_meta, const float* theta, int64_t theta_stride_k,
+                  int64_t theta_stride_g, float* dx, float* dtheta, float* dbias, int64_t num_rows,
+                  int64_t num_graphs, int K, int fin, int fout, int max_nodes, int block_diagonal,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A6  kernel-biased attention core of DiffTransformerEncoderLayer (the layer transformer/models.py:4
+ *     imports; contract from models.py:166-167):  per (graph b, head h)
+ *         S = scale * Q K^T ; masked keys -> -inf ; E = exp(S - rowmax) * pe ;
+ *         P = E / max(rowsum(E), 1e-6) ; O = P V
+ * q/k/v are addressed as ptr[n*stride_n + b*stride_b + h*dh + c] (the [Nmax, B, 3d] in_proj output
+ * is consumed in place).  mask [B, Nmax] bytes, nonzero = padding.  pe [B, Nmax, Nmax] or NULL.
+ * Writes attn [B, H, Nmax, Nmax] (rows of padded queries are written as 0), o_heads
+ * [B, Nmax, H, dh] (= `out_each_head`, models.py:179) and rowflag [B, H, Nmax]
+ * (1 where rowsum > 1e-6, 0 where the clamp was active or the query is padding) for the backward.
+ * --------------------------------------------------------------------------------------- */
+int feta_attn_fwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
+                  const float* pe, const uint8_t* mask, float* attn, float* o_heads, float* rowflag,
+                  int B, int H, int nmax, int dh, float scale, void* stream);
+/* Backward: d_o_heads [B, Nmax, H, dh] and optional d_attn [B, H, Nmax, Nmax] in; dq/dk/dv out with
+ * their own strides (dq_ptr[n*dstride_n + b*dstride_b + h*dh + c]); every real (n, b) row is
+ * written, padded rows are written as 0. */
+int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
+                  const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o_heads,
+                  const float* d_attn, float* dq, float* dk, float* dv, int64_t dstride_n,
+                  int64_t dstride_b, int B, int H, int nmax, int dh, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A4  DiffTransformerEncoderGenGCN.get_filter_coefficients (transformer/models.py:240-287).
+ * With x == 1 the all-pairs GCNConv of :280-282 is  s_j * colsum(W) + b  with a per-node scalar
+ *     loop_j = a_jj != 0 ? a_jj : 1;  deg_j = sum_{i != j} a_ij + loop_j;
+ *     s_j = deg_j^-1/2 * ( sum_{i != j} deg_i^-1/2 a_ij + deg_j^-1/2 loop_j )
+ * (a = attn[b, h] restricted to real nodes; PyG-1.7 gcn_norm / add_remaining_self_loops).
+ * feta_coeff_scalar writes s in stacked-row order  s[h*N + node_ptr[b] + j].
+ * feta_coeff_pool_fwd:  pooled[g, c] = mean_{j in g} tanh(s_j * wbar[c] + gbias[c])  (:282-283),
+ * g = h*B + b; feta_coeff_pool_bwd returns d wbar, d gbias (attention is detached, :282).
+ * --------------------------------------------------------------------------------------- */
+int feta_coeff_scalar(const float* attn /* [B,H,Nmax,Nmax] */, const uint8_t* mask /* [B,Nmax] */,
+                      const int32_t* node_ptr /* [B+1] packed offsets of real nodes */,
+                      float* s /* [H*N] */, int B, int H, int nmax, int64_t num_nodes, void* stream);
+int feta_coeff_pool_fwd(const float* s /* [R] */, const int32_t* graph_ptr /* [G+1] */,
+                        const float* wbar /* [C] */, const float* gbias /* [C] */,
+                        float* pooled /* [G, C] */, int64_t num_graphs, int C, void* stream);
+int feta_coeff_pool_bwd(const float* s, const int32_t* graph_ptr, const float* wbar,
+                        const float* gbias, const float* d_pooled /* [G, C] */,
+                        float* d_wbar /* [C] */, float* d_gbias /* [C] */, float* partial /* [nblk, 2, C] */,
+                        int nblk, int64_t num_graphs, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A5  scatter / pool / pack ops (torch_scatter + advanced indexing in the reference).
+ * feature_indices [N, 2] int64 = (graph, node) rows as data.py:218 builds them.
+ * --------------------------------------------------------------------------------------- */
+/* models.py:177-185 + :347: x[h*N + i, :] = o_heads[fi[i,0], fi[i,1], h, :] */
+int feta_pack_heads(const float* o_heads /* [B,Nmax,H,dh] */, const int64_t* feature_indices,
+                    float* x /* [H*N, dh] */, int64_t N, int B, int nmax, int H, int dh, void* stream);
+/* adjoint of pack_heads: d_o_heads zero-filled then scattered */
+int feta_pack_heads_bwd(const float* dx, const int64_t* feature_indices, float* d_o_heads,
+                        int64_t N, int B, int nmax, int H, int dh, void* stream);
+/* models.py:200-202: out[fi[i,1], fi[i,0], h*dh + c] = y[h*N + i, c], zero elsewhere; out [Nmax,B,H*dh] */
+int feta_unpack_heads(const float* y /* [H*N, dh] */, const int64_t* feature_indices,
+                      float* out /* [Nmax,B,H*dh] */, int64_t N, int B, int nmax, int H, int dh,
+                      void* stream);
+int feta_unpack_heads_bwd(const float* d_out, const int64_t* feature_indices, float* dy, int64_t N,
+                          int B, int nmax, int H, int dh, void* stream);
+/* PyG global_mean_pool over sorted segments (models.py:283):  out[g] = mean_{r in g} x[r] */
+int feta_segment_mean_fwd(const float* x /* [R, C] */, const int32_t* graph_ptr, float* out /* [G, C] */,
+                          int64_t num_graphs, int C, void* stream);
+int feta_segment_mean_bwd(const float* d_out, const int32_t* graph_ptr, float* dx, int64_t num_graphs,
+                          int C, void* stream);
+/* GlobalAvg1D (models.py:586-595): out[b] = sum_{n real} x[b,n] / count;  x addressed
+ * x[b*stride_b + n*stride_n + c] */
+int feta_masked_mean_fwd(const float* x, int64_t stride_b, int64_t stride_n, const uint8_t* mask,
+                         float* out /* [B, C] */, int B, int nmax, int C, void* stream);
+int feta_masked_mean_bwd(const float* d_out /* [B, C] */, const uint8_t* mask, float* dx /* [B,Nmax,C] contiguous */,
+                         int B, int nmax, int C, void* stream);
+/* cls_output[~masks] (models.py:1070-1071) and the packed<->padded moves of :347 / :201-202 for
+ * one feature block:  packed[i, :] = padded[fi[i,0]*stride_b + fi[i,1]*stride_n + :] */
+int feta_gather_rows(const float* padded, int64_t stride_b, int64_t stride_n,
+                     const int64_t* feature_indices, float* packed /* [N, C] */, int64_t N, int C,
+                     void* stream);
+int feta_scatter_rows(const float* packed, const int64_t* feature_indices, float* padded,
+                      int64_t stride_b, int64_t stride_n, int64_t N, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A7  collate index builders (transformer/data.py:161-225, :394-460): GPU batch builder over a
+ * dataset pre-packed on the device.  Given the ids of the B graphs of a mini-batch and the
+ * packed dataset (node_ptr/edge_ptr prefix sums, edge_index local to each graph), writes the
+ * reference's integer outputs bit-exactly: mask [B,Nmax] (1 = pad), edge_indices [2,E]
+ * (= local + node offset), batch_indices [N], feature_indices [N,2].
+ * --------------------------------------------------------------------------------------- */
+int feta_collate_indices(const int64_t* graph_ids /* [B] */, const int64_t* ds_node_ptr,
+                         const int64_t* ds_edge_ptr, const int64_t* ds_edge_index /* [2, E_ds] */,
+                         int64_t ds_num_edges, const int64_t* out_node_ptr /* [B+1] */,
+                         const int64_t* out_edge_ptr /* [B+1] */, uint8_t* mask, int64_t* edge_indices,
+                         int64_t* batch_indices, int64_t* feature_indices, int B, int nmax,
+                         int64_t N, int64_t E, void* stream);
+/* padded feature / PE / degree fill for the same batch:
+ *   dst[b, n, :] = src[ds_node_ptr[graph_ids[b]] + n, :]  (n < len_b), 0 elsewhere;
+ *   pe_dst[b, i, j] = pe_src[ds_pe_ptr[gid] + i*len + j]   (i, j < len_b), 0 elsewhere. */
+int feta_collate_pad_rows(const int64_t* graph_ids, const int64_t* ds_node_ptr, const float* src,
+                          float* dst, int B, int nmax, int C, void* stream);
+int feta_collate_pad_pe(const int64_t* graph_ids, const int64_t* ds_node_ptr, const int64_t* ds_pe_ptr,
+                        const float* pe_src, float* pe_dst, int B, int nmax, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FETA_B200_H_ */

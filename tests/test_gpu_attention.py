@@ -1,0 +1,116 @@
+"""GPU parity: fused kernel-biased attention layer vs the CPU oracle (through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle.layers import OracleDiffTransformerEncoderLayer
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _inputs(seed, B, nmax, d, lens=None, with_pe=True):
+    g = torch.Generator().manual_seed(seed)
+    if lens is None:
+        lens = torch.randint(1, nmax + 1, (B,), generator=g)
+        lens[0] = nmax
+    lens = torch.as_tensor(lens)
+    mask = torch.arange(nmax)[None, :] >= lens[:, None]
+    src = torch.randn(nmax, B, d, generator=g)
+    pe = None
+    if with_pe:
+        a = torch.rand(B, nmax, nmax, generator=g)
+        pe = (a + a.transpose(1, 2)) * 0.5
+        pe = pe * (torch.rand(B, nmax, nmax, generator=g) > 0.2)          # exact zeros are meaningful
+        valid = (~mask)[:, :, None] & (~mask)[:, None, :]
+        pe = pe * valid                                                    # zero padded (data.py:182,212)
+    degree = torch.rand(B, nmax, generator=g) * (~mask)
+    return src, pe, degree, mask
+
+
+def _pair(cuda, d, H, seed, **kw):
+    from feta_tmlr_b200 import DiffTransformerEncoderLayer
+    torch.manual_seed(seed)
+    o = OracleDiffTransformerEncoderLayer(d, H, 2 * d, 0.0, **kw)
+    o.zero_padded_queries = True                                           # product's documented convention
+    m = DiffTransformerEncoderLayer(d, H, 2 * d, 0.0, **kw).to(cuda)
+    m.load_state_dict(o.state_dict())
+    return o, m
+
+
+@pytest.mark.parametrize("d,H", [(64, 8), (64, 4), (32, 1), (64, 1), (16, 4)])
+@pytest.mark.parametrize("nmax", [7, 38, 100])
+def test_attention_layer_parity(cuda, d, H, nmax):
+    o, m = _pair(cuda, d, H, seed=d + H + nmax)
+    src, pe, degree, mask = _inputs(nmax, 5, nmax, d)
+    so = src.clone().requires_grad_()
+    oo, oa, oh = o(so, pe=pe, degree=degree, src_key_padding_mask=mask, need_heads=True)
+    sg = src.to(cuda).requires_grad_()
+    go, ga, gh = m(sg, pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda), need_heads=True)
+    assert ga.shape == oa.shape and gh.shape == oh.shape
+    assert rel_err(ga, oa) < TOL and rel_err(gh, oh) < TOL and rel_err(go, oo) < TOL
+    assert torch.equal(ga.cpu() == 0, oa == 0)                             # exact zeros preserved (models.py:276)
+    w = torch.randn(oo.shape, generator=torch.Generator().manual_seed(1))
+    wh = torch.randn(oh.shape, generator=torch.Generator().manual_seed(2))
+    wa = torch.randn(oa.shape, generator=torch.Generator().manual_seed(3))
+    ((oo * w).sum() + (oh * wh).sum() + (oa * wa).sum()).backward()
+    ((go * w.to(cuda)).sum() + (gh * wh.to(cuda)).sum() + (ga * wa.to(cuda)).sum()).backward()
+    assert rel_err(sg.grad, so.grad) < TOL
+    for (n1, p1), (n2, p2) in zip(o.named_parameters(), m.named_parameters()):
+        assert n1 == n2
+        assert rel_err(p2.grad, p1.grad) < 2e-4, n1
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(share_qk=True), dict(attn_bias=True), dict(batch_norm=True)])
+def test_attention_variants(cuda, kw):
+    o, m = _pair(cuda, 32, 4, seed=11, **kw)
+    src, pe, degree, mask = _inputs(3, 6, 20, 32)
+    so, sg = src.clone().requires_grad_(), src.to(cuda).requires_grad_()
+    oo, oa = o(so, pe=pe, degree=degree, src_key_padding_mask=mask)
+    go, ga = m(sg, pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda))
+    assert rel_err(go, oo) < TOL and rel_err(ga, oa) < TOL
+    oo.square().sum().backward()
+    go.square().sum().backward()
+    assert rel_err(sg.grad, so.grad) < 2e-4
+    for (n1, p1), (n2, p2) in zip(o.named_parameters(), m.named_parameters()):
+        assert rel_err(p2.grad, p1.grad) < 5e-4, n1
+
+
+def test_attention_no_pe_and_pe_diag_scaling(cuda):
+    o, m = _pair(cuda, 32, 4, seed=12)
+    src, pe, degree, mask = _inputs(4, 4, 15, 32)
+    oo, oa = o(src, pe=None, degree=degree, src_key_padding_mask=mask)     # pe=None: plain softmax rows
+    go, ga = m(src.to(cuda), pe=None, degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda))
+    assert rel_err(go, oo) < TOL and rel_err(ga, oa) < TOL
+    real = ~mask
+    rows = ga.cpu().sum(-1)[real[:, None, :].expand(-1, 4, -1)]
+    assert torch.allclose(rows, torch.ones_like(rows), atol=1e-5)
+    pe2 = pe + torch.eye(15)[None] * (~mask)[:, :, None]
+    oo, _ = o(src, pe=pe2, degree=None, src_key_padding_mask=mask)         # degree=None -> pe-diagonal scaling
+    go, _ = m(src.to(cuda), pe=pe2.to(cuda), degree=None, src_key_padding_mask=mask.to(cuda))
+    assert rel_err(go, oo) < TOL
+
+
+def test_attention_large_graph_pattern_shape(cuda):
+    o, m = _pair(cuda, 64, 4, seed=13)
+    src, pe, degree, mask = _inputs(5, 3, 188, 64, lens=[188, 44, 120], with_pe=False)
+    so, sg = src.clone().requires_grad_(), src.to(cuda).requires_grad_()
+    oo, oa, oh = o(so, pe=None, degree=degree, src_key_padding_mask=mask, need_heads=True)
+    go, ga, gh = m(sg, pe=None, degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda), need_heads=True)
+    assert rel_err(go, oo) < TOL and rel_err(ga, oa) < TOL and rel_err(gh, oh) < TOL
+    (oo.sum() + oh.square().sum()).backward()
+    (go.sum() + gh.square().sum()).backward()
+    assert rel_err(sg.grad, so.grad) < TOL
+
+
+def test_attention_rejects_unsupported(cuda):
+    from feta_tmlr_b200 import DiffTransformerEncoderLayer
+    m = DiffTransformerEncoderLayer(36, 3, 72, 0.0).to(cuda)               # head dim 12 not templated
+    src, pe, degree, mask = _inputs(6, 2, 5, 36)
+    with pytest.raises(RuntimeError):
+        m(src.to(cuda), pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda))
+    m = DiffTransformerEncoderLayer(32, 4, 64, 0.5).to(cuda).train()       # attention dropout
+    src, pe, degree, mask = _inputs(6, 2, 5, 32)
+    with pytest.raises(NotImplementedError):
+        m(src.to(cuda), pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda))
