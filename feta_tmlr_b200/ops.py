@@ -58,12 +58,12 @@ class ChebPlan(object):
         m = self.meta_host()
         if m[META_BAD_INDEX]:
             raise IndexError("ChebConvDynamic: edge_index holds a node id outside [0, %d)" % self.num_rows)
+        if not m[META_SORTED]:
+            raise ValueError("ChebConvDynamic: `batch` must be sorted (nodes of a graph contiguous)")
         if self.num_rows > 0 and m[META_NUM_GRAPHS] != self.num_graphs:
             raise RuntimeError(
                 "ChebConvDynamic: `batch` holds %d graphs but filter_coeff has %d "
                 "(repeat_interleave size mismatch, ChebNetDynamic.py:149)" % (m[META_NUM_GRAPHS], self.num_graphs))
-        if not m[META_SORTED]:
-            raise ValueError("ChebConvDynamic: `batch` must be sorted (nodes of a graph contiguous)")
         if m[META_GUARD]:
             raise RuntimeError("ChebConvDynamic: a fused kernel refused to run because the host-side "
                                "plan hints (max_nodes=%d, block_diagonal) did not hold: meta=%s"

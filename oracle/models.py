@@ -284,6 +284,19 @@ class OracleAtomEncoder(nn.Module):
         return out
 
 
+class OracleBondEncoder(nn.Module):
+    """ogb ``BondEncoder`` parameter shell (constructed at models.py:621, never called)."""
+    FULL_BOND_FEATURE_DIMS = [5, 6, 2]
+
+    def __init__(self, emb_dim):
+        super().__init__()
+        self.bond_embedding_list = nn.ModuleList()
+        for dim in self.FULL_BOND_FEATURE_DIMS:
+            emb = nn.Embedding(dim, emb_dim)
+            nn.init.xavier_uniform_(emb.weight.data)
+            self.bond_embedding_list.append(emb)
+
+
 class OracleDiffGraphTransformerGenGCNMolHiv(nn.Module):
     """models.py:598-725 (molhiv head; BondEncoder of :621 is constructed but unused)."""
 
@@ -298,6 +311,7 @@ class OracleDiffGraphTransformerGenGCNMolHiv(nn.Module):
             self.embedding_lap_pos_enc = nn.Linear(lap_pos_enc_dim, d_model)
         self.d_model = d_model
         self.embedding = OracleAtomEncoder(emb_dim=d_model)
+        self.edge_embeddings = OracleBondEncoder(emb_dim=d_model)                      # :621 (unused)
         encoder_layer = OracleDiffTransformerEncoderLayer(d_model, nb_heads, dim_feedforward,
                                                           dropout, batch_norm=batch_norm,
                                                           **layer_kw)
