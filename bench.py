@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- graphs/s (fwd + bwd + optimizer step) of the FeTA spectral hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host cores
+
+One "step" = one training step of the BASELINE configs[1] model (ZINC-shape, batch 128 per GPU,
+ChebConvDynamic + diffusion PE beta=1, H=8, L=10, d=64) over one synthetic mini-batch.
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "graphs/sec fwd+bwd"
+UNIT = "graphs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--config", default="ZINC", choices=["MUTAG", "ZINC", "PATTERN", "CLUSTER", "MOLHIV"])
+    ap.add_argument("--pool", type=int, default=0, help="distinct batches in the rotating pool (0 = auto: > L2)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the HBM-sized Chebyshev kernel sweep")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="override graphs per GPU per step")
+    ap.add_argument("--sweep-only", action="store_true", help="run only the HBM-sized Chebyshev sweep")
+    ap.add_argument("--sweep-f", type=int, default=0, help="feature width for --sweep-only (default: config's dh)")
+    ap.add_argument("--sweep-rows", type=int, default=6_000_000)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def loss_fn_for(name):
+    import torch.nn.functional as F
+    if name in ("PATTERN", "CLUSTER", "MUTAG"):
+        return lambda out, y: F.cross_entropy(out, y.long())
+    if name == "ZINC":
+        return lambda out, y: F.l1_loss(out, y)                      # run_transformer_gengcn.py:301
+    return lambda out, y: F.binary_cross_entropy_with_logits(out.reshape(-1), y.reshape(-1))
+
+
+def batch_nbytes(batch):
+    return sum(t.numel() * t.element_size() for t in batch if t is not None)
+
+
+class ClockSampler(object):
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, "/tmp/feta_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    smax.append(float(c[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def make_pool(name, cfg, B, n_batches, seed):
+    """Host-side pool of distinct mini-batches (reference collate tuple each)."""
+    from feta_tmlr_b200 import data as fdata, synthetic
+    graphs = synthetic.make_dataset(name, B * n_batches, seed=seed)
+    store = fdata.GraphStore(graphs, kind=cfg['kind'], n_tags=cfg['n_tags'])
+    return [fdata.collate_host(store, np.arange(i * B, (i + 1) * B))[:9] for i in range(n_batches)]
+
+
+def call_model(model, b):
+    px, mask, pe, lap, deg, labels, ei, bi, fi = b
+    return model(px, ei, bi, fi, mask, pe, lap, deg)
+
+
+def run_reference(args, cfg, B):
+    """The reference's algorithm (CPU restatement, oracle/) on all host cores -- bounded sample."""
+    import oracle.models as omodels
+    from feta_tmlr_b200 import synthetic
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    pool = make_pool(args.config, cfg, B, 2, seed=0)
+    torch.manual_seed(0)
+    model = synthetic.build_model(args.config, omodels)         # literal all-pairs GCN (models.py:240-287)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    lf = loss_fn_for(args.config)
+
+    def step(i):
+        b = pool[i % len(pool)]
+        opt.zero_grad()
+        loss = lf(call_model(model, b)[0], b[5])
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    return val, dt, cores
+
+
+def cheb_algorithmic_bytes(R, F, nnz, G, K):
+    """x + out + CSR(colidx, vals, rowptr) + Theta + graph_ptr + bias."""
+    return 4 * R * F + 4 * R * F + 8 * nnz + 4 * (R + 1) + 4 * G * K * F * F + 4 * (G + 1) + 4 * F
+
+
+def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=6_000_000):
+    """The fused Chebyshev kernel on an HBM-sized (>> 126 MB L2) batch of molecule-shape graphs."""
+    from feta_tmlr_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(0)
+    G = target_rows // 25
+    sizes = torch.randint(10, 41, (G,), device=dev, generator=g)
+    gp = torch.zeros(G + 1, dtype=torch.int64, device=dev)
+    gp[1:] = torch.cumsum(sizes, 0)
+    R = int(gp[-1])
+    batch = torch.repeat_interleave(torch.arange(G, device=dev), sizes)
+    idx = torch.arange(R, device=dev)
+    first = gp[:-1][batch]
+    chain = idx[idx != first]                                      # bond (i-1, i) inside each molecule
+    extra_src = idx[::9]
+    span = sizes[batch[extra_src]]
+    extra_dst = first[extra_src] + (extra_src - first[extra_src] + 3) % span   # a few ring closures
+    s = torch.cat([chain - 1, extra_src])
+    t = torch.cat([chain, extra_dst])
+    ei = torch.stack([torch.cat([s, t]), torch.cat([t, s])])
+    plan = ops.build_cheb_plan(ei, batch, R, G, 2.0)
+    nnz = plan.meta_host()[0]
+    x = torch.randn(R, F, device=dev, generator=g)
+    theta = (torch.randn(G, K * F * F, device=dev, generator=g) * 0.1).reshape(G, K, F, F).permute(1, 0, 2, 3)
+    bias = torch.zeros(F, device=dev)
+    for _ in range(3):
+        ops.cheb_filter(x, theta, bias, plan)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    iters = 10
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(iters):
+        ops.cheb_filter(x, theta, bias, plan)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / iters
+    nbytes = cheb_algorithmic_bytes(R, F, nnz, G, K)
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "cheb_fwd_fused_kernel<%d>" % F, "workload": "molecule-shape, %d graphs, %d rows, %d nnz, "
+            "K=%d, F=%d (working set %.2f GB >> L2)" % (G, R, nnz, K, F, nbytes / 1e9), "bound": "hbm",
+            "achieved": round(ach, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(ach / hbm_gbs, 4),
+            "ms_per_launch": round(ms, 4), "algorithmic_bytes": nbytes}
+
+
+def main():
+    args = parse_args()
+    from feta_tmlr_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS[args.config])
+    B = args.batch or cfg['batch']
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = ("%s-shape synthetic, batch %d/GPU, ChebConvDynamic K=4, H=%d, L=%d, d=%d, pos_enc=%s, "
+                "lap_dim=%d, LayerNorm, Adam" % (args.config, B, cfg['heads'], cfg['layers'], cfg['d_model'],
+                                                 cfg['pos_enc'], cfg['lap_dim']))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        val, dt, cores = run_reference(args, cfg, B)
+        line = {"impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": workload, "where": "host CPU, %d threads" % cores},
+                "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "%d steps of one %d-graph batch each (oracle/, literal reference op "
+                                           "sequence incl. all-pairs GCN)" % (args.steps, B)},
+                "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this repo's CUDA path
+    import torch.distributed as dist
+    import feta_tmlr_b200.models as fmodels
+    from feta_tmlr_b200 import _lib, ddp, ops
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    hbm_gbs, peak_src = peaks()
+    if args.sweep_only:
+        dh = cfg['d_model'] // cfg['heads']
+        print(json.dumps(cheb_sweep(dev, hbm_gbs, F=args.sweep_f or dh, target_rows=args.sweep_rows)))
+        return 0
+
+    # rotating pool of distinct batches whose device-resident total exceeds the 126 MB L2
+    probe = make_pool(args.config, cfg, B, 1, seed=1000 + rank)
+    per_batch = batch_nbytes(probe[0])
+    n_pool = args.pool or int(min(256, max(8, np.ceil(160e6 / per_batch))))
+    pool_host = make_pool(args.config, cfg, B, n_pool, seed=rank)
+    pool_pinned = [tuple(None if t is None else t.pin_memory() for t in b) for b in pool_host]
+    pool_dev = [tuple(None if t is None else t.to(dev) for t in b) for b in pool_host]
+
+    torch.manual_seed(0)
+    model = synthetic.build_model(args.config, fmodels).to(dev)
+    ddp.broadcast_parameters(model)
+    bucket = ddp.FlatGradBucket(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    lf = loss_fn_for(args.config)
+
+    def step(b):
+        bucket.zero()
+        loss = lf(call_model(model, b)[0], b[5])
+        loss.backward()
+        bucket.all_reduce_mean()
+        opt.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K, W, offset=0):
+        for i in range(W):
+            fn(i + offset)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for i in range(K):
+            fn(W + i + offset)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), _lib.launch_count() - n0
+
+    # ---- leg 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    ops.enable_kernel_timer("cheb_fwd")
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(lambda i: step(pool_dev[i % n_pool]), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    cheb_ms = ops.kernel_timer_ms("cheb_fwd")[-args.steps:]
+    ops.disable_kernel_timers()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- leg 2: end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    d2h = [0]
+
+    def e2e_step(i):
+        hb = pool_pinned[i % n_pool]
+        b = tuple(None if t is None else t.to(dev, non_blocking=True) for t in hb)
+        loss = step(b)
+        d2h[0] = float(loss.detach().cpu())          # device -> host read of the step's result
+
+    ms_e2e, _ = timed(e2e_step, args.steps, args.warmup, offset=7)
+    e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d_bytes = int(np.mean([batch_nbytes(b) for b in pool_pinned]))
+
+    # ---- roofline of the fused Chebyshev kernel inside the step (+ the HBM-sized sweep)
+    line = None
+    if rank == 0:
+        plan_rows = []
+        H = cfg['heads']
+        dh = cfg['d_model'] // H
+        for b in pool_dev[:min(n_pool, 8)]:
+            N, E = b[8].shape[0], b[6].shape[1]
+            nnz = int((b[6][0] != b[6][1]).sum())
+            plan_rows.append(cheb_algorithmic_bytes(H * N, dh, nnz, H * B, 4))
+        alg_bytes = float(np.mean(plan_rows))
+        k_ms = float(np.mean(cheb_ms)) if cheb_ms else float("nan")
+        ach = alg_bytes / (k_ms * 1e-3) / 1e9
+        roofline = {"kernel": "cheb_fwd_fused_kernel<%d>" % dh, "bound": "hbm", "achieved": round(ach, 2),
+                    "peak": hbm_gbs, "unit": "GB/s", "frac": round(ach / hbm_gbs, 5), "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes": int(alg_bytes),
+                    "us_per_launch": round(k_ms * 1e3, 2),
+                    "note": "in-step launch at the BASELINE config is %.2f MB, L2-resident and launch-latency "
+                            "bound (SURVEY.md F5); roofline_sweep is the same kernel on an HBM-sized batch"
+                            % (alg_bytes / 1e6)}
+        sweep = None
+        if not args.no_sweep:
+            try:
+                sweep = cheb_sweep(dev, hbm_gbs, F=dh if dh in (4, 8, 16, 32) else 16)
+            except torch.OutOfMemoryError as e:       # bounded sweep; never take the box down
+                sweep = {"error": "OOM: %s" % str(e)[:80]}
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            a2 = argparse.Namespace(**vars(args))
+            a2.steps, a2.warmup = 4, 1
+            cval, cdt, cores = run_reference(a2, cfg, B)
+            cpu_baseline = {"value": round(cval, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "4 timed steps (1 warm-up) of one %d-graph batch each, oracle/ on host cores"
+                                      % B}
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "graphs_per_step": world * B,
+                           "parallelism": "dp%d (graphs sharded, one flat-bucket NCCL all-reduce of %d B/step)"
+                                          % (world, bucket.nbytes()) if world > 1 else "single GPU",
+                           "l2": "inputs rotate through a pool of %d distinct device-resident batches "
+                                 "(%.0f MB > 126 MB L2)" % (n_pool, n_pool * per_batch / 1e6),
+                           "edges": "reference-faithful un-tiled edge_index (SURVEY.md F4)",
+                           "execution": "eager PyTorch autograd over C-ABI kernels, current stream"},
+                "clocks": clocks,
+                "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_sweep": sweep,
+                "cpu_baseline": cpu_baseline, "last_loss": d2h[0]}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

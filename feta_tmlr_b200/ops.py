@@ -19,6 +19,45 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-kernel CUDA-event timers (bench.py's live roofline measurement): when a name is
+# enabled, every launch of that kernel is bracketed by two events on the launching stream.
+_TIMERS = {}
+
+
+def enable_kernel_timer(name):
+    _TIMERS[name] = []
+
+
+def disable_kernel_timers():
+    _TIMERS.clear()
+
+
+def kernel_timer_ms(name):
+    """Synchronises; returns the list of per-launch durations (ms) recorded for ``name``."""
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in _TIMERS.get(name, [])]
+
+
+class _timed(object):
+    __slots__ = ("name", "a")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if self.name in _TIMERS:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.name in _TIMERS:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _TIMERS[self.name].append((self.a, b))
+        return False
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -165,11 +204,12 @@ class ChebFilterFn(torch.autograd.Function):
         fused = fin == fout and fin in (4, 8, 16, 32) and plan.block_diagonal
         ws = None if fused else torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         biasc = None if bias is None else _f32c(bias)
-        rc = lib.feta_cheb_fwd(_ptr(x), _ptr(plan.rowptr), _ptr(plan.colidx), _ptr(plan.vals),
-                               _ptr(plan.graph_ptr), _ptr(plan.row_graph), _ptr(plan.meta), _ptr(theta),
-                               sk, sg, _ptr(biasc), _ptr(out), R, G, K, fin, fout, plan.max_nodes,
-                               int(plan.block_diagonal), _ptr(ws), ws_bytes if ws is not None else 0,
-                               _stream())
+        with _timed("cheb_fwd"):
+            rc = lib.feta_cheb_fwd(_ptr(x), _ptr(plan.rowptr), _ptr(plan.colidx), _ptr(plan.vals),
+                                   _ptr(plan.graph_ptr), _ptr(plan.row_graph), _ptr(plan.meta), _ptr(theta),
+                                   sk, sg, _ptr(biasc), _ptr(out), R, G, K, fin, fout, plan.max_nodes,
+                                   int(plan.block_diagonal), _ptr(ws), ws_bytes if ws is not None else 0,
+                                   _stream())
         if rc == -3 and ws is None:     # graph too large for the fused tile: un-fused path
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             rc = lib.feta_cheb_fwd(_ptr(x), _ptr(plan.rowptr), _ptr(plan.colidx), _ptr(plan.vals),
@@ -244,8 +284,9 @@ class DiffAttentionFn(torch.autograd.Function):
         rowflag = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
         base = qkv.data_ptr()
         qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
-        check(lib.feta_attn_fwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(attn), _ptr(o_heads),
-                                _ptr(rowflag), B, H, N, dh, float(scale), _stream()), "feta_attn_fwd")
+        with _timed("attn_fwd"):
+            check(lib.feta_attn_fwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(attn), _ptr(o_heads),
+                                    _ptr(rowflag), B, H, N, dh, float(scale), _stream()), "feta_attn_fwd")
         ctx.save_for_backward(qkv, mask_u8, attn, rowflag)
         ctx.cfg = (H, float(scale), bool(share_qk))
         ctx.mark_non_differentiable(rowflag)
@@ -267,9 +308,10 @@ class DiffAttentionFn(torch.autograd.Function):
         base = qkv.data_ptr()
         qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
         db = dqkv.data_ptr()
-        check(lib.feta_attn_bwd(qp, kp, vp, B * d3, d3, _ptr(mask_u8), _ptr(attn), _ptr(rowflag),
-                                _ptr(d_o_heads), _ptr(d_attn_c), db, db + d * 4, db + 2 * d * 4, B * d3, d3,
-                                B, H, N, dh, scale, _stream()), "feta_attn_bwd")
+        with _timed("attn_bwd"):
+            check(lib.feta_attn_bwd(qp, kp, vp, B * d3, d3, _ptr(mask_u8), _ptr(attn), _ptr(rowflag),
+                                    _ptr(d_o_heads), _ptr(d_attn_c), db, db + d * 4, db + 2 * d * 4, B * d3, d3,
+                                    B, H, N, dh, scale, _stream()), "feta_attn_bwd")
         if share_qk:
             dqkv[..., :d] += dqkv[..., d:2 * d]
             dqkv[..., d:2 * d] = 0
