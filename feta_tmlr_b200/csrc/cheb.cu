@@ -10,9 +10,16 @@
 //
 // HBM traffic per launch = x + out + CSR + Theta (each read/written once); everything else
 // lives in shared memory / registers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace feta {
+
+// csrc/cheb_warp.cu: warp-per-graph TMA-staged forward (graphs of <= 64 rows); 1 = not eligible
+int cheb_fwd_warp_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                      const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias,
+                      float* out, int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -556,6 +563,11 @@ extern "C" int feta_cheb_fwd(const float* x, const int32_t* rowptr, const int32_
   const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)theta % 16 == 0) &&
                        (sk % 4 == 0) && (sg % 4 == 0);
   FusedCfg cfg = fused_config(fin, max_nodes, 2, false);
+  if (fin == fout && block_diagonal && aligned && getenv("FETA_CHEB_NO_WARP_KERNEL") == nullptr) {
+    rc = cheb_fwd_warp_try(x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, fin, max_nodes,
+                           plan_meta, st);
+    if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = shape not eligible
+  }
   if (fin == fout && block_diagonal && aligned && cfg.ok) {
     FETA_DISPATCH_F(fin, return launch_fwd<FF>(cfg, x, rowptr, colidx, vals, graph_ptr, row_graph, theta, sk, sg,
                                                bias, out, R, K, plan_meta, G, max_nodes, st));

@@ -1,0 +1,368 @@
+// A1/A3: warp-per-graph, TMA-staged, persistent forward of ChebConvDynamic for batches of small
+// graphs (every graph <= 64 rows): the HBM-roofline variant of csrc/cheb.cu.
+//
+// Why a second kernel: ncu on the chunk kernel (profiles/r1_cheb_fwd_chunk_sweep.md) showed 53 %
+// long-scoreboard stalls (Theta / CSR read through L1 in the inner loop) and 38 % barrier stalls
+// (idle threads + block-wide __syncthreads per Chebyshev order).  Here
+//   * one WARP owns one graph at a time (lane = row, up to RPL rows per lane), so the only
+//     synchronisation between Chebyshev orders is __syncwarp;
+//   * everything a graph needs -- its x rows, its Theta block, its CSR slice -- is brought into
+//     shared memory by cp.async.bulk (TMA, 1-D) completing on an mbarrier, double buffered, issued
+//     one graph ahead; the scalars that size those copies (graph_ptr / rowptr reads) are fetched
+//     two and three graphs ahead, so no global-load latency sits on the critical path;
+//   * the filter is applied with packed fp32x2 FMAs (FFMA2) against Theta rows broadcast from
+//     shared memory; the output slab goes back with one cp.async.bulk store per graph;
+//   * the grid is persistent: 148 CTAs, each warp strides over the graph list.
+#include "common.cuh"
+
+namespace feta {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+// global -> shared bulk copy (TMA, UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// shared -> global bulk store
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct WarpCfg {
+  int rpl, warps, nnz_cap, rows_cap;
+  size_t per_warp, smem;
+  bool ok;
+};
+
+static inline size_t warp_region_bytes(int F, int K, int rows_cap, int nnz_cap) {
+  const size_t ta = (size_t)rows_cap * (F + 4) * 4;  // odd orders, padded rows (gather target)
+  const size_t t0 = (size_t)rows_cap * F * 4;        // x slab / even orders, dense (one bulk copy)
+  const size_t csr = align_up((size_t)(nnz_cap + 8) * 4, 16);
+  const size_t stage = t0 + (size_t)K * F * F * 4 + 2 * csr;
+  return align_up(16 + ta + 2 * stage, 128);
+}
+
+static WarpCfg warp_config(int F, int K, int max_nodes) {
+  WarpCfg c{0, 0, 0, 0, 0, 0, false};
+  if (!(F == 4 || F == 8 || F == 16) || max_nodes < 1 || max_nodes > 64) return c;
+  if ((size_t)K * F * F * 4 > 16 * 1024) return c;
+  c.rpl = max_nodes <= 32 ? 1 : 2;
+  c.rows_cap = (max_nodes + 7) / 8 * 8;  // buffers sized for the largest graph, not for 32 * rpl
+  c.nnz_cap = c.rows_cap * 4;
+  c.per_warp = warp_region_bytes(F, K, c.rows_cap, c.nnz_cap);
+  int w = (int)((220 * 1024) / c.per_warp);
+  if (w > 16) w = 16;
+  if (w < 4) return c;
+  c.warps = w;
+  c.smem = c.per_warp * w;
+  c.ok = true;
+  return c;
+}
+
+template <int F>
+__device__ __forceinline__ void apply_theta_s(float2 (&acc)[F / 2], const float (&t)[F], const float* __restrict__ th) {
+#pragma unroll
+  for (int i = 0; i < F; ++i) {
+    const float2 tt = make_float2(t[i], t[i]);
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      const float4 w = *reinterpret_cast<const float4*>(th + i * F + 4 * q);
+      acc[2 * q] = __ffma2_rn(tt, make_float2(w.x, w.y), acc[2 * q]);
+      acc[2 * q + 1] = __ffma2_rn(tt, make_float2(w.z, w.w), acc[2 * q + 1]);
+    }
+  }
+}
+
+template <int F, int LD, bool STAGED>
+__device__ __forceinline__ void gather_row_w(float (&t)[F], const float* __restrict__ buf, int r0,
+                                             const int32_t* __restrict__ ci, const float* __restrict__ cv, int e0,
+                                             int e1) {
+  float2 a2[F / 2];
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) a2[i] = make_float2(0.f, 0.f);
+  for (int e = e0; e < e1; ++e) {
+    const int c = (STAGED ? ci[e] : __ldg(ci + e)) - r0;
+    const float w = STAGED ? cv[e] : __ldg(cv + e);
+    const float2 ww = make_float2(w, w);
+    const float* row = buf + c * LD;
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(row + 4 * q);
+      a2[2 * q] = __ffma2_rn(ww, make_float2(a.x, a.y), a2[2 * q]);
+      a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a.z, a.w), a2[2 * q + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) t[2 * i] = a2[i].x, t[2 * i + 1] = a2[i].y;
+}
+
+template <int RPL>
+struct GraphDesc {  // scalars of one graph, fetched ahead of use
+  int r0, r1, e_lo, e_hi;
+  int e0[RPL], e1[RPL];
+};
+
+template <int F, int RPL>
+__global__ void __launch_bounds__(512, 1) cheb_fwd_warp_kernel(
+    const float* __restrict__ x, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+    const float* __restrict__ vals, const int32_t* __restrict__ graph_ptr, const float* __restrict__ theta,
+    int64_t sk, int64_t sg, const float* __restrict__ bias, float* __restrict__ out, int64_t R, int64_t G, int K,
+    int nnz_cap, int rows_cap, int per_warp_bytes, int32_t* meta, int max_nodes) {
+  constexpr int LD = F + 4;
+  const uint32_t TA = (uint32_t)rows_cap * LD * 4;  // padded odd-order buffer
+  const uint32_t TB = (uint32_t)rows_cap * F * 4;   // dense x slab / even-order buffer (per stage)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // device-side plan guard (same contract as the chunk kernel)
+  if (meta != nullptr) {
+    const bool ok = meta[FETA_META_SORTED] == 1 && meta[FETA_META_BLOCKDIAG] == 1 &&
+                    meta[FETA_META_NUM_GRAPHS] == (int32_t)G && meta[FETA_META_MAX_NODES] <= max_nodes &&
+                    meta[FETA_META_BAD_INDEX] == 0;
+    if (!ok) {
+      if (threadIdx.x == 0) meta[FETA_META_GUARD] = 1;
+      return;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * warps + warp, stride = (int64_t)gridDim.x * warps;
+  if (gw >= G) return;
+  const int n_it = (int)((G - gw + stride - 1) / stride);
+
+  unsigned char* base = smem_raw + (size_t)warp * per_warp_bytes;
+  const uint32_t csr_bytes = (uint32_t)(((nnz_cap + 8) * 4 + 15) / 16 * 16);
+  const uint32_t th_bytes = (uint32_t)K * F * F * 4;
+  const uint32_t stage_bytes = TB + th_bytes + 2 * csr_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base);
+  float* bufA = reinterpret_cast<float*>(base + 16);
+  unsigned char* stage0 = base + 16 + TA;
+  const bool theta_contig = (sk == (int64_t)F * F);
+
+  if (lane == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int nnz_total = __ldg(rowptr + R);
+  float bias_r[F];
+#pragma unroll
+  for (int i = 0; i < F; ++i) bias_r[i] = bias ? __ldg(bias + i) : 0.0f;
+
+  auto fetch_a = [&](int it, GraphDesc<RPL>& d) {  // stage "a": row range of the graph
+    d.r0 = d.r1 = 0;
+    if (it < n_it) {
+      const int64_t g = gw + (int64_t)it * stride;
+      d.r0 = __ldg(graph_ptr + g);
+      d.r1 = __ldg(graph_ptr + g + 1);
+    }
+  };
+  auto fetch_b = [&](int it, GraphDesc<RPL>& d) {  // stage "b": CSR extents (depends on stage a)
+    d.e_lo = d.e_hi = 0;
+#pragma unroll
+    for (int m = 0; m < RPL; ++m) d.e0[m] = d.e1[m] = 0;
+    if (it < n_it) {
+      d.e_lo = __ldg(rowptr + d.r0);
+      d.e_hi = __ldg(rowptr + d.r1);
+#pragma unroll
+      for (int m = 0; m < RPL; ++m) {
+        const int row = lane + 32 * m;
+        if (row < d.r1 - d.r0) {
+          d.e0[m] = __ldg(rowptr + d.r0 + row);
+          d.e1[m] = __ldg(rowptr + d.r0 + row + 1);
+        }
+      }
+    }
+  };
+  auto staged_csr = [&](const GraphDesc<RPL>& d, int& a_lo, int& a_hi) {
+    a_lo = d.e_lo & ~3;
+    a_hi = (d.e_hi + 3) & ~3;
+    return (a_hi - a_lo <= nnz_cap + 4) && (a_hi <= nnz_total);
+  };
+  auto issue = [&](int it, const GraphDesc<RPL>& d) {  // stage "c": TMA copies into stage[it & 1]
+    if (it >= n_it) return;
+    const int s = it & 1;
+    unsigned char* st = stage0 + (size_t)s * stage_bytes;
+    const uint32_t bar = smem_u32(&bars[s]);
+    const int n = d.r1 - d.r0;
+    const int64_t g = gw + (int64_t)it * stride;
+    int a_lo, a_hi;
+    const bool staged = staged_csr(d, a_lo, a_hi);
+    const bool copy_csr = staged && (d.e_hi > d.e_lo);
+    const uint32_t bytes = (uint32_t)n * F * 4 + th_bytes + (copy_csr ? 2u * (uint32_t)(a_hi - a_lo) * 4u : 0u);
+    fence_proxy_async();  // generic-proxy writes into this stage (even orders) before the TMA refills it
+    __syncwarp();         // every lane is done with this stage (used two graphs ago)
+    if (lane == 0) {  // one thread drives the TMA: 1 x-slab + 1 (or K) Theta + 2 CSR copies per graph
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_g2s(smem_u32(st), x + (size_t)d.r0 * F, (uint32_t)n * F * 4, bar);
+      if (theta_contig) {
+        bulk_g2s(smem_u32(st + TB), theta + g * sg, th_bytes, bar);
+      } else {
+        for (int k = 0; k < K; ++k)
+          bulk_g2s(smem_u32(st + TB + (size_t)k * F * F * 4), theta + g * sg + (int64_t)k * sk, F * F * 4, bar);
+      }
+      if (copy_csr) {
+        bulk_g2s(smem_u32(st + TB + th_bytes), colidx + a_lo, (uint32_t)(a_hi - a_lo) * 4, bar);
+        bulk_g2s(smem_u32(st + TB + th_bytes + csr_bytes), vals + a_lo, (uint32_t)(a_hi - a_lo) * 4, bar);
+      }
+    }
+  };
+
+  GraphDesc<RPL> d0, d1, d2, d3;
+  fetch_a(0, d0);
+  fetch_a(1, d1);
+  fetch_a(2, d2);
+  fetch_b(0, d0);
+  fetch_b(1, d1);
+  issue(0, d0);
+
+  for (int it = 0; it < n_it; ++it) {
+    fetch_a(it + 3, d3);
+    fetch_b(it + 2, d2);
+    issue(it + 1, d1);
+
+    // ---------------- compute graph `it` out of stage[it & 1]
+    const int s = it & 1;
+    unsigned char* st = stage0 + (size_t)s * stage_bytes;
+    float* T0 = reinterpret_cast<float*>(st);
+    const float* th = reinterpret_cast<const float*>(st + TB);
+    int a_lo, a_hi;
+    const bool staged = staged_csr(d0, a_lo, a_hi);
+    const int32_t* ci = staged ? reinterpret_cast<const int32_t*>(st + TB + th_bytes) - a_lo : colidx;
+    const float* cv = staged ? reinterpret_cast<const float*>(st + TB + th_bytes + csr_bytes) - a_lo : vals;
+    const int n = d0.r1 - d0.r0;
+    mbar_wait(smem_u32(&bars[s]), (uint32_t)((it >> 1) & 1));
+    if (lane == 0) bulk_wait_read0();  // the previous graph's output store has drained bufA
+    __syncwarp();
+
+    float2 acc[RPL][F / 2];
+    float t[F];
+#pragma unroll
+    for (int m = 0; m < RPL; ++m) {
+#pragma unroll
+      for (int i = 0; i < F / 2; ++i) acc[m][i] = make_float2(0.f, 0.f);
+      const int row = lane + 32 * m;
+      if (row < n) {
+#pragma unroll
+        for (int q = 0; q < F / 4; ++q) {
+          const float4 a = *reinterpret_cast<const float4*>(T0 + row * F + 4 * q);
+          t[4 * q] = a.x, t[4 * q + 1] = a.y, t[4 * q + 2] = a.z, t[4 * q + 3] = a.w;
+        }
+        apply_theta_s<F>(acc[m], t, th);  // k = 0
+      }
+    }
+    // even orders live in the (dense) stage buffer, odd orders in the padded bufA; T_k overwrites the
+    // own row of T_{k-2} (nobody else reads it any more)
+    for (int k = 1; k < K; ++k) {
+      const bool odd = (k & 1) != 0;
+#pragma unroll
+      for (int m = 0; m < RPL; ++m) {
+        const int row = lane + 32 * m;
+        if (row < n) {
+          if (odd) {
+            if (staged) gather_row_w<F, F, true>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            else gather_row_w<F, F, false>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+          } else {
+            if (staged) gather_row_w<F, LD, true>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            else gather_row_w<F, LD, false>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+          }
+          float* drow = odd ? bufA + row * LD : T0 + row * F;
+          if (k >= 2) {
+#pragma unroll
+            for (int q = 0; q < F / 4; ++q) {
+              const float4 o = *reinterpret_cast<const float4*>(drow + 4 * q);
+              t[4 * q] = fmaf(2.0f, t[4 * q], -o.x), t[4 * q + 1] = fmaf(2.0f, t[4 * q + 1], -o.y);
+              t[4 * q + 2] = fmaf(2.0f, t[4 * q + 2], -o.z), t[4 * q + 3] = fmaf(2.0f, t[4 * q + 3], -o.w);
+            }
+          }
+          if (k + 1 < K) {
+#pragma unroll
+            for (int q = 0; q < F / 4; ++q)
+              *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+          }
+          apply_theta_s<F>(acc[m], t, th + (size_t)k * F * F);
+        }
+      }
+      __syncwarp();
+    }
+    // epilogue: + bias, dense slab in bufA, one bulk store
+#pragma unroll
+    for (int m = 0; m < RPL; ++m) {
+      const int row = lane + 32 * m;
+      if (row < n) {
+#pragma unroll
+        for (int q = 0; q < F / 4; ++q)
+          *reinterpret_cast<float4*>(bufA + row * F + 4 * q) =
+              make_float4(acc[m][2 * q].x + bias_r[4 * q], acc[m][2 * q].y + bias_r[4 * q + 1],
+                          acc[m][2 * q + 1].x + bias_r[4 * q + 2], acc[m][2 * q + 1].y + bias_r[4 * q + 3]);
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(out + (size_t)d0.r0 * F, smem_u32(bufA), (uint32_t)n * F * 4);
+      bulk_commit();
+    }
+    d0 = d1;
+    d1 = d2;
+    d2 = d3;
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+}
+
+template <int F, int RPL>
+static int launch_warp(const WarpCfg& c, const float* x, const int32_t* rowptr, const int32_t* colidx,
+                       const float* vals, const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg,
+                       const float* bias, float* out, int64_t R, int64_t G, int K, int32_t* meta, int max_nodes,
+                       cudaStream_t st) {
+  FETA_CUDA(cudaFuncSetAttribute(cheb_fwd_warp_kernel<F, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)c.smem));
+  int64_t grid = ceil_div(G, c.warps);
+  if (grid > kNumSMs) grid = kNumSMs;
+  cheb_fwd_warp_kernel<F, RPL><<<(unsigned)grid, c.warps * 32, c.smem, st>>>(
+      x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, c.nnz_cap, c.rows_cap, (int)c.per_warp,
+      meta, max_nodes);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+
+// returns FETA_OK if launched, 1 if this shape is not eligible (caller falls back to the chunk kernel)
+int cheb_fwd_warp_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                      const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias,
+                      float* out, int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st) {
+  WarpCfg c = warp_config(F, K, max_nodes);
+  if (!c.ok) return 1;
+  if (((uintptr_t)colidx % 16) || ((uintptr_t)vals % 16)) return 1;
+#define FETA_WARP_CASE(F_, R_)                                                                                      \
+  if (F == F_ && c.rpl == R_)                                                                                       \
+    return launch_warp<F_, R_>(c, x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, meta,     \
+                               max_nodes, st);
+  FETA_WARP_CASE(4, 1) FETA_WARP_CASE(4, 2) FETA_WARP_CASE(8, 1) FETA_WARP_CASE(8, 2) FETA_WARP_CASE(16, 1)
+  FETA_WARP_CASE(16, 2)
+#undef FETA_WARP_CASE
+  return 1;
+}
+
+}  // namespace feta
