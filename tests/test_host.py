@@ -1,0 +1,182 @@
+"""CPU tests of the host-side logic: collate parity (bit exact), the C-ABI boundary (header <->
+ctypes <-> exported symbols, no compute calls), loud failure without a GPU, DDP plumbing under
+gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_batch, oracle_graphs
+import oracle.data as od
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["MUTAG", "ZINC", "PATTERN", "CLUSTER", "MOLHIV"])
+def test_collate_host_bit_exact_vs_reference_loops(name):
+    ids = np.array([5, 0, 9, 3, 3, 7])                                   # unordered, with a repeat
+    cfg, graphs, store, out = make_batch(name, 10, seed=7, ids=ids)
+    ogs = oracle_graphs([graphs[i] for i in ids], cfg['n_tags'])
+    fn = {'v2': od.collate_v2, 'sbm': od.collate_sbm, 'ogb': od.collate_v2}[cfg['kind']]
+    ref = fn(ogs, n_tags=cfg['n_tags'], n_features=store.n_features)
+    for i, (a, b) in enumerate(zip(out, ref)):
+        assert (a is None) == (b is None), i
+        if a is not None:
+            assert a.shape == b.shape and torch.equal(a.to(b.dtype), b), (name, i)
+    # integer outputs keep the reference dtypes
+    assert out[1].dtype == torch.bool and out[6].dtype == torch.int64 and out[8].dtype == torch.int64
+
+
+def test_collate_single_node_and_edgeless_graphs():
+    from feta_tmlr_b200 import data as fdata
+    graphs = [dict(x=np.zeros((1, 1), dtype=np.int64), edge_index=np.zeros((2, 0), dtype=np.int64),
+                   y=np.int64(0), degree=np.ones(1, dtype=np.float32), pe=None, lap_pe=None),
+              dict(x=np.ones((3, 1), dtype=np.int64), edge_index=np.array([[0, 1], [1, 0]]), y=np.int64(1),
+                   degree=np.ones(3, dtype=np.float32), pe=None, lap_pe=None)]
+    store = fdata.GraphStore(graphs, kind='v2', n_tags=2)
+    px, mask, pe, lap, deg, y, ei, bi, fi = fdata.collate_host(store, [0, 1])
+    assert mask.tolist() == [[False, True, True], [False, False, False]]
+    assert ei.tolist() == [[1, 2], [2, 1]] and bi.tolist() == [0, 1, 1, 1]
+    assert fi.tolist() == [[0, 0], [1, 0], [1, 1], [1, 2]]
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "feta_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|size_t|int64_t|const char\*)\s+(feta_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        out[m.group(1)] = n
+    return out
+
+
+def test_abi_header_ctypes_and_exports_agree():
+    """Every entry point include/feta_b200.h declares is exported by the .so and bound with the
+    right arity (no compute calls: this runs without a GPU)."""
+    from feta_tmlr_b200 import _lib
+    decl = _header_functions()
+    assert len(decl) >= 25
+    assert set(decl) == set(_lib.SIGNATURES), set(decl) ^ set(_lib.SIGNATURES)
+    for name, n in decl.items():
+        assert len(_lib.SIGNATURES[name][1]) == n, (name, n, len(_lib.SIGNATURES[name][1]))
+    lib = _lib.load()
+    for name in decl:
+        assert hasattr(lib, name)
+    assert lib.feta_version() >= 100
+    assert lib.feta_last_error_string() is not None
+    assert lib.feta_cheb_plan_workspace_bytes(100, 1000) > 0 and lib.feta_cheb_workspace_bytes(100, 16, 16, 4) > 0
+    # argument validation happens before any CUDA call: a NULL pointer is rejected with FETA_EINVAL
+    assert lib.feta_cheb_fwd(*([0] * 7), 0, 0, 0, 0, 0, 10, 1, 4, 16, 16, 8, 1, 0, 0, 0) == -1
+    assert b"NULL" in lib.feta_last_error_string()
+
+
+def test_sass_is_blackwell_native():
+    """The shipped binary is sm_100a SASS and uses TMA bulk copies + packed fp32x2 FMAs."""
+    so = os.path.join(ROOT, "feta_tmlr_b200", "libfeta_b200.so")
+    elf = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun",
+                           "_ZN4feta20cheb_fwd_warp_kernelILi16ELi2EEEvPKfPKiS4_S2_S4_S2_llS2_PflliiiiPii", so],
+                          capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "FFMA2" in sass and "SYNCS" in sass
+
+
+def test_no_cpu_fallback():
+    import feta_tmlr_b200 as f
+    m = f.ChebConvDynamic(4, 4, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(3, 4), torch.zeros((2, 0), dtype=torch.long), torch.zeros(2, 1, 4, 4), batch=torch.zeros(3))
+    layer = f.DiffTransformerEncoderLayer(8, 2, 16, 0.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        layer(torch.zeros(3, 1, 8), pe=None, degree=torch.ones(1, 3))
+    with pytest.raises(NotImplementedError):
+        f.ChebConvDynamic(4, 4, 2, aggr='mean')
+    with pytest.raises(NotImplementedError):
+        f.DiffTransformerEncoderGenGCN(8, 2, layer, 1, gnn_type='GENGCN')
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "feta_tmlr_b200")):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_state_dict_keys_match_reference_layout():
+    import feta_tmlr_b200 as f
+    m = f.DiffGraphTransformerGenGCNSBM(3, 2, 64, 4, 128, 0.0, 3)
+    keys = set(m.state_dict())
+    for k in ["embedding.weight", "encoder.layers.0.self_attn.in_proj_weight",
+              "encoder.layers.2.self_attn.out_proj.weight", "encoder.layers.1.linear1.weight",
+              "encoder.layers.1.norm2.bias", "encoder.spectral_gnns.bias", "encoder.gcn.weight",
+              "encoder.gcn.bias", "encoder.linear.weight", "encoder.linear_cat.weight", "classifier.2.bias"]:
+        assert k in keys, k
+    assert m.state_dict()["encoder.gcn.weight"].shape == (1024, 1024)    # ncoef = K * dh^2 (models.py:133)
+    lo = f.DiffTransformerEncoderGenGCN(64, 4, f.DiffTransformerEncoderLayer(64, 4, 128, 0.0), 2,
+                                        learn_only_filter_order_coeff=True)
+    assert lo.state_dict()["spectral_gnns.weight"].shape == (4, 16, 16)
+
+
+_DDP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from feta_tmlr_b200 import ddp
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+torch.manual_seed(rank)                       # replicas start different ...
+model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+ddp.broadcast_parameters(model)               # ... and are made identical
+bucket = ddp.FlatGradBucket(model.parameters())
+g = torch.Generator().manual_seed(0)
+X, Y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
+idx = list(ddp.shard_indices(8, rank, world))
+bucket.zero()
+((model(X[idx]) - Y[idx]) ** 2).sum().div(8).backward()
+flat_local = bucket.flat.clone()
+bucket.all_reduce_mean()
+# single-process reference on the full batch with rank 0's weights
+ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+ref.load_state_dict(model.state_dict())
+((ref(X) - Y) ** 2).sum().div(8).backward()
+ref_flat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+assert torch.allclose(bucket.flat * world, ref_flat, atol=1e-6), (bucket.flat * world - ref_flat).abs().max()
+assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_ddp_flat_bucket_gloo_world2(tmp_path):
+    script = tmp_path / "ddp_worker.py"
+    script.write_text(_DDP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+def test_shard_indices_cover_everything():
+    from feta_tmlr_b200 import ddp
+    for n, w in [(10, 3), (8, 8), (5, 8), (1024, 4)]:
+        parts = [list(ddp.shard_indices(n, r, w)) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--config", "MUTAG", "--batch", "4"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
