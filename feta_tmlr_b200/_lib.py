@@ -31,8 +31,8 @@ SIGNATURES = {
     "feta_attn_bwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P,
                               c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, _P]),
     "feta_coeff_scalar": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, _P]),
-    "feta_coeff_pool_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, _P]),
-    "feta_coeff_pool_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, _P]),
+    "feta_coeff_pool_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "feta_coeff_pool_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, _P]),
     "feta_pack_heads": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "feta_pack_heads_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "feta_unpack_heads": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),

@@ -69,14 +69,15 @@ __global__ void __launch_bounds__(kCoeffThreads) coeff_scalar_kernel(const float
 
 // pooled[g, c] = mean_{j in g} tanh(s_j * wbar[c] + gbias[c]);  grid (G, ceil(C / 256))
 __global__ void __launch_bounds__(kCoeffThreads) coeff_pool_fwd_kernel(const float* __restrict__ s,
-                                                                      const int32_t* __restrict__ graph_ptr,
+                                                                      const int32_t* __restrict__ seg_lo,
+                                                                      const int32_t* __restrict__ seg_hi,
                                                                       const float* __restrict__ wbar,
                                                                       const float* __restrict__ gbias,
                                                                       float* __restrict__ pooled, int C) {
   const int g = blockIdx.x;
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+  const int lo = seg_lo[g], hi = seg_hi[g];
   const float w = wbar[c], bb = gbias[c];
   float acc = 0.0f;
   for (int j = lo; j < hi; ++j) acc += tanhf(fmaf(__ldg(s + j), w, bb));
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(kCoeffThreads) coeff_pool_fwd_kernel(const flo
 
 // partial[bx, 0, c] = sum_{g = bx mod nblk} sum_j dpool[g,c]/n_g * (1 - t^2) * s_j ; [bx, 1, c] without s_j
 __global__ void __launch_bounds__(kCoeffThreads) coeff_pool_bwd_kernel(
-    const float* __restrict__ s, const int32_t* __restrict__ graph_ptr, const float* __restrict__ wbar,
+    const float* __restrict__ s, const int32_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_hi,
+    const float* __restrict__ wbar,
     const float* __restrict__ gbias, const float* __restrict__ d_pooled, float* __restrict__ partial, int64_t G,
     int C) {
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(kCoeffThreads) coeff_pool_bwd_kernel(
   const float w = wbar[c], bb = gbias[c];
   float aw = 0.0f, ab = 0.0f;
   for (int64_t g = blockIdx.x; g < G; g += gridDim.x) {
-    const int lo = graph_ptr[g], hi = graph_ptr[g + 1];
+    const int lo = seg_lo[g], hi = seg_hi[g];
     const int cnt = hi - lo;
     const float dg = d_pooled[(size_t)g * C + c] / (float)(cnt > 0 ? cnt : 1);
     float tw = 0.0f, tb = 0.0f;
@@ -146,27 +148,29 @@ extern "C" int feta_coeff_scalar(const float* attn, const uint8_t* mask, const i
   return FETA_OK;
 }
 
-extern "C" int feta_coeff_pool_fwd(const float* s, const int32_t* graph_ptr, const float* wbar, const float* gbias,
+extern "C" int feta_coeff_pool_fwd(const float* s, const int32_t* seg_lo, const int32_t* seg_hi, const float* wbar,
+                                   const float* gbias,
                                    float* pooled, int64_t G, int C, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(G >= 0 && C >= 1, "coeff_pool_fwd: bad sizes");
   if (G == 0) return FETA_OK;
-  FETA_REQUIRE(s && graph_ptr && wbar && gbias && pooled, "coeff_pool_fwd: NULL pointer argument");
+  FETA_REQUIRE(s && seg_lo && seg_hi && wbar && gbias && pooled, "coeff_pool_fwd: NULL pointer argument");
   dim3 grid((unsigned)G, (unsigned)ceil_div(C, kCoeffThreads));
-  coeff_pool_fwd_kernel<<<grid, kCoeffThreads, 0, st>>>(s, graph_ptr, wbar, gbias, pooled, C);
+  coeff_pool_fwd_kernel<<<grid, kCoeffThreads, 0, st>>>(s, seg_lo, seg_hi, wbar, gbias, pooled, C);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
 
-extern "C" int feta_coeff_pool_bwd(const float* s, const int32_t* graph_ptr, const float* wbar, const float* gbias,
+extern "C" int feta_coeff_pool_bwd(const float* s, const int32_t* seg_lo, const int32_t* seg_hi, const float* wbar,
+                                   const float* gbias,
                                    const float* d_pooled, float* d_wbar, float* d_gbias, float* partial, int nblk,
                                    int64_t G, int C, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(G >= 0 && C >= 1 && nblk >= 1, "coeff_pool_bwd: bad sizes");
-  FETA_REQUIRE(s && graph_ptr && wbar && gbias && d_pooled && d_wbar && d_gbias && partial,
+  FETA_REQUIRE(s && seg_lo && seg_hi && wbar && gbias && d_pooled && d_wbar && d_gbias && partial,
                "coeff_pool_bwd: NULL pointer argument");
   dim3 grid((unsigned)nblk, (unsigned)ceil_div(C, kCoeffThreads));
-  coeff_pool_bwd_kernel<<<grid, kCoeffThreads, 0, st>>>(s, graph_ptr, wbar, gbias, d_pooled, partial, G, C);
+  coeff_pool_bwd_kernel<<<grid, kCoeffThreads, 0, st>>>(s, seg_lo, seg_hi, wbar, gbias, d_pooled, partial, G, C);
   FETA_LAUNCH_CHECK();
   coeff_pool_bwd_final_kernel<<<(unsigned)ceil_div(C, kCoeffThreads), kCoeffThreads, 0, st>>>(partial, nblk, C,
                                                                                               d_wbar, d_gbias);

@@ -79,12 +79,23 @@ def _ranges(starts, lens):
     return np.arange(total, dtype=np.int64) - out_ptr[owner] + starts[owner], owner
 
 
-def collate_host(store, ids, device='cpu'):
-    """Vectorised restatement of GraphDataset_*.collate_fn (data.py:161-225 / :277-344 / :394-460)."""
+def collate_host(store, ids, device='cpu', static=None):
+    """Vectorised restatement of GraphDataset_*.collate_fn (data.py:161-225 / :277-344 / :394-460).
+
+    ``static=(nmax_cap, e_cap)`` (extension, for engine.GraphedTrainStep): pad the node axis to
+    ``nmax_cap`` instead of the batch maximum, pad ``edge_indices`` to ``e_cap`` columns with
+    (0, 0) self loops, and (node-level labels) return labels as ``[B, nmax_cap]`` with -100 in
+    padded slots -- every returned shape but batch_indices / feature_indices is then batch
+    independent."""
     ids = np.asarray(ids, dtype=np.int64)
     B = len(ids)
     lens, elens = store.sizes(ids)
     nmax = int(lens.max())
+    if static is not None:
+        if nmax > static[0] or int(elens.sum()) > static[1]:
+            raise ValueError("batch exceeds the static capacity: nmax %d > %d or E %d > %d"
+                             % (nmax, static[0], int(elens.sum()), static[1]))
+        nmax = int(static[0])
     src_rows, owner = _ranges(store.node_ptr[ids], lens)
     local = np.arange(len(owner), dtype=np.int64) - np.concatenate([[0], np.cumsum(lens)])[:-1][owner]
     padded_x = np.zeros((B, nmax, store.n_features), dtype=np.float32)
@@ -107,11 +118,20 @@ def collate_host(store, ids, device='cpu'):
     node_off = np.concatenate([[0], np.cumsum(lens)])[:-1]
     e_src, e_owner = _ranges(store.edge_ptr[ids], elens)
     edge_indices = store.edge_index[:, e_src] + node_off[e_owner][None, :]           # :219
+    if static is not None:
+        padded_e = np.zeros((2, int(static[1])), dtype=np.int64)
+        padded_e[:, :edge_indices.shape[1]] = edge_indices
+        edge_indices = padded_e
     batch_indices = owner.astype(np.int64)                                           # :220
     feature_indices = np.stack([owner, local], axis=1).astype(np.int64)              # :218
     if store.kind == 'sbm':
         y_rows, _ = _ranges(store.node_ptr[ids], lens)
-        labels = torch.from_numpy(store.y[y_rows])                                   # :457
+        if static is not None:
+            lab = np.full((B, nmax), -100, dtype=np.int64)
+            lab[owner, local] = store.y[y_rows]
+            labels = torch.from_numpy(lab)
+        else:
+            labels = torch.from_numpy(store.y[y_rows])                               # :457
     else:
         labels = torch.from_numpy(store.y[ids])                                      # default_collate
     t = torch.from_numpy

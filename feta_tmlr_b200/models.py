@@ -42,7 +42,8 @@ class GCNConv(nn.Module):
 
 class BatchContext(object):
     """Index structures of one mini-batch shared by every filtering layer of a forward pass."""
-    __slots__ = ("N", "B", "nmax", "H", "node_ptr", "batch_all_heads", "plan", "edge_index")
+    __slots__ = ("N", "B", "nmax", "H", "node_ptr", "batch_all_heads", "plan", "edge_index", "seg_lo", "seg_hi",
+                 "real")
 
 
 class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
@@ -176,6 +177,84 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         return output, attn, coeffs.permute([1, 0, 2])                              # :238
 
 
+    # ---------------------------------------------------------------------------------------
+    # Static-shape ("padded domain") variant of forward(): every tensor shape depends only on
+    # (B, Nmax, E_cap), never on the number of real nodes, so a whole training step can be captured
+    # in ONE CUDA graph and replayed on new mini-batches (engine.GraphedTrainStep).  Every padded
+    # slot (b, i) is treated as a node of graph b: padded slots carry x = 0, no edges, and are
+    # masked out of the coefficient pooling and of the scattered-back result, so real nodes get
+    # bit-for-bit the same arithmetic as forward().  `edge_index` holds the reference's packed
+    # node ids, padded to a fixed width with (0, 0) self loops (dropped by remove_self_loops,
+    # ChebNetDynamic.py:113).
+    def static_context(self, edge_index, masks, nmax):
+        ctx = BatchContext()
+        B, H = masks.shape[0], self.num_heads
+        dev = masks.device
+        ctx.N, ctx.B, ctx.nmax, ctx.H = B * nmax, B, nmax, H
+        lens = (~masks).sum(dim=1)
+        node_ptr = torch.cumsum(lens, dim=0)                                        # packed end offsets
+        starts = (torch.arange(B, device=dev) * nmax)
+        ctx.node_ptr = starts.to(torch.int32)                                       # slot offset of graph b
+        g = torch.arange(H * B, device=dev)
+        ctx.seg_lo = (g * nmax).to(torch.int32)
+        ctx.seg_hi = (g * nmax + lens.repeat(H)).to(torch.int32)
+        # packed node id -> padded slot id  (b * nmax + i)
+        b_of = torch.searchsorted(node_ptr, edge_index, right=True).clamp_(max=B - 1)
+        first = node_ptr - lens
+        ei = edge_index - first[b_of] + b_of * nmax
+        if self.tile_edges_per_head:
+            heads = torch.arange(H, device=dev, dtype=torch.int64)
+            ei = (ei.view(2, 1, -1) + (heads * B * nmax).view(1, H, 1)).reshape(2, -1)
+        ctx.edge_index = ei
+        ctx.batch_all_heads = torch.arange(H * B * nmax, device=dev, dtype=torch.int64) // nmax
+        ctx.plan = ops.build_cheb_plan(ei, ctx.batch_all_heads, H * B * nmax, H * B, 2.0,
+                                       hints={'max_nodes': int(nmax), 'block_diagonal': True})
+        ctx.real = (~masks).t().unsqueeze(-1).to(torch.float32)                     # [nmax, B, 1]
+        return ctx
+
+    def forward_static(self, src, pe, edge_index, degree, masks):
+        output = src
+        nmax, B, d = src.shape
+        H = self.num_heads
+        coefficients = []
+        allout_filtered = None
+        num_layers = len(self.layers)
+        ctx = None
+        attn = None
+        for layer_num, mod in enumerate(self.layers):
+            output, attn, out_each_head = mod(output, pe=pe, degree=degree, src_key_padding_mask=masks,
+                                              need_heads=True)
+            if self.last_layer_filter and layer_num + 1 != num_layers:
+                continue
+            if ctx is None:
+                ctx = self.static_context(edge_index, masks, nmax)
+            s = ops.coeff_scalar(attn, masks, ctx.node_ptr, B * nmax, zero_fill=True)
+            pooled = ops.coeff_pool(s, ctx.seg_lo, self.gcn.weight.sum(dim=0), self.gcn.bias, seg_hi=ctx.seg_hi)
+            coeff_all_heads = self.linear(pooled).reshape((H, B, -1))
+            coeff = coeff_all_heads.reshape((H * B, coeff_all_heads.shape[2]))
+            x = out_each_head.permute(2, 0, 1, 3).reshape(H * B * nmax, -1)          # padded-domain stacking
+            filtered = self.filter(coeff, None, ctx.edge_index, None, ctx.batch_all_heads,
+                                   self.spectral_gnns, x=x, plan=ctx.plan)
+            coefficients.append(coeff_all_heads)
+            out_filtered = filtered.reshape(H, B, nmax, -1).permute(2, 1, 0, 3).reshape(nmax, B, d) * ctx.real
+            if self.use_skip_conn:
+                allout_filtered = out_filtered if allout_filtered is None else allout_filtered + out_filtered
+            else:
+                allout_filtered = out_filtered
+                output = allout_filtered
+        if self.use_skip_conn:
+            if allout_filtered is not None:
+                output = self.linear_cat(torch.cat((output, allout_filtered), dim=-1))
+        else:
+            if allout_filtered is not None:
+                output = allout_filtered
+        if self.norm is not None:
+            output = self.norm(output)
+        coeffs = torch.cat(coefficients, dim=0) if coefficients else \
+            torch.empty((0, B, self.num_coefficients), device=src.device)
+        return output, attn, coeffs.permute([1, 0, 2])
+
+
 class GlobalAvg1D(nn.Module):
     """models.py:586-595 -- masked mean over the padded node axis, one kernel."""
 
@@ -243,6 +322,17 @@ class DiffGraphTransformerGenGCN(nn.Module):
         return self.classifier(output_pooled), filter_coeff_reg
 
 
+def _graph_head_forward_static(self, x, edge_index, masks, pe, x_lap_pos_enc=None, degree=None):
+    """Static-shape forward of the graph-level heads (same numbers as forward(); see
+    DiffTransformerEncoderGenGCN.forward_static).  Returns the classifier output only."""
+    output = self._embed(x, x_lap_pos_enc)
+    output, attn, filter_coeff = self.encoder.forward_static(output, pe, edge_index, degree, masks)
+    return self.classifier(self.pooling(output.permute(1, 0, 2), masks))
+
+
+DiffGraphTransformerGenGCN.forward_static = _graph_head_forward_static
+
+
 class DiffGraphTransformerGenGCNSBM(nn.Module):
     """models.py:1008-1076 (node-level head: PATTERN / CLUSTER)."""
 
@@ -284,6 +374,17 @@ class DiffGraphTransformerGenGCNSBM(nn.Module):
         if return_filter_coeff:
             return cls_output, filter_coeff_reg, filter_coeff
         return cls_output, filter_coeff_reg
+
+
+def _node_head_forward_static(self, x, edge_index, masks, pe, x_lap_pos_enc=None, degree=None):
+    """Static-shape forward of the node-level head: logits for EVERY padded slot [B, Nmax, C];
+    the caller's loss ignores padded slots (labels = -100) instead of gathering ``[~masks]``."""
+    output = self._embed(x, x_lap_pos_enc)
+    output, attn, filter_coeff = self.encoder.forward_static(output, pe, edge_index, degree, masks)
+    return self.classifier(output.permute(1, 0, 2))
+
+
+DiffGraphTransformerGenGCNSBM.forward_static = _node_head_forward_static
 
 
 class AtomEncoder(nn.Module):
@@ -376,3 +477,16 @@ class DiffGraphTransformerGenGCNMolHiv(nn.Module):
         if return_filter_coeff:
             return cls_out.squeeze(), filter_coeff_reg, self.sigmoid(cls_out).squeeze(), filter_coeff
         return cls_out.squeeze(), filter_coeff_reg, self.sigmoid(cls_out).squeeze()
+
+
+def _molhiv_forward_static(self, x, edge_index, masks, pe, x_lap_pos_enc=None, degree=None):
+    x_t = x.reshape([-1, x.shape[-1]])
+    output = self.embedding(x_t.to(torch.int64))
+    output = output.reshape([x.shape[0], x.shape[1], self.d_model]).permute(1, 0, 2)
+    if self.lap_pos_enc and x_lap_pos_enc is not None:
+        output = output + self.embedding_lap_pos_enc(x_lap_pos_enc.transpose(0, 1))
+    output, attn, filter_coeff = self.encoder.forward_static(output, pe, edge_index, degree, masks)
+    return self.classifier(self.pooling(output.permute(1, 0, 2), masks)).squeeze(-1)
+
+
+DiffGraphTransformerGenGCNMolHiv.forward_static = _molhiv_forward_static

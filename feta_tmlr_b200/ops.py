@@ -328,15 +328,17 @@ def diff_attention(qkv, pe, key_padding_mask, num_heads, scale, share_qk=False):
 # =====================================================================================
 # A4: filter-coefficient path
 # =====================================================================================
-def coeff_scalar(attn, key_padding_mask, node_ptr, num_nodes):
+def coeff_scalar(attn, key_padding_mask, node_ptr, num_nodes, zero_fill=False):
     """s [H*N]: the per-node scalar the all-ones GCN of models.py:280-282 reduces to.
-    Not differentiable (the reference detaches the attention, models.py:282)."""
+    Not differentiable (the reference detaches the attention, models.py:282).
+    ``zero_fill``: start from zeros (padded layouts, where masked positions own a slot)."""
     _need_cuda(attn, node_ptr)
     lib = _lib.load()
     attn = _f32c(attn.detach())
     B, H, nmax, _ = attn.shape
     mask_u8 = _mask_u8(key_padding_mask, B, nmax, attn.device)
-    s = torch.empty(H * int(num_nodes), dtype=torch.float32, device=attn.device)
+    alloc = torch.zeros if zero_fill else torch.empty
+    s = alloc(H * int(num_nodes), dtype=torch.float32, device=attn.device)
     check(lib.feta_coeff_scalar(_ptr(attn), _ptr(mask_u8), _ptr(node_ptr), _ptr(s), B, H, nmax,
                                 int(num_nodes), _stream()), "feta_coeff_scalar")
     return s
@@ -346,40 +348,43 @@ _POOL_BWD_BLOCKS = 148
 
 
 class CoeffPoolFn(torch.autograd.Function):
-    """pooled[g] = mean_{j in g} tanh(s_j * wbar + gbias)   (models.py:282-283 with x == 1)."""
+    """pooled[g] = mean_{j in [lo_g, hi_g)} tanh(s_j * wbar + gbias)   (models.py:282-283 with x == 1)."""
 
     @staticmethod
-    def forward(ctx, s, graph_ptr, wbar, gbias):
-        _need_cuda(s, graph_ptr, wbar, gbias)
+    def forward(ctx, s, seg_lo, seg_hi, wbar, gbias):
+        _need_cuda(s, seg_lo, seg_hi, wbar, gbias)
         lib = _lib.load()
         s, wbar, gbias = _f32c(s), _f32c(wbar), _f32c(gbias)
-        G = graph_ptr.numel() - 1
+        G = seg_lo.numel()
         C = wbar.numel()
         pooled = torch.empty((G, C), dtype=torch.float32, device=s.device)
-        check(lib.feta_coeff_pool_fwd(_ptr(s), _ptr(graph_ptr), _ptr(wbar), _ptr(gbias), _ptr(pooled), G, C,
-                                      _stream()), "feta_coeff_pool_fwd")
-        ctx.save_for_backward(s, graph_ptr, wbar, gbias)
+        check(lib.feta_coeff_pool_fwd(_ptr(s), _ptr(seg_lo), _ptr(seg_hi), _ptr(wbar), _ptr(gbias), _ptr(pooled),
+                                      G, C, _stream()), "feta_coeff_pool_fwd")
+        ctx.save_for_backward(s, seg_lo, seg_hi, wbar, gbias)
         return pooled
 
     @staticmethod
     def backward(ctx, d_pooled):
         lib = _lib.load()
-        s, graph_ptr, wbar, gbias = ctx.saved_tensors
-        G = graph_ptr.numel() - 1
+        s, seg_lo, seg_hi, wbar, gbias = ctx.saved_tensors
+        G = seg_lo.numel()
         C = wbar.numel()
         d_pooled = _f32c(d_pooled)
         nblk = max(1, min(_POOL_BWD_BLOCKS, G))
         partial = torch.empty((nblk, 2, C), dtype=torch.float32, device=s.device)
         d_w = torch.empty(C, dtype=torch.float32, device=s.device)
         d_b = torch.empty(C, dtype=torch.float32, device=s.device)
-        check(lib.feta_coeff_pool_bwd(_ptr(s), _ptr(graph_ptr), _ptr(wbar), _ptr(gbias), _ptr(d_pooled),
-                                      _ptr(d_w), _ptr(d_b), _ptr(partial), nblk, G, C, _stream()),
+        check(lib.feta_coeff_pool_bwd(_ptr(s), _ptr(seg_lo), _ptr(seg_hi), _ptr(wbar), _ptr(gbias),
+                                      _ptr(d_pooled), _ptr(d_w), _ptr(d_b), _ptr(partial), nblk, G, C, _stream()),
               "feta_coeff_pool_bwd")
-        return None, None, d_w, d_b
+        return None, None, None, d_w, d_b
 
 
-def coeff_pool(s, graph_ptr, wbar, gbias):
-    return CoeffPoolFn.apply(s, graph_ptr, wbar, gbias)
+def coeff_pool(s, graph_ptr, wbar, gbias, seg_hi=None):
+    """``graph_ptr`` [G+1] (packed plan) or, with ``seg_hi``, explicit [G] segment starts / ends."""
+    if seg_hi is None:
+        return CoeffPoolFn.apply(s, graph_ptr[:-1], graph_ptr[1:], wbar, gbias)
+    return CoeffPoolFn.apply(s, graph_ptr, seg_hi, wbar, gbias)
 
 
 # =====================================================================================

@@ -145,16 +145,18 @@ int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t stride
  *     s_j = deg_j^-1/2 * ( sum_{i != j} deg_i^-1/2 a_ij + deg_j^-1/2 loop_j )
  * (a = attn[b, h] restricted to real nodes; PyG-1.7 gcn_norm / add_remaining_self_loops).
  * feta_coeff_scalar writes s in stacked-row order  s[h*N + node_ptr[b] + j].
- * feta_coeff_pool_fwd:  pooled[g, c] = mean_{j in g} tanh(s_j * wbar[c] + gbias[c])  (:282-283),
- * g = h*B + b; feta_coeff_pool_bwd returns d wbar, d gbias (attention is detached, :282).
+ * feta_coeff_pool_fwd:  pooled[g, c] = mean_{j in [seg_lo[g], seg_hi[g])} tanh(s_j * wbar[c] + gbias[c])
+ * (:282-283), g = h*B + b; seg_lo/seg_hi are two int32 arrays of G entries (for a packed plan pass
+ * graph_ptr and graph_ptr + 1; a padded layout passes g*Nmax and g*Nmax + len_b).
+ * feta_coeff_pool_bwd returns d wbar, d gbias (attention is detached, :282).
  * --------------------------------------------------------------------------------------- */
 int feta_coeff_scalar(const float* attn /* [B,H,Nmax,Nmax] */, const uint8_t* mask /* [B,Nmax] */,
                       const int32_t* node_ptr /* [B+1] packed offsets of real nodes */,
                       float* s /* [H*N] */, int B, int H, int nmax, int64_t num_nodes, void* stream);
-int feta_coeff_pool_fwd(const float* s /* [R] */, const int32_t* graph_ptr /* [G+1] */,
+int feta_coeff_pool_fwd(const float* s /* [R] */, const int32_t* seg_lo /* [G] */, const int32_t* seg_hi /* [G] */,
                         const float* wbar /* [C] */, const float* gbias /* [C] */,
                         float* pooled /* [G, C] */, int64_t num_graphs, int C, void* stream);
-int feta_coeff_pool_bwd(const float* s, const int32_t* graph_ptr, const float* wbar,
+int feta_coeff_pool_bwd(const float* s, const int32_t* seg_lo, const int32_t* seg_hi, const float* wbar,
                         const float* gbias, const float* d_pooled /* [G, C] */,
                         float* d_wbar /* [C] */, float* d_gbias /* [C] */, float* partial /* [nblk, 2, C] */,
                         int nblk, int64_t num_graphs, int C, void* stream);
