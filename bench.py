@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--no-sweep", action="store_true", help="skip the HBM-sized Chebyshev kernel sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="override graphs per GPU per step")
+    ap.add_argument("--eager", action="store_true", help="eager autograd instead of the whole-step CUDA graph")
     ap.add_argument("--sweep-only", action="store_true", help="run only the HBM-sized Chebyshev sweep")
     ap.add_argument("--sweep-f", type=int, default=0, help="feature width for --sweep-only (default: config's dh)")
     ap.add_argument("--sweep-rows", type=int, default=6_000_000)
@@ -120,12 +121,14 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------
-def make_pool(name, cfg, B, n_batches, seed):
-    """Host-side pool of distinct mini-batches (reference collate tuple each)."""
-    from feta_tmlr_b200 import data as fdata, synthetic
+def make_pool(name, cfg, B, n_batches, seed, static=False):
+    """Host-side pool of distinct mini-batches (reference collate tuple each).  ``static``: pad every
+    batch to the dataset-wide (Nmax, E_cap) so one CUDA graph serves all of them."""
+    from feta_tmlr_b200 import data as fdata, engine, synthetic
     graphs = synthetic.make_dataset(name, B * n_batches, seed=seed)
     store = fdata.GraphStore(graphs, kind=cfg['kind'], n_tags=cfg['n_tags'])
-    return [fdata.collate_host(store, np.arange(i * B, (i + 1) * B))[:9] for i in range(n_batches)]
+    caps = engine.static_caps(store, B) if static else None
+    return [fdata.collate_host(store, np.arange(i * B, (i + 1) * B), static=caps)[:9] for i in range(n_batches)]
 
 
 def call_model(model, b):
@@ -256,33 +259,47 @@ def main():
         return 0
 
     # rotating pool of distinct batches whose device-resident total exceeds the 126 MB L2
-    probe = make_pool(args.config, cfg, B, 1, seed=1000 + rank)
-    per_batch = batch_nbytes(probe[0])
+    use_graph = not args.eager
+    probe = make_pool(args.config, cfg, B, 1, seed=1000 + rank, static=use_graph)
+    per_batch = batch_nbytes(probe[0][:7])
     n_pool = args.pool or int(min(256, max(8, np.ceil(160e6 / per_batch))))
-    pool_host = make_pool(args.config, cfg, B, n_pool, seed=rank)
+    pool_host = make_pool(args.config, cfg, B, n_pool, seed=rank, static=use_graph)
     pool_pinned = [tuple(None if t is None else t.pin_memory() for t in b) for b in pool_host]
     pool_dev = [tuple(None if t is None else t.to(dev) for t in b) for b in pool_host]
 
     torch.manual_seed(0)
     model = synthetic.build_model(args.config, fmodels).to(dev)
     ddp.broadcast_parameters(model)
-    bucket = ddp.FlatGradBucket(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
     lf = loss_fn_for(args.config)
-
-    def step(b):
-        bucket.zero()
-        loss = lf(call_model(model, b)[0], b[5])
-        loss.backward()
-        bucket.all_reduce_mean()
-        opt.step()
-        return loss
+    if cfg['head'] == 'node':
+        lf = lambda out, y: torch.nn.functional.cross_entropy(out.reshape(-1, out.shape[-1]), y.reshape(-1),
+                                                              ignore_index=-100) if use_graph else \
+            torch.nn.functional.cross_entropy(out, y.long())
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if use_graph:
+        from feta_tmlr_b200 import engine
+        eng = engine.GraphedTrainStep(model, lf, pool_dev[0], lr=1e-3, device=dev)
+        bucket = eng.bucket
+        step = eng.step                                   # copies the batch into static buffers + 1 graph launch
+        launches_per_step = eng.launches_per_step
+    else:
+        bucket = ddp.FlatGradBucket(model.parameters())
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+
+        def step(b):
+            bucket.zero()
+            loss = lf(call_model(model, b)[0], b[5])
+            loss.backward()
+            bucket.all_reduce_mean()
+            opt.step()
+            return loss
+        launches_per_step = None
 
     def timed(fn, K, W, offset=0):
         for i in range(W):
@@ -302,13 +319,12 @@ def main():
 
     # ---- leg 1: inputs resident in HBM
     sampler = ClockSampler(local_rank)
-    ops.enable_kernel_timer("cheb_fwd")
     if rank == 0:
         sampler.start()
     ms, launches = timed(lambda i: step(pool_dev[i % n_pool]), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    cheb_ms = ops.kernel_timer_ms("cheb_fwd")[-args.steps:]
-    ops.disable_kernel_timers()
+    if use_graph:
+        launches = launches_per_step * args.steps        # kernels replayed from the captured graph
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- leg 2: end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
@@ -316,34 +332,67 @@ def main():
 
     def e2e_step(i):
         hb = pool_pinned[i % n_pool]
-        b = tuple(None if t is None else t.to(dev, non_blocking=True) for t in hb)
-        loss = step(b)
-        d2h[0] = float(loss.detach().cpu())          # device -> host read of the step's result
+        if use_graph:
+            loss = step(hb)                               # H2D straight into the graph's static buffers
+        else:
+            loss = step(tuple(None if t is None else t.to(dev, non_blocking=True) for t in hb))
+        d2h[0] = float(loss.detach().cpu())              # device -> host read of the step's result
 
     ms_e2e, _ = timed(e2e_step, args.steps, args.warmup, offset=7)
     e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
-    h2d_bytes = int(np.mean([batch_nbytes(b) for b in pool_pinned]))
+    h2d_bytes = int(np.mean([batch_nbytes(b[:7]) for b in pool_pinned]))
+    if use_graph and eng.plan_guard_tripped():
+        raise RuntimeError("device-side plan guard tripped: static capacities do not cover a batch")
 
-    # ---- roofline of the fused Chebyshev kernel inside the step (+ the HBM-sized sweep)
+    # ---- leg 3 (rank 0, not part of value/e2e): the same step run eagerly with CUDA events around this
+    # repo's hot kernels, for the live roofline numbers (events cannot be recorded inside a graph replay)
+    kern_ms = {}
+    if rank == 0:
+        for nm in ("cheb_fwd", "attn_fwd", "attn_bwd"):
+            ops.enable_kernel_timer(nm)
+        opt_e = torch.optim.SGD(model.parameters(), lr=0.0)
+        for i in range(6):
+            b = pool_dev[(i * 5 + 3) % n_pool]
+            if use_graph:
+                loss = lf(model.forward_static(b[0], b[6], b[1], b[2], b[3], b[4]), b[5])
+            else:
+                loss = lf(call_model(model, b)[0], b[5])
+            loss.backward()
+            opt_e.zero_grad(set_to_none=False)
+        for nm in ("cheb_fwd", "attn_fwd", "attn_bwd"):
+            t = ops.kernel_timer_ms(nm)
+            kern_ms[nm] = float(np.mean(t[len(t) // 3:])) if t else float("nan")
+        ops.disable_kernel_timers()
+
+    # ---- roofline of this repo's dominant kernel inside the step (+ the HBM-sized Chebyshev sweep)
     line = None
     if rank == 0:
-        plan_rows = []
-        H = cfg['heads']
+        H, L = cfg['heads'], cfg['layers']
         dh = cfg['d_model'] // H
+        d = cfg['d_model']
+        cheb_rows, attn_rows = [], []
         for b in pool_dev[:min(n_pool, 8)]:
-            N, E = b[8].shape[0], b[6].shape[1]
+            real = ~b[1]
+            lens = real.sum(1).double()
+            N, sumsq = int(lens.sum()), float((lens * lens).sum())
             nnz = int((b[6][0] != b[6][1]).sum())
-            plan_rows.append(cheb_algorithmic_bytes(H * N, dh, nnz, H * B, 4))
-        alg_bytes = float(np.mean(plan_rows))
-        k_ms = float(np.mean(cheb_ms)) if cheb_ms else float("nan")
-        ach = alg_bytes / (k_ms * 1e-3) / 1e9
-        roofline = {"kernel": "cheb_fwd_fused_kernel<%d>" % dh, "bound": "hbm", "achieved": round(ach, 2),
-                    "peak": hbm_gbs, "unit": "GB/s", "frac": round(ach / hbm_gbs, 5), "traffic": None,
-                    "peak_source": peak_src, "algorithmic_bytes": int(alg_bytes),
-                    "us_per_launch": round(k_ms * 1e3, 2),
-                    "note": "in-step launch at the BASELINE config is %.2f MB, L2-resident and launch-latency "
-                            "bound (SURVEY.md F5); roofline_sweep is the same kernel on an HBM-sized batch"
-                            % (alg_bytes / 1e6)}
+            cheb_rows.append(cheb_algorithmic_bytes(H * N, dh, nnz, H * B, 4))
+            # q,k,v + pe + attn write + O
+            attn_rows.append(3 * 4 * N * d + (4 * sumsq if b[2] is not None else 0) + 4 * H * sumsq + 4 * N * d)
+        cheb_bytes, attn_bytes = float(np.mean(cheb_rows)), float(np.mean(attn_rows))
+
+        def roof(kernel, nbytes, ms_, launches_per_step_, note):
+            ach = nbytes / (ms_ * 1e-3) / 1e9
+            return {"kernel": kernel, "bound": "hbm", "achieved": round(ach, 2), "peak": hbm_gbs, "unit": "GB/s",
+                    "frac": round(ach / hbm_gbs, 5), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes": int(nbytes), "us_per_launch": round(ms_ * 1e3, 2),
+                    "launches_per_step": launches_per_step_, "note": note}
+        small = ("%.2f MB per launch: L2-resident and launch-latency bound at the BASELINE shape (SURVEY.md F5); "
+                 "timed with CUDA events around each launch in an eager pass of the same step")
+        roofline = roof("attn_fwd_kernel<%d>" % dh, attn_bytes, kern_ms.get("attn_fwd", float("nan")), L,
+                        "largest share of the step among this repo's kernels (profiles/); " + small % (attn_bytes / 1e6))
+        roofline_cheb = roof("cheb_fwd_warp_kernel<%d>" % dh, cheb_bytes, kern_ms.get("cheb_fwd", float("nan")), 1,
+                             small % (cheb_bytes / 1e6) + "; roofline_sweep is the same kernel on an HBM-sized batch")
         sweep = None
         if not args.no_sweep:
             try:
@@ -367,11 +416,14 @@ def main():
                            "l2": "inputs rotate through a pool of %d distinct device-resident batches "
                                  "(%.0f MB > 126 MB L2)" % (n_pool, n_pool * per_batch / 1e6),
                            "edges": "reference-faithful un-tiled edge_index (SURVEY.md F4)",
-                           "execution": "eager PyTorch autograd over C-ABI kernels, current stream"},
+                           "execution": ("whole training step captured once as ONE CUDA graph over static shapes "
+                                         "(engine.GraphedTrainStep), replayed per mini-batch") if use_graph else
+                           "eager PyTorch autograd over C-ABI kernels, current stream"},
                 "clocks": clocks,
                 "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
-                "gpu_launches": int(launches), "roofline": roofline, "roofline_sweep": sweep,
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_cheb_in_step": roofline_cheb,
+                "roofline_sweep": sweep,
                 "cpu_baseline": cpu_baseline, "last_loss": d2h[0]}
     if world > 1:
         dist.barrier()
