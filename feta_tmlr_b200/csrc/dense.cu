@@ -1,0 +1,265 @@
+// A6 (layer glue): the two token-axis reductions of DiffTransformerEncoderLayer's backward that
+// the stock libraries under-parallelise at FeTA's shapes (T = Nmax*B ~ 5k tokens, d = 64..192):
+//   * weight gradients  dW[out, in] = sum_t dY[t, out] X[t, in]  (+ db = sum_t dY[t])  -- cuBLAS picks a
+//     54-CTA SIMT sgemm taking 39 us (profiles/r1a_launches_eager_zinc.md); here the token axis is
+//     split over ~T/128 CTAs per output tile, partials reduced deterministically in a second pass;
+//   * residual-add + LayerNorm forward/backward with the gamma/beta gradients reduced across all
+//     SMs (PyTorch's GammaBetaBackward runs on 2 CTAs, 39 us).
+// These replace `F.linear` backward / `nn.LayerNorm` inside the layer the reference imports at
+// transformer/models.py:4 (residual + norm1 / FFN + norm2 of the GraphiT layer).
+#include "common.cuh"
+
+namespace feta {
+
+constexpr int kWgTile = 64, kWgTT = 32, kWgThreads = 256;
+
+__global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float* __restrict__ dY,
+                                                                  const float* __restrict__ X,
+                                                                  float* __restrict__ partial,
+                                                                  float* __restrict__ partial_db, int T, int out,
+                                                                  int in, int t_per_cta, int in_tiles) {
+  __shared__ __align__(16) float sA[kWgTT][kWgTile];
+  __shared__ __align__(16) float sB[kWgTT][kWgTile];
+  const int tile = blockIdx.x, s = blockIdx.y;
+  const int o0 = (tile / in_tiles) * kWgTile, i0 = (tile % in_tiles) * kWgTile;
+  const int t0 = s * t_per_cta, t1 = min(T, t0 + t_per_cta);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tt0 = t0; tt0 < t1; tt0 += kWgTT) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = threadIdx.x + kWgThreads * j;
+      const int row = idx >> 4, c4 = (idx & 15) * 4;
+      const int t = tt0 + row;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      if (t < t1) {
+        if (o0 + c4 < out) va = __ldg(reinterpret_cast<const float4*>(dY + (size_t)t * out + o0 + c4));
+        if (i0 + c4 < in) vb = __ldg(reinterpret_cast<const float4*>(X + (size_t)t * in + i0 + c4));
+      }
+      *reinterpret_cast<float4*>(&sA[row][c4]) = va;
+      *reinterpret_cast<float4*>(&sB[row][c4]) = vb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int tt = 0; tt < kWgTT; ++tt) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[tt][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sB[tt][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        dbacc[p] += av[p];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+      }
+    }
+    __syncthreads();
+  }
+  float* pt = partial + (size_t)s * out * in;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int o = o0 + ty * 4 + p;
+    if (o >= out) continue;
+    if (i0 + tx * 4 < in)
+      *reinterpret_cast<float4*>(pt + (size_t)o * in + i0 + tx * 4) =
+          make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+    if (partial_db != nullptr && i0 == 0 && tx == 0) partial_db[(size_t)s * out + o] = dbacc[p];
+  }
+}
+
+// out[e] = sum_s partial[s, e]
+__global__ void __launch_bounds__(256) slices_reduce_kernel(const float* __restrict__ partial, int S, int64_t n,
+                                                           float* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    float a = 0.0f;
+    for (int s = 0; s < S; ++s) a += partial[(size_t)s * n + e];
+    out[e] = a;
+  }
+}
+
+// ---------------------------------------------------------------- residual add + LayerNorm ----
+constexpr int kLnWarps = 8, kLnMaxPerLane = 8;  // D <= 256
+
+__global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_fwd_kernel(
+    const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ z, float* __restrict__ mean,
+    float* __restrict__ rstd, int64_t T, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= T) return;
+  float v[kLnMaxPerLane];
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxPerLane; ++j) {
+    const int c = lane + 32 * j;
+    v[j] = 0.0f;
+    if (c < D) {
+      v[j] = a[row * D + c] + (b ? b[row * D + c] : 0.0f);
+      s += v[j];
+    }
+  }
+  const float mu = warp_sum(s) / (float)D;
+  float q = 0.0f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxPerLane; ++j) {
+    const int c = lane + 32 * j;
+    if (c < D) q = fmaf(v[j] - mu, v[j] - mu, q);
+  }
+  const float rs = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+  for (int j = 0; j < kLnMaxPerLane; ++j) {
+    const int c = lane + 32 * j;
+    if (c < D) {
+      z[row * D + c] = v[j];
+      y[row * D + c] = (v[j] - mu) * rs * gamma[c] + beta[c];
+    }
+  }
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+}
+
+__global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
+    const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dz,
+    float* __restrict__ partial /* [grid, 2, D] */, int64_t T, int D) {
+  __shared__ float sg[kLnWarps][kLnMaxPerLane * 32];
+  __shared__ float sb[kLnWarps][kLnMaxPerLane * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float dg[kLnMaxPerLane], db[kLnMaxPerLane], gm[kLnMaxPerLane];
+#pragma unroll
+  for (int j = 0; j < kLnMaxPerLane; ++j) {
+    dg[j] = db[j] = 0.0f;
+    const int c = lane + 32 * j;
+    gm[j] = c < D ? gamma[c] : 0.0f;
+  }
+  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < T; row += (int64_t)gridDim.x * kLnWarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[kLnMaxPerLane], xh[kLnMaxPerLane];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kLnMaxPerLane; ++j) {
+      const int c = lane + 32 * j;
+      g[j] = xh[j] = 0.0f;
+      if (c < D) {
+        const float d = dy[row * D + c];
+        xh[j] = (z[row * D + c] - mu) * rs;
+        g[j] = d * gm[j];
+        s1 += g[j];
+        s2 = fmaf(g[j], xh[j], s2);
+        dg[j] = fmaf(d, xh[j], dg[j]);
+        db[j] += d;
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int j = 0; j < kLnMaxPerLane; ++j) {
+      const int c = lane + 32 * j;
+      if (c < D) dz[row * D + c] = rs * (g[j] - s1 - xh[j] * s2);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kLnMaxPerLane; ++j) {
+    sg[warp][lane + 32 * j] = dg[j];
+    sb[warp][lane + 32 * j] = db[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.0f, b = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) {
+      a += sg[w][c];
+      b += sb[w][c];
+    }
+    partial[((size_t)blockIdx.x * 2 + 0) * D + c] = a;
+    partial[((size_t)blockIdx.x * 2 + 1) * D + c] = b;
+  }
+}
+
+// dgamma[c] = sum_blk partial[blk, 0, c]; dbeta likewise
+__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial, int nblk, int D,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float a = 0.0f, b = 0.0f;
+  for (int k = 0; k < nblk; ++k) {
+    a += partial[((size_t)k * 2 + 0) * D + c];
+    b += partial[((size_t)k * 2 + 1) * D + c];
+  }
+  dgamma[c] = a;
+  dbeta[c] = b;
+}
+
+}  // namespace feta
+
+using namespace feta;
+
+extern "C" int feta_linear_wgrad_slices(int64_t T) { return (int)ceil_div(T > 0 ? T : 1, 128); }
+
+extern "C" int feta_linear_wgrad(const float* dY, const float* X, float* dW, float* db, float* partial,
+                                 size_t partial_floats, int64_t T, int out, int in, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  FETA_REQUIRE(T >= 0 && out >= 4 && in >= 4 && out % 4 == 0 && in % 4 == 0,
+               "linear_wgrad: needs out, in multiples of 4 (got %d, %d)", out, in);
+  FETA_REQUIRE(dW && partial && (T == 0 || (dY && X)), "linear_wgrad: NULL pointer argument");
+  FETA_REQUIRE(((uintptr_t)dY % 16 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)partial % 16 == 0),
+               "linear_wgrad: pointers must be 16-byte aligned");
+  const int S = feta_linear_wgrad_slices(T);
+  if (partial_floats < (size_t)S * ((size_t)out * in + out)) {
+    set_last_error("linear_wgrad: partial buffer too small (%zu < %zu floats)", partial_floats,
+                   (size_t)S * ((size_t)out * in + out));
+    return FETA_EWORKSPACE;
+  }
+  float* pdb = db ? partial + (size_t)S * out * in : nullptr;
+  const int out_tiles = (int)ceil_div(out, kWgTile), in_tiles = (int)ceil_div(in, kWgTile);
+  dim3 grid((unsigned)(out_tiles * in_tiles), (unsigned)S);
+  wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(dY, X, partial, pdb, (int)T, out, in, 128, in_tiles);
+  FETA_LAUNCH_CHECK();
+  const int64_t n = (int64_t)out * in;
+  slices_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, S, n, dW);
+  FETA_LAUNCH_CHECK();
+  if (db) {
+    slices_reduce_kernel<<<(unsigned)ceil_div(out, 256), 256, 0, st>>>(pdb, S, out, db);
+    FETA_LAUNCH_CHECK();
+  }
+  return FETA_OK;
+}
+
+extern "C" int feta_add_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* y,
+                                      float* z, float* mean, float* rstd, int64_t T, int D, float eps, void* stream_) {
+  FETA_REQUIRE(T >= 0 && D >= 1 && D <= kLnMaxPerLane * 32, "add_layernorm: D=%d not in [1, %d]", D,
+               kLnMaxPerLane * 32);
+  if (T == 0) return FETA_OK;
+  FETA_REQUIRE(a && gamma && beta && y && z && mean && rstd, "add_layernorm_fwd: NULL pointer argument");
+  add_layernorm_fwd_kernel<<<(unsigned)ceil_div(T, kLnWarps), kLnWarps * 32, 0, (cudaStream_t)stream_>>>(
+      a, b, gamma, beta, y, z, mean, rstd, T, D, eps);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+
+extern "C" int feta_add_layernorm_bwd_blocks(int64_t T) {
+  int64_t b = ceil_div(T > 0 ? T : 1, kLnWarps * 4);
+  return (int)(b < 2 * kNumSMs ? b : 2 * kNumSMs);
+}
+
+extern "C" int feta_add_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
+                                      const float* gamma, float* dz, float* dgamma, float* dbeta, float* partial,
+                                      int64_t T, int D, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  FETA_REQUIRE(T >= 0 && D >= 1 && D <= kLnMaxPerLane * 32, "add_layernorm: D=%d not in [1, %d]", D,
+               kLnMaxPerLane * 32);
+  FETA_REQUIRE(dgamma && dbeta && partial && (T == 0 || (dy && z && mean && rstd && gamma && dz)),
+               "add_layernorm_bwd: NULL pointer argument");
+  const int nblk = feta_add_layernorm_bwd_blocks(T);
+  add_layernorm_bwd_kernel<<<nblk, kLnWarps * 32, 0, st>>>(dy, z, mean, rstd, gamma, dz, partial, T, D);
+  FETA_LAUNCH_CHECK();
+  ln_param_reduce_kernel<<<(unsigned)ceil_div(D, 256), 256, 0, st>>>(partial, nblk, D, dgamma, dbeta);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}

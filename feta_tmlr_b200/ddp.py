@@ -15,16 +15,21 @@ import torch.distributed as dist
 class FlatGradBucket(object):
     """Makes every ``p.grad`` a view into one contiguous buffer and averages it across ranks."""
 
-    def __init__(self, params, process_group=None):
+    def __init__(self, params, process_group=None, attach=True):
+        """``attach=False``: only build the flat buffer and its per-parameter views (``self.views``);
+        the caller copies gradients in with one multi-tensor copy (engine.GraphedTrainStep)."""
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
         total = sum(p.numel() for p in self.params)
         dev, dtype = self.params[0].device, self.params[0].dtype
         self.flat = torch.zeros(total, dtype=dtype, device=dev)
         off = 0
+        self.views = []
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)      # autograd accumulates in place
+            self.views.append(self.flat[off:off + n].view_as(p))
+            if attach:
+                p.grad = self.views[-1]                      # autograd accumulates in place
             off += n
 
     def zero(self):

@@ -34,7 +34,10 @@ class GraphedTrainStep(object):
         px, mask, pe, lap, deg, labels, ei = example_batch[:7]
         self.static = [None if t is None else torch.empty_like(t, device=dev) for t in
                        (px, mask, pe, lap, deg, labels, ei)]
-        self.bucket = ddp.FlatGradBucket(model.parameters())
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
+                                                           torch.distributed.is_initialized()) else 1
+        self.bucket = ddp.FlatGradBucket(self.params, attach=False)
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, fused=True, capturable=True)
         self.loss = None
         self.launches_per_step = 0
@@ -54,11 +57,17 @@ class GraphedTrainStep(object):
 
     def _body(self):
         px, mask, pe, lap, deg, labels, ei = self.static
-        self.bucket.zero()
+        for p in self.params:
+            p.grad = None                       # autograd then WRITES each gradient (no += kernels)
         out = self.model.forward_static(px, ei, mask, pe, lap, deg)
         loss = self.loss_fn(out, labels)
         loss.backward()
-        self.bucket.all_reduce_mean()
+        if self.world > 1:                      # one flat all-reduce; the optimizer reads the flat views
+            live = [(p, v) for p, v in zip(self.params, self.bucket.views) if p.grad is not None]
+            torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])
+            self.bucket.all_reduce_mean()
+            for p, v in live:
+                p.grad = v
         self.opt.step()
         self.loss = loss.detach()
 

@@ -18,6 +18,14 @@ import torch.nn.functional as F
 from . import ops
 
 
+class Linear(nn.Linear):
+    """``nn.Linear`` (same parameters / state_dict keys) whose weight and bias gradients are reduced
+    over the token axis by csrc/dense.cu instead of a 54-CTA SIMT sgemm."""
+
+    def forward(self, x):
+        return ops.linear(x, self.weight, self.bias)
+
+
 class DiffMultiheadAttention(nn.Module):
     def __init__(self, embed_dim, num_heads, dropout=0.0, bias=False, share_qk=False):
         super().__init__()
@@ -32,7 +40,7 @@ class DiffMultiheadAttention(nn.Module):
             self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
         else:
             self.register_parameter('in_proj_bias', None)
-        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.out_proj = Linear(embed_dim, embed_dim, bias=bias)
         nn.init.xavier_uniform_(self.in_proj_weight)
         if bias:
             nn.init.constant_(self.out_proj.bias, 0.0)
@@ -44,7 +52,7 @@ class DiffMultiheadAttention(nn.Module):
                                       "not implemented in the fused kernel (all reference drivers "
                                       "default to --dropout 0.0)")
         N, B, E = src.shape
-        qkv = F.linear(src, self.in_proj_weight, self.in_proj_bias)          # library GEMM
+        qkv = ops.linear(src, self.in_proj_weight, self.in_proj_bias)        # library GEMM (+ own wgrad)
         attn, heads = ops.diff_attention(qkv, pe, key_padding_mask, self.num_heads,
                                          float(self.head_dim) ** -0.5, self.share_qk)
         o = heads.view(B, N, E).transpose(0, 1)                              # concat heads, seq-first
@@ -60,9 +68,9 @@ class DiffTransformerEncoderLayer(nn.Module):
         super().__init__()
         self.self_attn = DiffMultiheadAttention(d_model, nhead, dropout=dropout, bias=attn_bias,
                                                 share_qk=share_qk)
-        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear1 = Linear(d_model, dim_feedforward)
         self.dropout = nn.Dropout(dropout)
-        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.linear2 = Linear(dim_feedforward, d_model)
         self.batch_norm = batch_norm
         if batch_norm:
             self.norm1 = nn.BatchNorm1d(d_model)
@@ -91,16 +99,19 @@ class DiffTransformerEncoderLayer(nn.Module):
                 self.scaling = 1. / pe.diagonal(dim1=1, dim2=2).max().item()
             src2 = (self.scaling * pe.diagonal(dim1=1, dim2=2)).transpose(0, 1) \
                 .contiguous().unsqueeze(-1) * src2
-        src = src + self.dropout1(src2)
         if self.batch_norm:
+            src = src + self.dropout1(src2)
             bsz = src.shape[1]
             src = src.reshape(-1, src.shape[-1])
-        src = self.norm1(src)
-        src2 = self.linear2(self.dropout(F.relu(self.linear1(src))))
-        src = src + self.dropout2(src2)
-        src = self.norm2(src)
-        if self.batch_norm:
+            src = self.norm1(src)
+            src2 = self.linear2(self.dropout(F.relu(self.linear1(src))))
+            src = src + self.dropout2(src2)
+            src = self.norm2(src)
             src = src.view(-1, bsz, src.shape[-1])
+        else:                                    # residual add fused into the LayerNorm kernels
+            src = ops.add_layer_norm(src, self.dropout1(src2), self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            src2 = self.linear2(self.dropout(F.relu(self.linear1(src))))
+            src = ops.add_layer_norm(src, self.dropout2(src2), self.norm2.weight, self.norm2.bias, self.norm2.eps)
         if need_heads:
             return src, attn, heads
         return src, attn

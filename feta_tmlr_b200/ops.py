@@ -565,3 +565,90 @@ class GatherRowsFn(torch.autograd.Function):
 
 def gather_rows(padded, feature_indices):
     return GatherRowsFn.apply(padded, _fi64(feature_indices))
+
+
+# =====================================================================================
+# A6 layer glue: token-axis reductions (weight gradients, LayerNorm)
+# =====================================================================================
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b.  Forward and dX are library GEMMs; dW / db (reductions over the ~5k-token axis
+    the libraries under-parallelise here) go through feta_linear_wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, weight = ctx.saved_tensors
+        out_f, in_f = weight.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = dy.matmul(weight)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dy2 = _f32c(dy.reshape(-1, out_f))
+            x2 = _f32c(x.reshape(-1, in_f))
+            T = dy2.shape[0]
+            if out_f % 4 or in_f % 4:
+                dw = dy2.t().matmul(x2)
+                db = dy2.sum(0) if ctx.has_bias else None
+            else:
+                S = lib.feta_linear_wgrad_slices(T)
+                n_part = S * (out_f * in_f + out_f)
+                partial = torch.empty(n_part, dtype=torch.float32, device=dy.device)
+                dw = torch.empty((out_f, in_f), dtype=torch.float32, device=dy.device)
+                db = torch.empty(out_f, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+                check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part, T,
+                                            out_f, in_f, _stream()), "feta_linear_wgrad")
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    _need_cuda(x, weight, bias)
+    return LinearFn.apply(x, weight, bias)
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(a + b) * gamma + beta  (residual + norm1 / norm2 of the layer), one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, a, b, gamma, beta, eps):
+        _need_cuda(a, b, gamma, beta)
+        lib = _lib.load()
+        a = _f32c(a)
+        b = None if b is None else _f32c(b)
+        D = a.shape[-1]
+        T = a.numel() // D
+        y = torch.empty_like(a)
+        z = torch.empty_like(a)
+        mean = torch.empty(T, dtype=torch.float32, device=a.device)
+        rstd = torch.empty(T, dtype=torch.float32, device=a.device)
+        gamma, beta = _f32c(gamma), _f32c(beta)
+        check(lib.feta_add_layernorm_fwd(_ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(z), _ptr(mean),
+                                         _ptr(rstd), T, D, float(eps), _stream()), "feta_add_layernorm_fwd")
+        ctx.save_for_backward(z, mean, rstd, gamma)
+        ctx.has_b = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        z, mean, rstd, gamma = ctx.saved_tensors
+        D = z.shape[-1]
+        T = z.numel() // D
+        dy = _f32c(dy)
+        dz = torch.empty_like(z)
+        nblk = lib.feta_add_layernorm_bwd_blocks(T)
+        partial = torch.empty(nblk * 2 * D, dtype=torch.float32, device=z.device)
+        dg = torch.empty(D, dtype=torch.float32, device=z.device)
+        db = torch.empty(D, dtype=torch.float32, device=z.device)
+        check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dz), _ptr(dg),
+                                         _ptr(db), _ptr(partial), T, D, _stream()), "feta_add_layernorm_bwd")
+        return dz, (dz if ctx.has_b else None), dg, db, None
+
+
+def add_layer_norm(a, b, gamma, beta, eps=1e-5):
+    return AddLayerNormFn.apply(a, b, gamma, beta, eps)

@@ -139,6 +139,27 @@ int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t stride
                   int64_t dstride_b, int B, int H, int nmax, int dh, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * A6 (layer glue)  token-axis reductions of the layer's backward (the residual + norm1 / FFN +
+ * norm2 part of the layer transformer/models.py:4 imports; torch F.linear / nn.LayerNorm in the
+ * reference's upstream).  T = Nmax*B tokens.
+ *   feta_linear_wgrad:  dW[out,in] = sum_t dY[t,out] X[t,in],  db[out] = sum_t dY[t,out] (db may be
+ *     NULL).  dY [T,out], X [T,in] contiguous, 16-byte aligned, out/in multiples of 4.  `partial`
+ *     needs feta_linear_wgrad_slices(T) * (out*in + out) floats.  Deterministic (two-pass).
+ *   feta_add_layernorm_fwd:  z = a + b (b may be NULL), y = LayerNorm(z) * gamma + beta; saves z, mean,
+ *     rstd [T] for the backward.  D <= 256.
+ *   feta_add_layernorm_bwd:  dz (gradient of both a and b), dgamma, dbeta; `partial` needs
+ *     feta_add_layernorm_bwd_blocks(T) * 2 * D floats.
+ * --------------------------------------------------------------------------------------- */
+int feta_linear_wgrad_slices(int64_t T);
+int feta_linear_wgrad(const float* dY, const float* X, float* dW, float* db, float* partial, size_t partial_floats,
+                      int64_t T, int out, int in, void* stream);
+int feta_add_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* y, float* z,
+                           float* mean, float* rstd, int64_t T, int D, float eps, void* stream);
+int feta_add_layernorm_bwd_blocks(int64_t T);
+int feta_add_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                           float* dz, float* dgamma, float* dbeta, float* partial, int64_t T, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * A4  DiffTransformerEncoderGenGCN.get_filter_coefficients (transformer/models.py:240-287).
  * With x == 1 the all-pairs GCNConv of :280-282 is  s_j * colsum(W) + b  with a per-node scalar
  *     loop_j = a_jj != 0 ? a_jj : 1;  deg_j = sum_{i != j} a_ij + loop_j;
