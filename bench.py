@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--no-sweep", action="store_true", help="skip the HBM-sized Chebyshev kernel sweep")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="override graphs per GPU per step")
+    ap.add_argument("--quick", action="store_true", help="leg 1 only (profiling runs)")
     ap.add_argument("--eager", action="store_true", help="eager autograd instead of the whole-step CUDA graph")
     ap.add_argument("--sweep-only", action="store_true", help="run only the HBM-sized Chebyshev sweep")
     ap.add_argument("--sweep-f", type=int, default=0, help="feature width for --sweep-only (default: config's dh)")
@@ -327,6 +328,11 @@ def main():
         launches = launches_per_step * args.steps        # kernels replayed from the captured graph
     value = world * B * args.steps / (ms * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": round(value, 1), "ms_per_step": round(ms / args.steps, 4),
+                              "quick": True}))
+        return 0
     # ---- leg 2: end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     d2h = [0]
 

@@ -40,7 +40,8 @@ template <int DH, int NCH>
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
     const float* __restrict__ pe, const uint8_t* __restrict__ mask, float* __restrict__ attn,
-    float* __restrict__ o_heads, float* __restrict__ rowflag, int H, int nmax, float scale) {
+    float* __restrict__ o_heads, int64_t osn, int64_t osb, float* __restrict__ rowflag, int H, int nmax,
+    float scale) {
   extern __shared__ float smem[];
   __shared__ int s_neff;
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
     const int i = i0 + ii;
     if (i >= nmax) break;
     float* arow = attn + (((size_t)b * H + h) * nmax + i) * nmax;
-    float* orow = o_heads + (((size_t)b * nmax + i) * H + h) * DH;
+    float* orow = o_heads + (int64_t)i * osn + (int64_t)b * osb + h * DH;
     if (mk[i]) {  // padded query: defined as zero (never consumed by the model)
       for (int j = lane; j < nmax; j += 32) arow[j] = 0.0f;
       if (lane < DH) orow[lane] = 0.0f;
@@ -150,8 +151,9 @@ template <int DH, int NCH>
 __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
     const uint8_t* __restrict__ mask, const float* __restrict__ attn, const float* __restrict__ rowflag,
-    const float* __restrict__ d_o, const float* __restrict__ d_attn, float* __restrict__ dq, float* __restrict__ dk,
-    float* __restrict__ dv, int64_t dsn, int64_t dsb, int H, int nmax, float scale) {
+    const float* __restrict__ d_o, int64_t osn, int64_t osb, const float* __restrict__ d_attn,
+    float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int64_t dsn, int64_t dsb, int H, int nmax,
+    float scale) {
   extern __shared__ float smem[];
   __shared__ int s_neff;
   __shared__ int s_valid[kAttnWarps];
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(
       kk = __ldg(k + base_in + (int64_t)j * sn + c);
       vv = __ldg(v + base_in + (int64_t)j * sn + c);
       qq = __ldg(q + base_in + (int64_t)j * sn + c);
-      dd = __ldg(d_o + (((size_t)b * nmax + j) * H + h) * DH + c);
+      dd = __ldg(d_o + (int64_t)j * osn + (int64_t)b * osb + h * DH + c);
     }
     Vt[c * npad + j] = vv;
     Ks[idx] = kk;
@@ -285,26 +287,26 @@ static size_t attn_bwd_smem(int dh, int nmax) {
 
 template <int DH, int NCH>
 static int launch_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
-                           const uint8_t* mask, float* attn, float* o_heads, float* rowflag, int B, int H, int nmax,
-                           float scale, cudaStream_t st) {
+                           const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag,
+                           int B, int H, int nmax, float scale, cudaStream_t st) {
   const size_t smem = attn_fwd_smem(DH, nmax);
   FETA_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)ceil_div(nmax, kRowsPerCta), (unsigned)(B * H));
-  attn_fwd_kernel<DH, NCH><<<grid, kAttnThreads, smem, st>>>(q, k, v, sn, sb, pe, mask, attn, o_heads, rowflag, H,
-                                                             nmax, scale);
+  attn_fwd_kernel<DH, NCH><<<grid, kAttnThreads, smem, st>>>(q, k, v, sn, sb, pe, mask, attn, o_heads, osn, osb,
+                                                             rowflag, H, nmax, scale);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
 template <int DH, int NCH>
 static int launch_attn_bwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
                            const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o,
-                           const float* d_attn, float* dq, float* dk, float* dv, int64_t dsn, int64_t dsb, int B,
-                           int H, int nmax, float scale, cudaStream_t st) {
+                           int64_t osn, int64_t osb, const float* d_attn, float* dq, float* dk, float* dv, int64_t dsn,
+                           int64_t dsb, int B, int H, int nmax, float scale, cudaStream_t st) {
   const size_t smem = attn_bwd_smem(DH, nmax);
   FETA_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attn_bwd_kernel<DH, NCH><<<(unsigned)(B * H), kAttnThreads, smem, st>>>(q, k, v, sn, sb, mask, attn, rowflag, d_o,
-                                                                          d_attn, dq, dk, dv, dsn, dsb, H, nmax,
-                                                                          scale);
+                                                                          osn, osb, d_attn, dq, dk, dv, dsn, dsb, H,
+                                                                          nmax, scale);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
@@ -332,8 +334,8 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, int64
 using namespace feta;
 
 extern "C" int feta_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
-                             const uint8_t* mask, float* attn, float* o_heads, float* rowflag, int B, int H, int nmax,
-                             int dh, float scale, void* stream_) {
+                             const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag,
+                             int B, int H, int nmax, int dh, float scale, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && dh >= 1, "attn_fwd: bad sizes");
   if (B == 0 || nmax == 0) return FETA_OK;
@@ -343,15 +345,16 @@ extern "C" int feta_attn_fwd(const float* q, const float* k, const float* v, int
                    attn_fwd_smem(dh, nmax));
     return FETA_EUNSUPPORTED;
   }
-  FETA_ATTN_DISPATCH(launch_attn_fwd, q, k, v, sn, sb, pe, mask, attn, o_heads, rowflag, B, H, nmax, scale, st);
+  FETA_ATTN_DISPATCH(launch_attn_fwd, q, k, v, sn, sb, pe, mask, attn, o_heads, osn, osb, rowflag, B, H, nmax, scale,
+                     st);
   set_last_error("attn_fwd: head dim %d not in {4,8,16,32,64}", dh);
   return FETA_EUNSUPPORTED;
 }
 
 extern "C" int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
                              const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o_heads,
-                             const float* d_attn, float* dq, float* dk, float* dv, int64_t dsn, int64_t dsb, int B,
-                             int H, int nmax, int dh, float scale, void* stream_) {
+                             int64_t osn, int64_t osb, const float* d_attn, float* dq, float* dk, float* dv,
+                             int64_t dsn, int64_t dsb, int B, int H, int nmax, int dh, float scale, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && dh >= 1, "attn_bwd: bad sizes");
   if (B == 0 || nmax == 0) return FETA_OK;
@@ -362,8 +365,8 @@ extern "C" int feta_attn_bwd(const float* q, const float* k, const float* v, int
                    attn_bwd_smem(dh, nmax));
     return FETA_EUNSUPPORTED;
   }
-  FETA_ATTN_DISPATCH(launch_attn_bwd, q, k, v, sn, sb, mask, attn, rowflag, d_o_heads, d_attn, dq, dk, dv, dsn, dsb, B,
-                     H, nmax, scale, st);
+  FETA_ATTN_DISPATCH(launch_attn_bwd, q, k, v, sn, sb, mask, attn, rowflag, d_o_heads, osn, osb, d_attn, dq, dk, dv,
+                     dsn, dsb, B, H, nmax, scale, st);
   set_last_error("attn_bwd: head dim %d not in {4,8,16,32,64}", dh);
   return FETA_EUNSUPPORTED;
 }

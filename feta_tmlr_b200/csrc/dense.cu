@@ -30,21 +30,32 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float* 
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int tt0 = t0; tt0 < t1; tt0 += kWgTT) {
+  // register-staged prefetch: the next 32-token tile is in flight while the current one is consumed
+  float4 ra[2], rb[2];
+  auto fetch = [&](int tt0) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int idx = threadIdx.x + kWgThreads * j;
       const int row = idx >> 4, c4 = (idx & 15) * 4;
       const int t = tt0 + row;
-      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      ra[j] = rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t < t1) {
-        if (o0 + c4 < out) va = __ldg(reinterpret_cast<const float4*>(dY + (size_t)t * out + o0 + c4));
-        if (i0 + c4 < in) vb = __ldg(reinterpret_cast<const float4*>(X + (size_t)t * in + i0 + c4));
+        if (o0 + c4 < out) ra[j] = __ldg(reinterpret_cast<const float4*>(dY + (size_t)t * out + o0 + c4));
+        if (i0 + c4 < in) rb[j] = __ldg(reinterpret_cast<const float4*>(X + (size_t)t * in + i0 + c4));
       }
-      *reinterpret_cast<float4*>(&sA[row][c4]) = va;
-      *reinterpret_cast<float4*>(&sB[row][c4]) = vb;
+    }
+  };
+  fetch(t0);
+  for (int tt0 = t0; tt0 < t1; tt0 += kWgTT) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = threadIdx.x + kWgThreads * j;
+      const int row = idx >> 4, c4 = (idx & 15) * 4;
+      *reinterpret_cast<float4*>(&sA[row][c4]) = ra[j];
+      *reinterpret_cast<float4*>(&sB[row][c4]) = rb[j];
     }
     __syncthreads();
+    if (tt0 + kWgTT < t1) fetch(tt0 + kWgTT);
 #pragma unroll 8
     for (int tt = 0; tt < kWgTT; ++tt) {
       const float4 a = *reinterpret_cast<const float4*>(&sA[tt][ty * 4]);
@@ -71,34 +82,46 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float* 
   }
 }
 
-// out[e] = sum_s partial[s, e]
-__global__ void __launch_bounds__(256) slices_reduce_kernel(const float* __restrict__ partial, int S, int64_t n,
-                                                           float* __restrict__ out) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    float a = 0.0f;
-    for (int s = 0; s < S; ++s) a += partial[(size_t)s * n + e];
-    out[e] = a;
+// dW[e] = sum_s partial[s, e] over float4 elements; slices summed in order (deterministic), loads unrolled
+__global__ void __launch_bounds__(128) slices_reduce4_kernel(const float4* __restrict__ partial, int S, int64_t n4,
+                                                            float4* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n4) return;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int k = 0;
+  for (; k + 8 <= S; k += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(partial + (size_t)(k + u) * n4 + e);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a.x += v[u].x, a.y += v[u].y, a.z += v[u].z, a.w += v[u].w;
   }
+  for (; k < S; ++k) {
+    const float4 v = __ldg(partial + (size_t)k * n4 + e);
+    a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+  }
+  out[e] = a;
 }
 
 // ---------------------------------------------------------------- residual add + LayerNorm ----
 constexpr int kLnWarps = 8, kLnMaxPerLane = 8;  // D <= 256
 
 __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_fwd_kernel(
-    const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ z, float* __restrict__ mean,
-    float* __restrict__ rstd, int64_t T, int D, float eps) {
+    const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bscale,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ z,
+    float* __restrict__ mean, float* __restrict__ rstd, int64_t T, int D, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= T) return;
   float v[kLnMaxPerLane];
   float s = 0.0f;
+  const float bs = bscale ? bscale[row] : 1.0f;
 #pragma unroll
   for (int j = 0; j < kLnMaxPerLane; ++j) {
     const int c = lane + 32 * j;
     v[j] = 0.0f;
     if (c < D) {
-      v[j] = a[row * D + c] + (b ? b[row * D + c] : 0.0f);
+      v[j] = a[row * D + c] + (b ? bs * b[row * D + c] : 0.0f);
       s += v[j];
     }
   }
@@ -126,10 +149,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_fwd_kernel(
 
 __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean,
-    const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dz,
-    float* __restrict__ partial /* [grid, 2, D] */, int64_t T, int D) {
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ bscale,
+    float* __restrict__ dz, float* __restrict__ db_scaled, float* __restrict__ partial /* [grid, 2, D] */,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int32_t* __restrict__ counter, int64_t T, int D) {
   __shared__ float sg[kLnWarps][kLnMaxPerLane * 32];
   __shared__ float sb[kLnWarps][kLnMaxPerLane * 32];
+  __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float dg[kLnMaxPerLane], db[kLnMaxPerLane], gm[kLnMaxPerLane];
 #pragma unroll
@@ -161,7 +186,11 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
 #pragma unroll
     for (int j = 0; j < kLnMaxPerLane; ++j) {
       const int c = lane + 32 * j;
-      if (c < D) dz[row * D + c] = rs * (g[j] - s1 - xh[j] * s2);
+      if (c < D) {
+        const float v = rs * (g[j] - s1 - xh[j] * s2);
+        dz[row * D + c] = v;
+        if (db_scaled) db_scaled[row * D + c] = v * bscale[row];   // gradient of the scaled branch
+      }
     }
   }
 #pragma unroll
@@ -180,34 +209,58 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
     partial[((size_t)blockIdx.x * 2 + 0) * D + c] = a;
     partial[((size_t)blockIdx.x * 2 + 1) * D + c] = b;
   }
-}
-
-// dgamma[c] = sum_blk partial[blk, 0, c]; dbeta likewise
-__global__ void __launch_bounds__(256) ln_param_reduce_kernel(const float* __restrict__ partial, int nblk, int D,
-                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
-  float a = 0.0f, b = 0.0f;
-  for (int k = 0; k < nblk; ++k) {
-    a += partial[((size_t)k * 2 + 0) * D + c];
-    b += partial[((size_t)k * 2 + 1) * D + c];
+  // last block folds the per-block partials (fixed order) and re-arms the counter
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(counter, 1);
+    s_last = (done == (int)gridDim.x - 1);
+    if (s_last) *counter = 0;
   }
-  dgamma[c] = a;
-  dbeta[c] = b;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // 256 threads = (256 / Dp) slices x Dp columns; slices combined through shared memory
+  const int nblk = gridDim.x;
+  float* red = &sg[0][0];                       // reuse: 2 * 256 floats needed
+  const int Dp = D <= 32 ? 32 : (D <= 64 ? 64 : (D <= 128 ? 128 : 256));
+  const int nsl = blockDim.x / Dp, sl = threadIdx.x / Dp, c = threadIdx.x % Dp;
+  float a = 0.0f, b = 0.0f;
+  if (c < D)
+    for (int k = sl; k < nblk; k += nsl) {
+      a += __ldcg(partial + ((size_t)k * 2 + 0) * D + c);
+      b += __ldcg(partial + ((size_t)k * 2 + 1) * D + c);
+    }
+  __syncthreads();
+  red[threadIdx.x] = a;
+  red[256 + threadIdx.x] = b;
+  __syncthreads();
+  if (sl == 0 && c < D) {
+    for (int k = 1; k < nsl; ++k) {
+      a += red[k * Dp + c];
+      b += red[256 + k * Dp + c];
+    }
+    dgamma[c] = a;
+    dbeta[c] = b;
+  }
 }
 
 }  // namespace feta
 
 using namespace feta;
 
-extern "C" int feta_linear_wgrad_slices(int64_t T) { return (int)ceil_div(T > 0 ? T : 1, 128); }
+constexpr int kWgTokensPerCta = 192;
+extern "C" int feta_linear_wgrad_slices(int64_t T) { return (int)ceil_div(T > 0 ? T : 1, kWgTokensPerCta); }
 
 extern "C" int feta_linear_wgrad(const float* dY, const float* X, float* dW, float* db, float* partial,
-                                 size_t partial_floats, int64_t T, int out, int in, void* stream_) {
+                                 size_t partial_floats, int32_t* counters, int64_t T, int out, int in,
+                                 void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(T >= 0 && out >= 4 && in >= 4 && out % 4 == 0 && in % 4 == 0,
                "linear_wgrad: needs out, in multiples of 4 (got %d, %d)", out, in);
+  (void)counters;
   FETA_REQUIRE(dW && partial && (T == 0 || (dY && X)), "linear_wgrad: NULL pointer argument");
+  FETA_REQUIRE(((uintptr_t)dW % 16 == 0) && (!db || (uintptr_t)db % 16 == 0), "linear_wgrad: dW/db must be 16-byte aligned");
   FETA_REQUIRE(((uintptr_t)dY % 16 == 0) && ((uintptr_t)X % 16 == 0) && ((uintptr_t)partial % 16 == 0),
                "linear_wgrad: pointers must be 16-byte aligned");
   const int S = feta_linear_wgrad_slices(T);
@@ -219,47 +272,51 @@ extern "C" int feta_linear_wgrad(const float* dY, const float* X, float* dW, flo
   float* pdb = db ? partial + (size_t)S * out * in : nullptr;
   const int out_tiles = (int)ceil_div(out, kWgTile), in_tiles = (int)ceil_div(in, kWgTile);
   dim3 grid((unsigned)(out_tiles * in_tiles), (unsigned)S);
-  wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(dY, X, partial, pdb, (int)T, out, in, 128, in_tiles);
+  wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(dY, X, partial, pdb, (int)T, out, in, kWgTokensPerCta, in_tiles);
   FETA_LAUNCH_CHECK();
-  const int64_t n = (int64_t)out * in;
-  slices_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, S, n, dW);
+  slices_reduce4_kernel<<<(unsigned)ceil_div((int64_t)out * in / 4, 128), 128, 0, st>>>(
+      reinterpret_cast<const float4*>(partial), S, (int64_t)out * in / 4, reinterpret_cast<float4*>(dW));
   FETA_LAUNCH_CHECK();
   if (db) {
-    slices_reduce_kernel<<<(unsigned)ceil_div(out, 256), 256, 0, st>>>(pdb, S, out, db);
+    slices_reduce4_kernel<<<(unsigned)ceil_div(out / 4, 128), 128, 0, st>>>(
+        reinterpret_cast<const float4*>(pdb), S, out / 4, reinterpret_cast<float4*>(db));
     FETA_LAUNCH_CHECK();
   }
   return FETA_OK;
 }
 
-extern "C" int feta_add_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* y,
-                                      float* z, float* mean, float* rstd, int64_t T, int D, float eps, void* stream_) {
+extern "C" int feta_add_layernorm_fwd(const float* a, const float* b, const float* bscale, const float* gamma,
+                                      const float* beta, float* y, float* z, float* mean, float* rstd, int64_t T, int D,
+                                      float eps, void* stream_) {
   FETA_REQUIRE(T >= 0 && D >= 1 && D <= kLnMaxPerLane * 32, "add_layernorm: D=%d not in [1, %d]", D,
                kLnMaxPerLane * 32);
   if (T == 0) return FETA_OK;
-  FETA_REQUIRE(a && gamma && beta && y && z && mean && rstd, "add_layernorm_fwd: NULL pointer argument");
+  FETA_REQUIRE(a && gamma && beta && y && z && mean && rstd && (b || !bscale),
+               "add_layernorm_fwd: NULL pointer argument");
   add_layernorm_fwd_kernel<<<(unsigned)ceil_div(T, kLnWarps), kLnWarps * 32, 0, (cudaStream_t)stream_>>>(
-      a, b, gamma, beta, y, z, mean, rstd, T, D, eps);
+      a, b, bscale, gamma, beta, y, z, mean, rstd, T, D, eps);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
 
 extern "C" int feta_add_layernorm_bwd_blocks(int64_t T) {
-  int64_t b = ceil_div(T > 0 ? T : 1, kLnWarps * 4);
-  return (int)(b < 2 * kNumSMs ? b : 2 * kNumSMs);
+  int64_t b = ceil_div(T > 0 ? T : 1, kLnWarps * 8);
+  return (int)(b < kNumSMs ? b : kNumSMs);
 }
 
 extern "C" int feta_add_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
-                                      const float* gamma, float* dz, float* dgamma, float* dbeta, float* partial,
-                                      int64_t T, int D, void* stream_) {
+                                      const float* gamma, const float* bscale, float* dz, float* db_scaled,
+                                      float* dgamma, float* dbeta, float* partial, int32_t* counter, int64_t T, int D,
+                                      void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(T >= 0 && D >= 1 && D <= kLnMaxPerLane * 32, "add_layernorm: D=%d not in [1, %d]", D,
                kLnMaxPerLane * 32);
-  FETA_REQUIRE(dgamma && dbeta && partial && (T == 0 || (dy && z && mean && rstd && gamma && dz)),
+  FETA_REQUIRE(dgamma && dbeta && partial && counter && (T == 0 || (dy && z && mean && rstd && gamma && dz)),
                "add_layernorm_bwd: NULL pointer argument");
+  FETA_REQUIRE(!db_scaled || bscale, "add_layernorm_bwd: db_scaled needs bscale");
   const int nblk = feta_add_layernorm_bwd_blocks(T);
-  add_layernorm_bwd_kernel<<<nblk, kLnWarps * 32, 0, st>>>(dy, z, mean, rstd, gamma, dz, partial, T, D);
-  FETA_LAUNCH_CHECK();
-  ln_param_reduce_kernel<<<(unsigned)ceil_div(D, 256), 256, 0, st>>>(partial, nblk, D, dgamma, dbeta);
+  add_layernorm_bwd_kernel<<<nblk, kLnWarps * 32, 0, st>>>(dy, z, mean, rstd, gamma, bscale, dz, db_scaled, partial,
+                                                           dgamma, dbeta, counter, T, D);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }

@@ -53,10 +53,11 @@ class DiffMultiheadAttention(nn.Module):
                                       "default to --dropout 0.0)")
         N, B, E = src.shape
         qkv = ops.linear(src, self.in_proj_weight, self.in_proj_bias)        # library GEMM (+ own wgrad)
-        attn, heads = ops.diff_attention(qkv, pe, key_padding_mask, self.num_heads,
-                                         float(self.head_dim) ** -0.5, self.share_qk)
-        o = heads.view(B, N, E).transpose(0, 1)                              # concat heads, seq-first
-        return self.out_proj(o), attn, heads
+        attn, o_sf = ops.diff_attention(qkv, pe, key_padding_mask, self.num_heads,
+                                        float(self.head_dim) ** -0.5, self.share_qk)
+        # the kernel writes O seq-first, so concat-heads -> out_proj needs no copy; `heads` is the
+        # [B, Nmax, H, dh] view the FeTA encoder consumes (models.py:179)
+        return self.out_proj(o_sf.view(N, B, E)), attn, o_sf.permute(1, 0, 2, 3)
 
 
 class DiffTransformerEncoderLayer(nn.Module):
@@ -91,16 +92,15 @@ class DiffTransformerEncoderLayer(nn.Module):
                                       "(models.py:166) and is not implemented")
         src2, attn, heads = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask)
         if degree is not None:
-            src2 = degree.transpose(0, 1).contiguous().unsqueeze(-1) * src2
+            rowscale = degree.transpose(0, 1).contiguous()                      # [Nmax, B]
         else:
             if pe is None:
                 raise ValueError("DiffTransformerEncoderLayer needs `degree` or `pe`")
             if self.scaling is None:
                 self.scaling = 1. / pe.diagonal(dim1=1, dim2=2).max().item()
-            src2 = (self.scaling * pe.diagonal(dim1=1, dim2=2)).transpose(0, 1) \
-                .contiguous().unsqueeze(-1) * src2
+            rowscale = (self.scaling * pe.diagonal(dim1=1, dim2=2)).transpose(0, 1).contiguous()
         if self.batch_norm:
-            src = src + self.dropout1(src2)
+            src = src + self.dropout1(rowscale.unsqueeze(-1) * src2)
             bsz = src.shape[1]
             src = src.reshape(-1, src.shape[-1])
             src = self.norm1(src)
@@ -109,7 +109,8 @@ class DiffTransformerEncoderLayer(nn.Module):
             src = self.norm2(src)
             src = src.view(-1, bsz, src.shape[-1])
         else:                                    # residual add fused into the LayerNorm kernels
-            src = ops.add_layer_norm(src, self.dropout1(src2), self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            src = ops.add_layer_norm(src, self.dropout1(src2), self.norm1.weight, self.norm1.bias, self.norm1.eps,
+                                     bscale=rowscale.reshape(-1))       # degree * src2 fused in
             src2 = self.linear2(self.dropout(F.relu(self.linear1(src))))
             src = ops.add_layer_norm(src, self.dropout2(src2), self.norm2.weight, self.norm2.bias, self.norm2.eps)
         if need_heads:

@@ -263,7 +263,7 @@ def _mask_u8(mask, B, nmax, device):
 
 
 class DiffAttentionFn(torch.autograd.Function):
-    """(attn [B,H,N,N], o_heads [B,N,H,dh]) = kernel-biased attention of qkv [N,B,3d].
+    """(attn [B,H,N,N], o [N,B,H,dh] seq-first) = kernel-biased attention of qkv [N,B,3d].
 
     The attention core of the layer models.py:166-167 calls."""
 
@@ -280,13 +280,13 @@ class DiffAttentionFn(torch.autograd.Function):
         if pec is not None and tuple(pec.shape) != (B, N, N):
             raise ValueError("pe must be [B, Nmax, Nmax] = %s, got %s" % ((B, N, N), tuple(pec.shape)))
         attn = torch.empty((B, H, N, N), dtype=torch.float32, device=qkv.device)
-        o_heads = torch.empty((B, N, H, dh), dtype=torch.float32, device=qkv.device)
+        o_heads = torch.empty((N, B, H, dh), dtype=torch.float32, device=qkv.device)   # seq-first
         rowflag = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
         base = qkv.data_ptr()
         qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
         with _timed("attn_fwd"):
             check(lib.feta_attn_fwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(attn), _ptr(o_heads),
-                                    _ptr(rowflag), B, H, N, dh, float(scale), _stream()), "feta_attn_fwd")
+                                    B * d, d, _ptr(rowflag), B, H, N, dh, float(scale), _stream()), "feta_attn_fwd")
         ctx.save_for_backward(qkv, mask_u8, attn, rowflag)
         ctx.cfg = (H, float(scale), bool(share_qk))
         ctx.mark_non_differentiable(rowflag)
@@ -301,7 +301,7 @@ class DiffAttentionFn(torch.autograd.Function):
         d = d3 // 3
         dh = d // H
         if d_o_heads is None:
-            d_o_heads = torch.zeros((B, N, H, dh), dtype=torch.float32, device=qkv.device)
+            d_o_heads = torch.zeros((N, B, H, dh), dtype=torch.float32, device=qkv.device)
         d_o_heads = _f32c(d_o_heads)
         d_attn_c = None if d_attn is None else _f32c(d_attn)
         dqkv = torch.empty_like(qkv)
@@ -310,8 +310,8 @@ class DiffAttentionFn(torch.autograd.Function):
         db = dqkv.data_ptr()
         with _timed("attn_bwd"):
             check(lib.feta_attn_bwd(qp, kp, vp, B * d3, d3, _ptr(mask_u8), _ptr(attn), _ptr(rowflag),
-                                    _ptr(d_o_heads), _ptr(d_attn_c), db, db + d * 4, db + 2 * d * 4, B * d3, d3,
-                                    B, H, N, dh, scale, _stream()), "feta_attn_bwd")
+                                    _ptr(d_o_heads), B * d, d, _ptr(d_attn_c), db, db + d * 4, db + 2 * d * 4,
+                                    B * d3, d3, B, H, N, dh, scale, _stream()), "feta_attn_bwd")
         if share_qk:
             dqkv[..., :d] += dqkv[..., d:2 * d]
             dqkv[..., d:2 * d] = 0
@@ -321,8 +321,8 @@ class DiffAttentionFn(torch.autograd.Function):
 def diff_attention(qkv, pe, key_padding_mask, num_heads, scale, share_qk=False):
     N, B, _ = qkv.shape
     mask_u8 = _mask_u8(key_padding_mask, B, N, qkv.device)
-    attn, o_heads, _ = DiffAttentionFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk)
-    return attn, o_heads
+    attn, o_sf, _ = DiffAttentionFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk)
+    return attn, o_sf            # o_sf [Nmax, B, H, dh]; out_each_head = o_sf.permute(1, 0, 2, 3)
 
 
 # =====================================================================================
@@ -570,6 +570,19 @@ def gather_rows(padded, feature_indices):
 # =====================================================================================
 # A6 layer glue: token-axis reductions (weight gradients, LayerNorm)
 # =====================================================================================
+_COUNTERS = {}
+
+
+def _counters(device):
+    """Per-device zero-initialised int32 scratch for the self-re-arming last-block counters of
+    csrc/dense.cu (slots 0..255: weight-gradient tiles, slot 256: LayerNorm)."""
+    t = _COUNTERS.get(device)
+    if t is None:
+        t = torch.zeros(512, dtype=torch.int32, device=device)
+        _COUNTERS[device] = t
+    return t
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b.  Forward and dX are library GEMMs; dW / db (reductions over the ~5k-token axis
     the libraries under-parallelise here) go through feta_linear_wgrad."""
@@ -601,8 +614,9 @@ class LinearFn(torch.autograd.Function):
                 partial = torch.empty(n_part, dtype=torch.float32, device=dy.device)
                 dw = torch.empty((out_f, in_f), dtype=torch.float32, device=dy.device)
                 db = torch.empty(out_f, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-                check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part, T,
-                                            out_f, in_f, _stream()), "feta_linear_wgrad")
+                check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
+                                            _ptr(_counters(dy.device)), T, out_f, in_f, _stream()),
+                      "feta_linear_wgrad")
         return dx, dw, db
 
 
@@ -612,43 +626,54 @@ def linear(x, weight, bias=None):
 
 
 class AddLayerNormFn(torch.autograd.Function):
-    """y = LayerNorm(a + b) * gamma + beta  (residual + norm1 / norm2 of the layer), one kernel each way."""
+    """y = LayerNorm(a + bscale * b) * gamma + beta  (degree scaling + residual + norm of the layer),
+    one kernel each way."""
 
     @staticmethod
-    def forward(ctx, a, b, gamma, beta, eps):
+    def forward(ctx, a, b, bscale, gamma, beta, eps):
         _need_cuda(a, b, gamma, beta)
         lib = _lib.load()
         a = _f32c(a)
         b = None if b is None else _f32c(b)
+        bscale = None if bscale is None else _f32c(bscale)
         D = a.shape[-1]
         T = a.numel() // D
+        if bscale is not None and bscale.numel() != T:
+            raise ValueError("bscale must have one entry per row")
         y = torch.empty_like(a)
         z = torch.empty_like(a)
         mean = torch.empty(T, dtype=torch.float32, device=a.device)
         rstd = torch.empty(T, dtype=torch.float32, device=a.device)
         gamma, beta = _f32c(gamma), _f32c(beta)
-        check(lib.feta_add_layernorm_fwd(_ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(z), _ptr(mean),
-                                         _ptr(rstd), T, D, float(eps), _stream()), "feta_add_layernorm_fwd")
-        ctx.save_for_backward(z, mean, rstd, gamma)
+        check(lib.feta_add_layernorm_fwd(_ptr(a), _ptr(b), _ptr(bscale), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(z),
+                                         _ptr(mean), _ptr(rstd), T, D, float(eps), _stream()),
+              "feta_add_layernorm_fwd")
+        ctx.save_for_backward(z, mean, rstd, gamma, bscale)
         ctx.has_b = b is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = _lib.load()
-        z, mean, rstd, gamma = ctx.saved_tensors
+        z, mean, rstd, gamma, bscale = ctx.saved_tensors
         D = z.shape[-1]
         T = z.numel() // D
         dy = _f32c(dy)
         dz = torch.empty_like(z)
+        dbs = torch.empty_like(z) if (ctx.has_b and bscale is not None) else None
         nblk = lib.feta_add_layernorm_bwd_blocks(T)
         partial = torch.empty(nblk * 2 * D, dtype=torch.float32, device=z.device)
         dg = torch.empty(D, dtype=torch.float32, device=z.device)
         db = torch.empty(D, dtype=torch.float32, device=z.device)
-        check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dz), _ptr(dg),
-                                         _ptr(db), _ptr(partial), T, D, _stream()), "feta_add_layernorm_bwd")
-        return dz, (dz if ctx.has_b else None), dg, db, None
+        cnt = _counters(z.device)
+        check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale),
+                                         _ptr(dz), _ptr(dbs), _ptr(dg), _ptr(db), _ptr(partial),
+                                         cnt.data_ptr() + 256 * 4, T, D, _stream()), "feta_add_layernorm_bwd")
+        grad_b = None
+        if ctx.has_b:
+            grad_b = dbs if dbs is not None else dz
+        return dz, grad_b, None, dg, db, None
 
 
-def add_layer_norm(a, b, gamma, beta, eps=1e-5):
-    return AddLayerNormFn.apply(a, b, gamma, beta, eps)
+def add_layer_norm(a, b, gamma, beta, eps=1e-5, bscale=None):
+    return AddLayerNormFn.apply(a, b, bscale, gamma, beta, eps)

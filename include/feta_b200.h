@@ -124,18 +124,21 @@ int feta_cheb_bwd(const float* dout /* [R, Fout] */, const float* x, const int32
  * q/k/v are addressed as ptr[n*stride_n + b*stride_b + h*dh + c] (the [Nmax, B, 3d] in_proj output
  * is consumed in place).  mask [B, Nmax] bytes, nonzero = padding.  pe [B, Nmax, Nmax] or NULL.
  * Writes attn [B, H, Nmax, Nmax] (rows of padded queries are written as 0), o_heads
- * [B, Nmax, H, dh] (= `out_each_head`, models.py:179) and rowflag [B, H, Nmax]
+ * (= `out_each_head`, models.py:179; addressed o[n*o_stride_n + b*o_stride_b + h*dh + c], so the
+ * caller picks [B, Nmax, H, dh] or the seq-first [Nmax, B, H*dh] the out-projection consumes without a
+ * copy) and rowflag [B, H, Nmax]
  * (1 where rowsum > 1e-6, 0 where the clamp was active or the query is padding) for the backward.
  * --------------------------------------------------------------------------------------- */
 int feta_attn_fwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
-                  const float* pe, const uint8_t* mask, float* attn, float* o_heads, float* rowflag,
-                  int B, int H, int nmax, int dh, float scale, void* stream);
-/* Backward: d_o_heads [B, Nmax, H, dh] and optional d_attn [B, H, Nmax, Nmax] in; dq/dk/dv out with
+                  const float* pe, const uint8_t* mask, float* attn, float* o_heads, int64_t o_stride_n,
+                  int64_t o_stride_b, float* rowflag, int B, int H, int nmax, int dh, float scale, void* stream);
+/* Backward: d_o_heads (same addressing as o_heads) and optional d_attn [B, H, Nmax, Nmax] in; dq/dk/dv out with
  * their own strides (dq_ptr[n*dstride_n + b*dstride_b + h*dh + c]); every real (n, b) row is
  * written, padded rows are written as 0. */
 int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
                   const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o_heads,
-                  const float* d_attn, float* dq, float* dk, float* dv, int64_t dstride_n,
+                  int64_t o_stride_n, int64_t o_stride_b, const float* d_attn, float* dq, float* dk, float* dv,
+                  int64_t dstride_n,
                   int64_t dstride_b, int B, int H, int nmax, int dh, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -144,20 +147,26 @@ int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t stride
  * reference's upstream).  T = Nmax*B tokens.
  *   feta_linear_wgrad:  dW[out,in] = sum_t dY[t,out] X[t,in],  db[out] = sum_t dY[t,out] (db may be
  *     NULL).  dY [T,out], X [T,in] contiguous, 16-byte aligned, out/in multiples of 4.  `partial`
- *     needs feta_linear_wgrad_slices(T) * (out*in + out) floats.  Deterministic (two-pass).
- *   feta_add_layernorm_fwd:  z = a + b (b may be NULL), y = LayerNorm(z) * gamma + beta; saves z, mean,
- *     rstd [T] for the backward.  D <= 256.
- *   feta_add_layernorm_bwd:  dz (gradient of both a and b), dgamma, dbeta; `partial` needs
- *     feta_add_layernorm_bwd_blocks(T) * 2 * D floats.
+ *     needs feta_linear_wgrad_slices(T) * (out*in + out) floats.  The token axis is split over CTAs,
+ *     a second pass folds the slices in slice order (deterministic).  `counters` is reserved (may be
+ *     NULL).
+ *   feta_add_layernorm_fwd:  z = a + bscale[row] * b (b, bscale may be NULL), y = LayerNorm(z)*gamma + beta;
+ *     saves z, mean, rstd [T] for the backward.  D <= 256.  bscale is the per-node `degree` factor the
+ *     layer applies to the attention branch before the residual.
+ *   feta_add_layernorm_bwd:  dz (= gradient of a), db_scaled (= bscale * dz, gradient of b; may be
+ *     NULL), dgamma, dbeta; `partial` needs feta_add_layernorm_bwd_blocks(T) * 2 * D floats;
+ *     `counter`: one int32, ZERO on entry, left zero on exit (the last CTA folds the per-block partials
+ *     and re-arms it; reusable by the next call on the same stream, not by concurrent streams).
  * --------------------------------------------------------------------------------------- */
 int feta_linear_wgrad_slices(int64_t T);
 int feta_linear_wgrad(const float* dY, const float* X, float* dW, float* db, float* partial, size_t partial_floats,
-                      int64_t T, int out, int in, void* stream);
-int feta_add_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float* y, float* z,
-                           float* mean, float* rstd, int64_t T, int D, float eps, void* stream);
+                      int32_t* counters, int64_t T, int out, int in, void* stream);
+int feta_add_layernorm_fwd(const float* a, const float* b, const float* bscale, const float* gamma, const float* beta,
+                           float* y, float* z, float* mean, float* rstd, int64_t T, int D, float eps, void* stream);
 int feta_add_layernorm_bwd_blocks(int64_t T);
 int feta_add_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
-                           float* dz, float* dgamma, float* dbeta, float* partial, int64_t T, int D, void* stream);
+                           const float* bscale, float* dz, float* db_scaled, float* dgamma, float* dbeta,
+                           float* partial, int32_t* counter, int64_t T, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * A4  DiffTransformerEncoderGenGCN.get_filter_coefficients (transformer/models.py:240-287).
