@@ -331,7 +331,11 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": round(value, 1), "ms_per_step": round(ms / args.steps, 4),
-                              "quick": True}))
+                              "quick": True}), flush=True)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
         return 0
     # ---- leg 2: end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
     d2h = [0]
@@ -431,11 +435,16 @@ def main():
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_cheb_in_step": roofline_cheb,
                 "roofline_sweep": sweep,
                 "cpu_baseline": cpu_baseline, "last_loss": d2h[0]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(line))
+        torch.cuda.synchronize()
+        # destroy_process_group() blocks forever once an NCCL collective has been captured into a CUDA
+        # graph (observed on this pool: scripts/ddp_graph_probe.py) -- leave without tearing NCCL down
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
