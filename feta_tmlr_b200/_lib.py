@@ -27,7 +27,7 @@ SIGNATURES = {
                               _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int,
                               _P, c_size_t, _P]),
     "feta_attn_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, c_int64, _P,
-                              c_int, c_int, c_int, c_int, c_float, _P]),
+                              c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "feta_attn_bwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P,
                               c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, _P]),
     "feta_linear_wgrad_slices": (c_int, [c_int64]),

@@ -11,6 +11,11 @@
 
 namespace feta {
 
+// csrc/attention_tc.cu: tcgen05 / TMEM forward (3xTF32); 1 = shape not eligible
+int attn_fwd_tc_try(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
+                    const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag, int B,
+                    int H, int nmax, int dh, float scale, cudaStream_t st);
+
 constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / 32;
 constexpr int kRowsPerCta = 32;  // forward: query rows per CTA
@@ -335,11 +340,16 @@ using namespace feta;
 
 extern "C" int feta_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
                              const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag,
-                             int B, int H, int nmax, int dh, float scale, void* stream_) {
+                             int B, int H, int nmax, int dh, float scale, int use_tensor_cores, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && dh >= 1, "attn_fwd: bad sizes");
   if (B == 0 || nmax == 0) return FETA_OK;
   FETA_REQUIRE(q && k && v && mask && attn && o_heads && rowflag, "attn_fwd: NULL pointer argument");
+  if (use_tensor_cores) {
+    const int rc = attn_fwd_tc_try(q, k, v, sn, sb, pe, mask, attn, o_heads, osn, osb, rowflag, B, H, nmax, dh, scale,
+                                   st);
+    if (rc <= 0) return rc;
+  }
   if (nmax > 1024 || attn_fwd_smem(dh, nmax) > 220 * 1024) {
     set_last_error("attn_fwd: nmax=%d dh=%d exceeds the shared-memory tile (nmax <= 1024, %zu B smem)", nmax, dh,
                    attn_fwd_smem(dh, nmax));

@@ -14,6 +14,10 @@ META_NNZ, META_NUM_GRAPHS, META_SORTED, META_BLOCKDIAG, META_MAX_NODES, META_MAX
 
 _DT = {torch.int64: 0, torch.int32: 1, torch.float32: 2, torch.float64: 3}
 
+import os as _os
+# tcgen05 (3xTF32) attention forward; FETA_ATTN_TC=0 selects the fp32 CUDA-core kernel
+ATTN_TENSOR_CORES = _os.environ.get("FETA_ATTN_TC", "1") != "0"
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -286,7 +290,8 @@ class DiffAttentionFn(torch.autograd.Function):
         qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
         with _timed("attn_fwd"):
             check(lib.feta_attn_fwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(attn), _ptr(o_heads),
-                                    B * d, d, _ptr(rowflag), B, H, N, dh, float(scale), _stream()), "feta_attn_fwd")
+                                    B * d, d, _ptr(rowflag), B, H, N, dh, float(scale), int(ATTN_TENSOR_CORES),
+                                    _stream()), "feta_attn_fwd")
         ctx.save_for_backward(qkv, mask_u8, attn, rowflag)
         ctx.cfg = (H, float(scale), bool(share_qk))
         ctx.mark_non_differentiable(rowflag)

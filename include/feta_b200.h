@@ -128,10 +128,14 @@ int feta_cheb_bwd(const float* dout /* [R, Fout] */, const float* x, const int32
  * caller picks [B, Nmax, H, dh] or the seq-first [Nmax, B, H*dh] the out-projection consumes without a
  * copy) and rowflag [B, H, Nmax]
  * (1 where rowsum > 1e-6, 0 where the clamp was active or the query is padding) for the backward.
+ * use_tensor_cores != 0: QK^T and PV run as tcgen05.mma kind::tf32 with a 3xTF32 split (fp32-grade
+ * accuracy), accumulators and P in TMEM (csrc/attention_tc.cu), when dh in {8,16,32} and
+ * Nmax <= 224; otherwise, or with 0, the fp32 CUDA-core kernel (csrc/attention.cu).
  * --------------------------------------------------------------------------------------- */
 int feta_attn_fwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
                   const float* pe, const uint8_t* mask, float* attn, float* o_heads, int64_t o_stride_n,
-                  int64_t o_stride_b, float* rowflag, int B, int H, int nmax, int dh, float scale, void* stream);
+                  int64_t o_stride_b, float* rowflag, int B, int H, int nmax, int dh, float scale,
+                  int use_tensor_cores, void* stream);
 /* Backward: d_o_heads (same addressing as o_heads) and optional d_attn [B, H, Nmax, Nmax] in; dq/dk/dv out with
  * their own strides (dq_ptr[n*dstride_n + b*dstride_b + h*dh + c]); every real (n, b) row is
  * written, padded rows are written as 0. */
