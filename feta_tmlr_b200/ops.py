@@ -15,8 +15,10 @@ META_NNZ, META_NUM_GRAPHS, META_SORTED, META_BLOCKDIAG, META_MAX_NODES, META_MAX
 _DT = {torch.int64: 0, torch.int32: 1, torch.float32: 2, torch.float64: 3}
 
 import os as _os
-# tcgen05 (3xTF32) attention forward; FETA_ATTN_TC=0 selects the fp32 CUDA-core kernel
-ATTN_TENSOR_CORES = _os.environ.get("FETA_ATTN_TC", "1") != "0"
+# FETA_ATTN_TC=1 routes the attention forward through the tcgen05 / TMEM kernel (3xTF32 QK^T and PV,
+# csrc/attention_tc.cu).  Default off: at FeTA's shapes (dh 8..16, <= 190 nodes) the two contractions
+# are < 2 % of the kernel's work and the fp32 CUDA-core kernel is 1.6-2.3x faster.
+ATTN_TENSOR_CORES = _os.environ.get("FETA_ATTN_TC", "0") == "1"
 
 
 def _stream():

@@ -39,9 +39,17 @@ def _pair(cuda, d, H, seed, **kw):
     return o, m
 
 
+@pytest.fixture(params=[False, True], ids=["cuda_core", "tcgen05"])
+def tensor_cores(request, monkeypatch):
+    """Run the test through both attention forward kernels (fp32 CUDA-core / tcgen05 3xTF32)."""
+    from feta_tmlr_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_TENSOR_CORES", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("d,H", [(64, 8), (64, 4), (32, 1), (64, 1), (16, 4)])
 @pytest.mark.parametrize("nmax", [7, 38, 100])
-def test_attention_layer_parity(cuda, d, H, nmax):
+def test_attention_layer_parity(cuda, d, H, nmax, tensor_cores):
     o, m = _pair(cuda, d, H, seed=d + H + nmax)
     src, pe, degree, mask = _inputs(nmax, 5, nmax, d)
     so = src.clone().requires_grad_()
@@ -81,7 +89,7 @@ def test_attention_variants(cuda, kw):
             assert rel_err(p2.grad, p1.grad) < 5e-4, n1
 
 
-def test_attention_no_pe_and_pe_diag_scaling(cuda):
+def test_attention_no_pe_and_pe_diag_scaling(cuda, tensor_cores):
     o, m = _pair(cuda, 32, 4, seed=12)
     src, pe, degree, mask = _inputs(4, 4, 15, 32)
     oo, oa = o(src, pe=None, degree=degree, src_key_padding_mask=mask)     # pe=None: plain softmax rows
@@ -96,7 +104,7 @@ def test_attention_no_pe_and_pe_diag_scaling(cuda):
     assert rel_err(go, oo) < TOL
 
 
-def test_attention_large_graph_pattern_shape(cuda):
+def test_attention_large_graph_pattern_shape(cuda, tensor_cores):
     o, m = _pair(cuda, 64, 4, seed=13)
     src, pe, degree, mask = _inputs(5, 3, 188, 64, lens=[188, 44, 120], with_pe=False)
     so, sg = src.clone().requires_grad_(), src.to(cuda).requires_grad_()

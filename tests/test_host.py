@@ -85,6 +85,10 @@ def test_sass_is_blackwell_native():
                            "_ZN4feta20cheb_fwd_warp_kernelILi16ELi2EEEvPKfPKiS4_S2_S4_S2_llS2_PflliiiiPii", so],
                           capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "FFMA2" in sass and "SYNCS" in sass
+    # tcgen05 attention forward: tensor-core MMA (UTC*MMA), TMEM loads / stores
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4feta18attn_fwd_tc_kernelILi16EEEvPKfS2_S2_llS2_PKhPfS5_llS5_iif",
+                           so], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "LDTM" in sass and "STTM" in sass
 
 
 def test_no_cpu_fallback():
