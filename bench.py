@@ -167,6 +167,31 @@ def run_reference(args, cfg, B):
     return val, dt, cores
 
 
+def time_graphed(fn, dev, reps=20, replays=10):
+    """Device time per call of ``fn`` (us): ``reps`` calls captured into one CUDA graph, replayed
+    ``replays`` times between two events -- no CPU launch gaps, warm L2 (the in-step situation)."""
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / (reps * replays) * 1e3
+
+
 def cheb_algorithmic_bytes(R, F, nnz, G, K):
     """x + out + CSR(colidx, vals, rowptr) + Theta + graph_ptr + bias."""
     return 4 * R * F + 4 * R * F + 8 * nnz + 4 * (R + 1) + 4 * G * K * F * F + 4 * (G + 1) + 4 * F
@@ -354,25 +379,40 @@ def main():
     if use_graph and eng.plan_guard_tripped():
         raise RuntimeError("device-side plan guard tripped: static capacities do not cover a batch")
 
-    # ---- leg 3 (rank 0, not part of value/e2e): the same step run eagerly with CUDA events around this
-    # repo's hot kernels, for the live roofline numbers (events cannot be recorded inside a graph replay)
-    kern_ms = {}
+    # ---- leg 3 (rank 0, not part of value/e2e): this repo's hot kernels alone, on one of the step's own
+    # batches, as CUDA-graph replays between two events (events cannot bracket a kernel inside a replay of
+    # the step graph; an eager pass would time the CPU launch gaps of such small kernels instead)
+    kern_us = {}
     if rank == 0:
-        for nm in ("cheb_fwd", "attn_fwd", "attn_bwd"):
-            ops.enable_kernel_timer(nm)
-        opt_e = torch.optim.SGD(model.parameters(), lr=0.0)
-        for i in range(6):
-            b = pool_dev[(i * 5 + 3) % n_pool]
-            if use_graph:
-                loss = lf(model.forward_static(b[0], b[6], b[1], b[2], b[3], b[4]), b[5])
-            else:
-                loss = lf(call_model(model, b)[0], b[5])
-            loss.backward()
-            opt_e.zero_grad(set_to_none=False)
-        for nm in ("cheb_fwd", "attn_fwd", "attn_bwd"):
-            t = ops.kernel_timer_ms(nm)
-            kern_ms[nm] = float(np.mean(t[len(t) // 3:])) if t else float("nan")
-        ops.disable_kernel_timers()
+        bq = pool_dev[3 % n_pool]
+        mask_b, pe_b = bq[1], bq[2]
+        nm, H_, d_ = mask_b.shape[1], cfg['heads'], cfg['d_model']
+        gq = torch.Generator(device=dev).manual_seed(1)
+        qkv_t = torch.randn(nm, B, 3 * d_, device=dev, generator=gq)
+        go_t = torch.randn(nm, B, H_, d_ // H_, device=dev, generator=gq)
+        sc = float(d_ // H_) ** -0.5
+
+        def attn_f():
+            ops.diff_attention(qkv_t, pe_b, mask_b, H_, sc)
+
+        def attn_fb():
+            xq = qkv_t.detach().requires_grad_()
+            _, o_ = ops.diff_attention(xq, pe_b, mask_b, H_, sc)
+            torch.autograd.grad(o_, xq, go_t)
+        kern_us["attn_fwd"] = time_graphed(attn_f, dev)
+        kern_us["attn_bwd"] = time_graphed(attn_fb, dev) - kern_us["attn_fwd"]
+        if use_graph:
+            ctx_t = model.encoder.static_context(bq[6], mask_b, nm)
+            Rt, Gt, dh_ = H_ * B * nm, H_ * B, d_ // H_
+        else:
+            ctx_t = model.encoder.batch_context(bq[6], bq[8], bq[7], mask_b, nm)
+            Rt, Gt, dh_ = H_ * bq[8].shape[0], H_ * B, d_ // H_
+        x_t = torch.randn(Rt, dh_, device=dev, generator=gq)
+        th_t = (torch.randn(Gt, 4 * dh_ * dh_, device=dev, generator=gq) * 0.1).reshape(Gt, 4, dh_, dh_).permute(1, 0, 2, 3)
+        bias_t = torch.zeros(dh_, device=dev)
+        kern_us["cheb_fwd"] = time_graphed(lambda: ops.cheb_filter(x_t, th_t, bias_t, ctx_t.plan), dev)
+        cheb_nnz = ctx_t.plan.meta_host()[0]
+        cheb_rows = Rt
 
     # ---- roofline of this repo's dominant kernel inside the step (+ the HBM-sized Chebyshev sweep)
     line = None
@@ -380,29 +420,31 @@ def main():
         H, L = cfg['heads'], cfg['layers']
         dh = cfg['d_model'] // H
         d = cfg['d_model']
-        cheb_rows, attn_rows = [], []
+        attn_rows = []
         for b in pool_dev[:min(n_pool, 8)]:
-            real = ~b[1]
-            lens = real.sum(1).double()
+            lens = (~b[1]).sum(1).double()
             N, sumsq = int(lens.sum()), float((lens * lens).sum())
-            nnz = int((b[6][0] != b[6][1]).sum())
-            cheb_rows.append(cheb_algorithmic_bytes(H * N, dh, nnz, H * B, 4))
             # q,k,v + pe + attn write + O
             attn_rows.append(3 * 4 * N * d + (4 * sumsq if b[2] is not None else 0) + 4 * H * sumsq + 4 * N * d)
-        cheb_bytes, attn_bytes = float(np.mean(cheb_rows)), float(np.mean(attn_rows))
+        attn_bytes = float(np.mean(attn_rows))
+        cheb_bytes = float(cheb_algorithmic_bytes(cheb_rows, dh, cheb_nnz, H * B, 4))
 
-        def roof(kernel, nbytes, ms_, launches_per_step_, note):
+        def roof(kernel, nbytes, us_, launches_per_step_, note):
+            ms_ = us_ * 1e-3
             ach = nbytes / (ms_ * 1e-3) / 1e9
             return {"kernel": kernel, "bound": "hbm", "achieved": round(ach, 2), "peak": hbm_gbs, "unit": "GB/s",
                     "frac": round(ach / hbm_gbs, 5), "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes": int(nbytes), "us_per_launch": round(ms_ * 1e3, 2),
                     "launches_per_step": launches_per_step_, "note": note}
-        small = ("%.2f MB per launch: L2-resident and launch-latency bound at the BASELINE shape (SURVEY.md F5); "
-                 "timed with CUDA events around each launch in an eager pass of the same step")
-        roofline = roof("attn_fwd_kernel<%d>" % dh, attn_bytes, kern_ms.get("attn_fwd", float("nan")), L,
+        small = ("%.2f MB per launch: L2-resident, instruction/latency bound at the BASELINE shape (SURVEY.md F5); "
+                 "timed as CUDA-graph replays of the kernel alone on one of the step's batches")
+        roofline = roof("attn_fwd_kernel<%d>" % dh, attn_bytes, kern_us.get("attn_fwd", float("nan")), L,
                         "largest share of the step among this repo's kernels (profiles/); " + small % (attn_bytes / 1e6))
-        roofline_cheb = roof("cheb_fwd_warp_kernel<%d>" % dh, cheb_bytes, kern_ms.get("cheb_fwd", float("nan")), 1,
-                             small % (cheb_bytes / 1e6) + "; roofline_sweep is the same kernel on an HBM-sized batch")
+        roofline["attn_bwd_us_per_launch"] = round(kern_us.get("attn_bwd", float("nan")), 2)
+        roofline_cheb = roof("cheb_fwd_%s_kernel<%d>" % ("warp" if nm <= 64 else "fused", dh), cheb_bytes,
+                             kern_us.get("cheb_fwd", float("nan")), 1,
+                             small % (cheb_bytes / 1e6) + "; roofline_sweep is the same kernel family on an HBM-sized "
+                             "batch; rows = %d (padded-domain static layout)" % cheb_rows)
         sweep = None
         if not args.no_sweep:
             try:

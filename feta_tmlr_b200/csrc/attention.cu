@@ -6,6 +6,7 @@
 // attention matrix the caller needs (models.py:173 consumes it) and O = P V per head, with K/V
 // of the (graph, head) staged once in shared memory.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -46,11 +47,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
     const float* __restrict__ pe, const uint8_t* __restrict__ mask, float* __restrict__ attn,
     float* __restrict__ o_heads, int64_t osn, int64_t osb, float* __restrict__ rowflag, int H, int nmax,
-    float scale) {
+    float scale, int rows_per_cta) {
   extern __shared__ float smem[];
   __shared__ int s_neff;
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
-  const int i0 = blockIdx.x * kRowsPerCta;
+  const int i0 = blockIdx.x * rows_per_cta;
   const uint8_t* mk = mask + (size_t)b * nmax;
   const int n = block_n_eff(mk, nmax, &s_neff);
   const int npad = nmax | 1;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* pr = prow + (size_t)warp * npad;
-  for (int ii = warp; ii < kRowsPerCta; ii += kAttnWarps) {
+  for (int ii = warp; ii < rows_per_cta; ii += kAttnWarps) {
     const int i = i0 + ii;
     if (i >= nmax) break;
     float* arow = attn + (((size_t)b * H + h) * nmax + i) * nmax;
@@ -296,9 +297,11 @@ static int launch_attn_fwd(const float* q, const float* k, const float* v, int64
                            int B, int H, int nmax, float scale, cudaStream_t st) {
   const size_t smem = attn_fwd_smem(DH, nmax);
   FETA_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((unsigned)ceil_div(nmax, kRowsPerCta), (unsigned)(B * H));
+  // small graphs: one CTA per (graph, head) so K/V are staged once; larger ones: 32-row tiles
+  const int rows_per_cta = nmax <= 64 ? ((nmax + kAttnWarps - 1) / kAttnWarps) * kAttnWarps : kRowsPerCta;
+  dim3 grid((unsigned)ceil_div(nmax, rows_per_cta), (unsigned)(B * H));
   attn_fwd_kernel<DH, NCH><<<grid, kAttnThreads, smem, st>>>(q, k, v, sn, sb, pe, mask, attn, o_heads, osn, osb,
-                                                             rowflag, H, nmax, scale);
+                                                             rowflag, H, nmax, scale, rows_per_cta);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
