@@ -234,7 +234,7 @@ def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=6_000_000):
     ms = ev[0].elapsed_time(ev[1]) / iters
     nbytes = cheb_algorithmic_bytes(R, F, nnz, G, K)
     ach = nbytes / (ms * 1e-3) / 1e9
-    return {"kernel": "cheb_fwd_fused_kernel<%d>" % F, "workload": "molecule-shape, %d graphs, %d rows, %d nnz, "
+    return {"kernel": "cheb_fwd_warp_kernel<%d,2>" % F, "workload": "molecule-shape, %d graphs, %d rows, %d nnz, "
             "K=%d, F=%d (working set %.2f GB >> L2)" % (G, R, nnz, K, F, nbytes / 1e9), "bound": "hbm",
             "achieved": round(ach, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(ach / hbm_gbs, 4),
             "ms_per_launch": round(ms, 4), "algorithmic_bytes": nbytes}
