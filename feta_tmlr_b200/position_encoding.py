@@ -1,0 +1,226 @@
+"""Position encodings (reference: transformer/position_encoding.py:11-176) -- SURVEY.md section 8(f) N3.
+
+Same class names, constructor arguments, ``apply_to`` behaviour and pickle cache format
+(``<savepath>.<split>`` holding a list of dense per-graph tensors, :35-49) as the reference, so a
+cache written by either side is readable by the other.  What changes is how the kernels are
+computed: the reference calls ``scipy.sparse.linalg.expm`` / ``np.linalg.eig`` once per graph on
+the host (minutes on full ZINC / molhiv); here all graphs of a dataset are padded into one
+``[G, n, n]`` batch and decomposed with ONE batched symmetric eigendecomposition
+(``torch.linalg.eigh``, on the GPU when one is present):
+
+    L_sym = U diag(w) U^T   ->   expm(-beta L) = U diag(exp(-beta w)) U^T        (DiffusionEncoding)
+                                 (I - beta L)^p = U diag((1 - beta w)^p) U^T     (PStepRWEncoding)
+                                 columns 1..dim of U (ascending w)               (LapEncoding)
+
+``'sym'`` and ``None`` normalisations are symmetric and take the batched path; ``'rw'`` (not
+symmetric) falls back to the per-graph dense formulas.  Graphs are dicts / objects with
+``edge_index`` and ``num_nodes`` (``x.shape[0]``), as produced by ``synthetic`` or PyG.
+"""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+
+def _num_nodes(g):
+    if isinstance(g, dict):
+        return int(g.get('num_nodes', g['x'].shape[0]))
+    return int(getattr(g, 'num_nodes', None) or g.x.shape[0])
+
+
+def _edge_index(g):
+    ei = g['edge_index'] if isinstance(g, dict) else g.edge_index
+    return np.asarray(ei.cpu() if torch.is_tensor(ei) else ei, dtype=np.int64)
+
+
+def dense_laplacians(graphs, normalization, device='cpu', dtype=torch.float64):
+    """Padded batch ``[G, nmax, nmax]`` of PyG ``get_laplacian`` matrices (self loops removed,
+    multi-edges summed, degree over the source index) + the node counts."""
+    ns = np.array([_num_nodes(g) for g in graphs], dtype=np.int64)
+    nmax = int(ns.max())
+    A = np.zeros((len(graphs), nmax, nmax), dtype=np.float64)
+    for i, g in enumerate(graphs):
+        s, t = _edge_index(g)
+        keep = s != t
+        np.add.at(A[i], (s[keep], t[keep]), 1.0)
+    A = torch.from_numpy(A).to(device=device, dtype=dtype)
+    deg = A.sum(dim=2)
+    eye = torch.eye(nmax, device=device, dtype=dtype).unsqueeze(0)
+    real = (torch.arange(nmax, device=device).unsqueeze(0) < torch.from_numpy(ns).to(device).unsqueeze(1))
+    real2 = (real.unsqueeze(1) & real.unsqueeze(2)).to(dtype)
+    if normalization is None:
+        L = torch.diag_embed(deg) - A
+    elif normalization == 'sym':
+        dis = torch.where(deg > 0, deg.clamp(min=1e-300).rsqrt(), torch.zeros_like(deg))
+        L = eye * real2 - dis.unsqueeze(2) * A * dis.unsqueeze(1)
+    elif normalization == 'rw':
+        di = torch.where(deg > 0, 1.0 / deg.clamp(min=1e-300), torch.zeros_like(deg))
+        L = eye * real2 - di.unsqueeze(2) * A
+    else:
+        raise ValueError("normalization must be None, 'sym' or 'rw'")
+    return L, ns
+
+
+def _spectral_map(graphs, normalization, fn, device):
+    """U f(w) U^T for every graph with one batched eigh (symmetric normalisations)."""
+    L, ns = dense_laplacians(graphs, normalization, device=device)
+    # padded rows/cols are zero: they add zero eigenvalues whose eigenvectors live in the padding
+    w, U = torch.linalg.eigh(L)
+    M = (U * fn(w).unsqueeze(1)) @ U.transpose(1, 2)
+    return [M[i, :n, :n].to(torch.float32).cpu() for i, n in enumerate(ns)]
+
+
+class PositionEncoding(object):
+    """transformer/position_encoding.py:11-52."""
+
+    def __init__(self, savepath=None, zero_diag=False, device=None):
+        self.savepath = savepath
+        self.zero_diag = zero_diag
+        self.device = device or ('cuda' if torch.cuda.is_available() else 'cpu')
+
+    def apply_to(self, dataset, split='train'):
+        saved_pos_enc = self.load(split)
+        graphs = [dataset[i] for i in range(len(dataset))]
+        all_pe = saved_pos_enc if saved_pos_enc is not None else self.compute_all(graphs)
+        dataset.pe_list = []
+        for pe in all_pe:
+            if self.zero_diag:
+                pe = pe.clone()
+                pe.diagonal()[:] = 0
+            dataset.pe_list.append(pe)
+        if saved_pos_enc is None:
+            self.save(all_pe, split)
+        return dataset
+
+    def save(self, pos_enc, split):
+        if self.savepath is None:
+            return
+        if not os.path.isfile(self.savepath + "." + split):
+            with open(self.savepath + "." + split, 'wb') as handle:
+                pickle.dump(pos_enc, handle)
+
+    def load(self, split):
+        if self.savepath is None:
+            return None
+        if not os.path.isfile(self.savepath + "." + split):
+            return None
+        with open(self.savepath + "." + split, 'rb') as handle:
+            return pickle.load(handle)
+
+    def compute_all(self, graphs):
+        return [self.compute_pe(g) for g in graphs]
+
+    def compute_pe(self, graph):
+        return self.compute_all([graph])[0]
+
+
+class DiffusionEncoding(PositionEncoding):
+    """:55-72 -- expm(-beta L)."""
+
+    def __init__(self, savepath, beta=1., use_edge_attr=False, normalization=None, zero_diag=False, device=None):
+        super().__init__(savepath, zero_diag, device)
+        if use_edge_attr:
+            raise NotImplementedError("use_edge_attr is never set by the reference drivers")
+        self.beta, self.normalization = beta, normalization
+
+    def compute_all(self, graphs):
+        if self.normalization == 'rw':
+            out = []
+            for g in graphs:
+                L, ns = dense_laplacians([g], 'rw')
+                out.append(torch.matrix_exp(-self.beta * L[0]).to(torch.float32))
+            return out
+        return _spectral_map(graphs, self.normalization, lambda w: torch.exp(-self.beta * w), self.device)
+
+
+class PStepRWEncoding(PositionEncoding):
+    """:75-93 -- (I - beta L)^p."""
+
+    def __init__(self, savepath, p=1, beta=0.5, use_edge_attr=False, normalization=None, zero_diag=False,
+                 device=None):
+        super().__init__(savepath, zero_diag, device)
+        if use_edge_attr:
+            raise NotImplementedError("use_edge_attr is never set by the reference drivers")
+        self.p, self.beta, self.normalization = p, beta, normalization
+
+    def compute_all(self, graphs):
+        if self.normalization == 'rw':
+            out = []
+            for g in graphs:
+                L, ns = dense_laplacians([g], 'rw')
+                M = torch.eye(L.shape[1], dtype=L.dtype) - self.beta * L[0]
+                out.append(torch.linalg.matrix_power(M, self.p).to(torch.float32))
+            return out
+        return _spectral_map(graphs, self.normalization, lambda w: (1.0 - self.beta * w) ** self.p, self.device)
+
+
+class AdjEncoding(PositionEncoding):
+    """:96-105 -- dense adjacency ([1, n, n] like PyG ``to_dense_adj``)."""
+
+    def __init__(self, savepath, normalization=None, zero_diag=False, device=None):
+        super().__init__(savepath, zero_diag, device)
+        self.normalization = normalization
+
+    def compute_all(self, graphs):
+        out = []
+        for g in graphs:
+            n = _num_nodes(g)
+            A = np.zeros((n, n), dtype=np.float32)
+            s, t = _edge_index(g)
+            np.add.at(A, (s, t), 1.0)
+            out.append(torch.from_numpy(A).unsqueeze(0))
+        return out
+
+
+class FullEncoding(PositionEncoding):
+    """:107-116 -- all ones."""
+
+    def __init__(self, savepath, zero_diag=False, device=None):
+        super().__init__(savepath, zero_diag, device)
+
+    def compute_all(self, graphs):
+        return [torch.ones((_num_nodes(g), _num_nodes(g))) for g in graphs]
+
+
+class LapEncoding(PositionEncoding):
+    """:118-168 -- first ``dim`` non-trivial Laplacian eigenvectors (ascending eigenvalue), zero padded.
+    The reference uses ``np.linalg.eig`` on a symmetric matrix; eigenvector signs (and bases of
+    repeated eigenvalues) are not unique -- the drivers randomise the sign anyway
+    (run_transformer_gengcn_SBM_cv.py:159-164)."""
+
+    def __init__(self, dim, use_edge_attr=False, normalization=None, device=None):
+        super().__init__(None, False, device)
+        if use_edge_attr:
+            raise NotImplementedError("use_edge_attr is never set by the reference drivers")
+        self.pos_enc_dim, self.normalization = dim, normalization
+
+    def compute_all(self, graphs):
+        if self.normalization == 'rw':
+            raise NotImplementedError("LapEncoding with 'rw' normalisation (non-symmetric) is not implemented")
+        L, ns = dense_laplacians(graphs, self.normalization, device=self.device)
+        nmax = L.shape[1]
+        # push the padding's zero eigenvalues to the top so real eigenpairs come first, ascending
+        pad = (torch.arange(nmax, device=L.device).unsqueeze(0) >= torch.from_numpy(ns).to(L.device).unsqueeze(1))
+        L = L + torch.diag_embed(pad.to(L.dtype) * 1e6)
+        w, U = torch.linalg.eigh(L)
+        out = []
+        for i, n in enumerate(ns):
+            pe = U[i, :n, 1:self.pos_enc_dim + 1]
+            pe = pe[:, :max(0, min(self.pos_enc_dim, n - 1))]
+            full = torch.zeros((n, self.pos_enc_dim), dtype=torch.float32)
+            full[:, :pe.shape[1]] = pe.to(torch.float32).cpu()
+            out.append(full)
+        return out
+
+    def apply_to(self, dataset):
+        graphs = [dataset[i] for i in range(len(dataset))]
+        dataset.lap_pe_list = self.compute_all(graphs)
+        return dataset
+
+
+POSENCODINGS = {
+    "diffusion": DiffusionEncoding,
+    "pstep": PStepRWEncoding,
+    "adj": AdjEncoding,
+}
