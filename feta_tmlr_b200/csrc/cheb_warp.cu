@@ -75,7 +75,7 @@ static WarpCfg warp_config(int F, int K, int max_nodes) {
   c.nnz_cap = c.rows_cap * 4;
   c.per_warp = warp_region_bytes(F, K, c.rows_cap, c.nnz_cap);
   int w = (int)((220 * 1024) / c.per_warp);
-  if (w > 16) w = 16;
+  if (w > (F >= 16 ? 12 : 16)) w = (F >= 16 ? 12 : 16);
   if (w < 4) return c;
   c.warps = w;
   c.smem = c.per_warp * w;
@@ -126,8 +126,13 @@ struct GraphDesc {  // scalars of one graph, fetched ahead of use
   int e0[RPL], e1[RPL];
 };
 
+template <int F>
+constexpr int warp_kernel_max_threads() {
+  return F >= 16 ? 384 : 512;   // F = 16: at most 12 warps fit shared memory -> ~170 registers/thread allowed
+}
+
 template <int F, int RPL>
-__global__ void __launch_bounds__(512, 1) cheb_fwd_warp_kernel(
+__global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
     const float* __restrict__ vals, const int32_t* __restrict__ graph_ptr, const float* __restrict__ theta,
     int64_t sk, int64_t sg, const float* __restrict__ bias, float* __restrict__ out, int64_t R, int64_t G, int K,
