@@ -13,6 +13,8 @@
 //   * the filter is applied with packed fp32x2 FMAs (FFMA2) against Theta rows broadcast from
 //     shared memory; the output slab goes back with one cp.async.bulk store per graph;
 //   * the grid is persistent: 148 CTAs, each warp strides over the graph list.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace feta {
@@ -54,26 +56,28 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 struct WarpCfg {
   int rpl, warps, nnz_cap, rows_cap;
+  bool mma;
   size_t per_warp, smem;
   bool ok;
 };
 
-static inline size_t warp_region_bytes(int F, int K, int rows_cap, int nnz_cap) {
+static inline size_t warp_region_bytes(int F, int K, int rows_cap, int nnz_cap, bool mma) {
   const size_t ta = (size_t)rows_cap * (F + 4) * 4;  // odd orders, padded rows (gather target)
   const size_t t0 = (size_t)rows_cap * F * 4;        // x slab / even orders, dense (one bulk copy)
   const size_t csr = align_up((size_t)(nnz_cap + 8) * 4, 16);
   const size_t stage = t0 + (size_t)K * F * F * 4 + 2 * csr;
-  return align_up(16 + ta + 2 * stage, 128);
+  return align_up(16 + (mma ? 2 : 1) * ta + 2 * stage, 128);   // mma variant: second padded buffer (even orders)
 }
 
 static WarpCfg warp_config(int F, int K, int max_nodes) {
-  WarpCfg c{0, 0, 0, 0, 0, 0, false};
+  WarpCfg c{0, 0, 0, 0, false, 0, 0, false};
+  c.mma = (F == 16) && getenv("FETA_CHEB_NO_MMA") == nullptr;   // F = 8: one k-step, the FFMA2 path is faster
   if (!(F == 4 || F == 8 || F == 16) || max_nodes < 1 || max_nodes > 64) return c;
   if ((size_t)K * F * F * 4 > 16 * 1024) return c;
   c.rpl = max_nodes <= 32 ? 1 : 2;
-  c.rows_cap = (max_nodes + 7) / 8 * 8;  // buffers sized for the largest graph, not for 32 * rpl
+  c.rows_cap = (max_nodes + 15) / 16 * 16;  // buffers sized for the largest graph (whole 16-row MMA tiles)
   c.nnz_cap = c.rows_cap * 4;
-  c.per_warp = warp_region_bytes(F, K, c.rows_cap, c.nnz_cap);
+  c.per_warp = warp_region_bytes(F, K, c.rows_cap, c.nnz_cap, c.mma);
   int w = (int)((220 * 1024) / c.per_warp);
   if (w > (F >= 16 ? 12 : 16)) w = (F >= 16 ? 12 : 16);
   if (w < 4) return c;
@@ -120,6 +124,59 @@ __device__ __forceinline__ void gather_row_w(float (&t)[F], const float* __restr
   for (int i = 0; i < F / 2; ++i) t[2 * i] = a2[i].x, t[2 * i + 1] = a2[i].y;
 }
 
+// ---- 3xTF32 on the (legacy, warp-level) tensor-core path: T_k . Theta_k as m16n8k8 MMAs -------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  // the tensor core reads only the top 19 bits of a tf32 operand (truncation), so "hi" is x itself and the
+  // remainder is exact in fp32:  x = trunc19(x) + lo,  |lo| <= 2^-10 |x|;  lo is truncated again by the
+  // hardware (relative error of the 3-term product ~ 2^-20).  2 instructions per element (LOP3 + FADD).
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// acc[mt][nt] += T[16mt .. 16mt+15, :] . Theta_k   for mt < MT, with hi/lo splits of both operands
+template <int F, int MTMAX, int ld>
+__device__ __forceinline__ void mma_order(float (&acc)[MTMAX][F / 8][4], const float* __restrict__ Tb,
+                                          const float* __restrict__ thk, int MT, int lane) {
+  constexpr int NT = F / 8, KS = F / 8;
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t bh[NT][KS][2], bl[NT][KS][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      split_tf32(thk[(8 * ks + tq) * F + 8 * nt + g], bh[nt][ks][0], bl[nt][ks][0]);
+      split_tf32(thk[(8 * ks + tq + 4) * F + 8 * nt + g], bh[nt][ks][1], bl[nt][ks][1]);
+    }
+#pragma unroll
+  for (int mt = 0; mt < MTMAX; ++mt) {
+    if (mt < MT) {
+      const float* r0 = Tb + (16 * mt + g) * ld;
+      const float* r1 = r0 + 8 * ld;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t ah[4], al[4];
+        split_tf32(r0[8 * ks + tq], ah[0], al[0]);
+        split_tf32(r1[8 * ks + tq], ah[1], al[1]);
+        split_tf32(r0[8 * ks + tq + 4], ah[2], al[2]);
+        split_tf32(r1[8 * ks + tq + 4], ah[3], al[3]);
+        // the three split terms are issued nt-interleaved: consecutive MMAs hit different accumulators
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], ah, bh[nt][ks]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], ah, bl[nt][ks]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], al, bh[nt][ks]);
+      }
+    }
+  }
+}
+
 template <int RPL>
 struct GraphDesc {  // scalars of one graph, fetched ahead of use
   int r0, r1, e_lo, e_hi;
@@ -131,7 +188,7 @@ constexpr int warp_kernel_max_threads() {
   return F >= 16 ? 384 : 512;   // F = 16: at most 12 warps fit shared memory -> ~170 registers/thread allowed
 }
 
-template <int F, int RPL>
+template <int F, int RPL, bool USE_MMA>
 __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
     const float* __restrict__ vals, const int32_t* __restrict__ graph_ptr, const float* __restrict__ theta,
@@ -162,7 +219,8 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
   const uint32_t stage_bytes = TB + th_bytes + 2 * csr_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base);
   float* bufA = reinterpret_cast<float*>(base + 16);
-  unsigned char* stage0 = base + 16 + TA;
+  float* bufB = reinterpret_cast<float*>(base + 16 + TA);          // USE_MMA only
+  unsigned char* stage0 = base + 16 + (USE_MMA ? 2 : 1) * TA;
   const bool theta_contig = (sk == (int64_t)F * F);
 
   if (lane == 0) {
@@ -262,67 +320,131 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
     if (lane == 0) bulk_wait_read0();  // the previous graph's output store has drained bufA
     __syncwarp();
 
-    float2 acc[RPL][F / 2];
-    float t[F];
+    if constexpr (USE_MMA) {
+      // ---- tensor-core variant: the filter application T_k . Theta_k runs as 3xTF32 m16n8k8 MMAs
+      constexpr int MTMAX = 2 * RPL, NT = F / 8;
+      float acc[MTMAX][NT][4];
 #pragma unroll
-    for (int m = 0; m < RPL; ++m) {
+      for (int mt = 0; mt < MTMAX; ++mt)
 #pragma unroll
-      for (int i = 0; i < F / 2; ++i) acc[m][i] = make_float2(0.f, 0.f);
-      const int row = lane + 32 * m;
-      if (row < n) {
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int q = 0; q < F / 4; ++q) {
-          const float4 a = *reinterpret_cast<const float4*>(T0 + row * F + 4 * q);
-          t[4 * q] = a.x, t[4 * q + 1] = a.y, t[4 * q + 2] = a.z, t[4 * q + 3] = a.w;
+          for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.0f;
+      const int MT = (n + 15) >> 4;
+      mma_order<F, MTMAX, F>(acc, T0, th, MT, lane);                    // k = 0 straight from the x slab
+      float t[F];
+      for (int k = 1; k < K; ++k) {
+        // buf_0 = T0 (dense), odd orders -> bufA, even orders >= 2 -> bufB; T_k overwrites own row of T_{k-2}
+        const float* src = (k == 1) ? T0 : ((k & 1) ? bufB : bufA);
+        float* dst = (k & 1) ? bufA : bufB;
+#pragma unroll
+        for (int m = 0; m < RPL; ++m) {
+          const int row = lane + 32 * m;
+          if (row < n) {
+            if (k == 1) {
+              if (staged) gather_row_w<F, F, true>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              else gather_row_w<F, F, false>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            } else {
+              if (staged) gather_row_w<F, LD, true>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              else gather_row_w<F, LD, false>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            }
+            if (k >= 2) {
+              const float* orow = (k == 2) ? T0 + row * F : dst + row * LD;
+#pragma unroll
+              for (int q = 0; q < F / 4; ++q) {
+                const float4 o = *reinterpret_cast<const float4*>(orow + 4 * q);
+                t[4 * q] = fmaf(2.0f, t[4 * q], -o.x), t[4 * q + 1] = fmaf(2.0f, t[4 * q + 1], -o.y);
+                t[4 * q + 2] = fmaf(2.0f, t[4 * q + 2], -o.z), t[4 * q + 3] = fmaf(2.0f, t[4 * q + 3], -o.w);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < F / 4; ++q)
+              *reinterpret_cast<float4*>(dst + row * LD + 4 * q) =
+                  make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+          }
         }
-        apply_theta_s<F>(acc[m], t, th);  // k = 0
+        __syncwarp();
+        mma_order<F, MTMAX, LD>(acc, dst, th + (size_t)k * F * F, MT, lane);
       }
-    }
-    // even orders live in the (dense) stage buffer, odd orders in the padded bufA; T_k overwrites the
-    // own row of T_{k-2} (nobody else reads it any more)
-    for (int k = 1; k < K; ++k) {
-      const bool odd = (k & 1) != 0;
+      __syncwarp();   // all lanes are done reading bufA before it becomes the output staging slab
+      const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
+      for (int mt = 0; mt < MTMAX; ++mt) {
+        if (mt < MT) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const int col = 8 * nt + 2 * tq;
+            const float b0 = bias ? __ldg(bias + col) : 0.0f, b1 = bias ? __ldg(bias + col + 1) : 0.0f;
+            const int ra = 16 * mt + g, rb = ra + 8;
+            if (ra < n) *reinterpret_cast<float2*>(bufA + ra * F + col) = make_float2(acc[mt][nt][0] + b0, acc[mt][nt][1] + b1);
+            if (rb < n) *reinterpret_cast<float2*>(bufA + rb * F + col) = make_float2(acc[mt][nt][2] + b0, acc[mt][nt][3] + b1);
+          }
+        }
+      }
+    } else {
+    float2 acc[RPL][F / 2];
+      float t[F];
+  #pragma unroll
+      for (int m = 0; m < RPL; ++m) {
+  #pragma unroll
+        for (int i = 0; i < F / 2; ++i) acc[m][i] = make_float2(0.f, 0.f);
+        const int row = lane + 32 * m;
+        if (row < n) {
+  #pragma unroll
+          for (int q = 0; q < F / 4; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(T0 + row * F + 4 * q);
+            t[4 * q] = a.x, t[4 * q + 1] = a.y, t[4 * q + 2] = a.z, t[4 * q + 3] = a.w;
+          }
+          apply_theta_s<F>(acc[m], t, th);  // k = 0
+        }
+      }
+      // even orders live in the (dense) stage buffer, odd orders in the padded bufA; T_k overwrites the
+      // own row of T_{k-2} (nobody else reads it any more)
+      for (int k = 1; k < K; ++k) {
+        const bool odd = (k & 1) != 0;
+  #pragma unroll
+        for (int m = 0; m < RPL; ++m) {
+          const int row = lane + 32 * m;
+          if (row < n) {
+            if (odd) {
+              if (staged) gather_row_w<F, F, true>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              else gather_row_w<F, F, false>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            } else {
+              if (staged) gather_row_w<F, LD, true>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              else gather_row_w<F, LD, false>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            }
+            float* drow = odd ? bufA + row * LD : T0 + row * F;
+            if (k >= 2) {
+  #pragma unroll
+              for (int q = 0; q < F / 4; ++q) {
+                const float4 o = *reinterpret_cast<const float4*>(drow + 4 * q);
+                t[4 * q] = fmaf(2.0f, t[4 * q], -o.x), t[4 * q + 1] = fmaf(2.0f, t[4 * q + 1], -o.y);
+                t[4 * q + 2] = fmaf(2.0f, t[4 * q + 2], -o.z), t[4 * q + 3] = fmaf(2.0f, t[4 * q + 3], -o.w);
+              }
+            }
+            if (k + 1 < K) {
+  #pragma unroll
+              for (int q = 0; q < F / 4; ++q)
+                *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+            }
+            apply_theta_s<F>(acc[m], t, th + (size_t)k * F * F);
+          }
+        }
+        __syncwarp();
+      }
+      // epilogue: + bias, dense slab in bufA, one bulk store
+  #pragma unroll
       for (int m = 0; m < RPL; ++m) {
         const int row = lane + 32 * m;
         if (row < n) {
-          if (odd) {
-            if (staged) gather_row_w<F, F, true>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-            else gather_row_w<F, F, false>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-          } else {
-            if (staged) gather_row_w<F, LD, true>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-            else gather_row_w<F, LD, false>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-          }
-          float* drow = odd ? bufA + row * LD : T0 + row * F;
-          if (k >= 2) {
-#pragma unroll
-            for (int q = 0; q < F / 4; ++q) {
-              const float4 o = *reinterpret_cast<const float4*>(drow + 4 * q);
-              t[4 * q] = fmaf(2.0f, t[4 * q], -o.x), t[4 * q + 1] = fmaf(2.0f, t[4 * q + 1], -o.y);
-              t[4 * q + 2] = fmaf(2.0f, t[4 * q + 2], -o.z), t[4 * q + 3] = fmaf(2.0f, t[4 * q + 3], -o.w);
-            }
-          }
-          if (k + 1 < K) {
-#pragma unroll
-            for (int q = 0; q < F / 4; ++q)
-              *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
-          }
-          apply_theta_s<F>(acc[m], t, th + (size_t)k * F * F);
+  #pragma unroll
+          for (int q = 0; q < F / 4; ++q)
+            *reinterpret_cast<float4*>(bufA + row * F + 4 * q) =
+                make_float4(acc[m][2 * q].x + bias_r[4 * q], acc[m][2 * q].y + bias_r[4 * q + 1],
+                            acc[m][2 * q + 1].x + bias_r[4 * q + 2], acc[m][2 * q + 1].y + bias_r[4 * q + 3]);
         }
       }
-      __syncwarp();
-    }
-    // epilogue: + bias, dense slab in bufA, one bulk store
-#pragma unroll
-    for (int m = 0; m < RPL; ++m) {
-      const int row = lane + 32 * m;
-      if (row < n) {
-#pragma unroll
-        for (int q = 0; q < F / 4; ++q)
-          *reinterpret_cast<float4*>(bufA + row * F + 4 * q) =
-              make_float4(acc[m][2 * q].x + bias_r[4 * q], acc[m][2 * q].y + bias_r[4 * q + 1],
-                          acc[m][2 * q + 1].x + bias_r[4 * q + 2], acc[m][2 * q + 1].y + bias_r[4 * q + 3]);
-      }
+
     }
     fence_proxy_async();
     __syncwarp();
@@ -337,16 +459,16 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
 }
 
-template <int F, int RPL>
+template <int F, int RPL, bool USE_MMA>
 static int launch_warp(const WarpCfg& c, const float* x, const int32_t* rowptr, const int32_t* colidx,
                        const float* vals, const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg,
                        const float* bias, float* out, int64_t R, int64_t G, int K, int32_t* meta, int max_nodes,
                        cudaStream_t st) {
-  FETA_CUDA(cudaFuncSetAttribute(cheb_fwd_warp_kernel<F, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  FETA_CUDA(cudaFuncSetAttribute(cheb_fwd_warp_kernel<F, RPL, USE_MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)c.smem));
   int64_t grid = ceil_div(G, c.warps);
   if (grid > kNumSMs) grid = kNumSMs;
-  cheb_fwd_warp_kernel<F, RPL><<<(unsigned)grid, c.warps * 32, c.smem, st>>>(
+  cheb_fwd_warp_kernel<F, RPL, USE_MMA><<<(unsigned)grid, c.warps * 32, c.smem, st>>>(
       x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, c.nnz_cap, c.rows_cap, (int)c.per_warp,
       meta, max_nodes);
   FETA_LAUNCH_CHECK();
@@ -360,12 +482,13 @@ int cheb_fwd_warp_try(const float* x, const int32_t* rowptr, const int32_t* coli
   WarpCfg c = warp_config(F, K, max_nodes);
   if (!c.ok) return 1;
   if (((uintptr_t)colidx % 16) || ((uintptr_t)vals % 16)) return 1;
-#define FETA_WARP_CASE(F_, R_)                                                                                      \
-  if (F == F_ && c.rpl == R_)                                                                                       \
-    return launch_warp<F_, R_>(c, x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, meta,     \
-                               max_nodes, st);
-  FETA_WARP_CASE(4, 1) FETA_WARP_CASE(4, 2) FETA_WARP_CASE(8, 1) FETA_WARP_CASE(8, 2) FETA_WARP_CASE(16, 1)
-  FETA_WARP_CASE(16, 2)
+#define FETA_WARP_CASE(F_, R_, M_)                                                                                  \
+  if (F == F_ && c.rpl == R_ && c.mma == M_)                                                                        \
+    return launch_warp<F_, R_, M_>(c, x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, meta, \
+                                   max_nodes, st);
+  FETA_WARP_CASE(4, 1, false) FETA_WARP_CASE(4, 2, false) FETA_WARP_CASE(8, 1, false) FETA_WARP_CASE(8, 2, false)
+  FETA_WARP_CASE(16, 1, false) FETA_WARP_CASE(16, 2, false) FETA_WARP_CASE(8, 1, true) FETA_WARP_CASE(8, 2, true)
+  FETA_WARP_CASE(16, 1, true) FETA_WARP_CASE(16, 2, true)
 #undef FETA_WARP_CASE
   return 1;
 }
