@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--eager", action="store_true", help="eager autograd instead of the whole-step CUDA graph")
     ap.add_argument("--sweep-only", action="store_true", help="run only the HBM-sized Chebyshev sweep")
     ap.add_argument("--sweep-f", type=int, default=0, help="feature width for --sweep-only (default: config's dh)")
-    ap.add_argument("--sweep-rows", type=int, default=6_000_000)
+    ap.add_argument("--sweep-rows", type=int, default=3_000_000)
     return ap.parse_args()
 
 
@@ -197,7 +197,13 @@ def cheb_algorithmic_bytes(R, F, nnz, G, K):
     return 4 * R * F + 4 * R * F + 8 * nnz + 4 * (R + 1) + 4 * G * K * F * F + 4 * (G + 1) + 4 * F
 
 
-def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=6_000_000):
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu --set full captures
+# (profiles/r1_cheb_fwd_ncu.md capture r1d: F=16, 3.0M rows; profiles/r1_attention_ncu.md: ZINC attention fwd)
+NCU_TRAFFIC = {("cheb_sweep", 16, 3_000_000): 747_484_416 + 174_554_880,
+               ("attn_fwd", "ZINC"): 2_729_984}
+
+
+def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=3_000_000):
     """The fused Chebyshev kernel on an HBM-sized (>> 126 MB L2) batch of molecule-shape graphs."""
     from feta_tmlr_b200 import ops
     g = torch.Generator(device=dev).manual_seed(0)
@@ -237,6 +243,7 @@ def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=6_000_000):
     return {"kernel": "cheb_fwd_warp_kernel<%d,2>" % F, "workload": "molecule-shape, %d graphs, %d rows, %d nnz, "
             "K=%d, F=%d (working set %.2f GB >> L2)" % (G, R, nnz, K, F, nbytes / 1e9), "bound": "hbm",
             "achieved": round(ach, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(ach / hbm_gbs, 4),
+            "traffic": NCU_TRAFFIC.get(("cheb_sweep", F, target_rows)),
             "ms_per_launch": round(ms, 4), "algorithmic_bytes": nbytes}
 
 
@@ -441,6 +448,8 @@ def main():
         roofline = roof("attn_fwd_kernel<%d>" % dh, attn_bytes, kern_us.get("attn_fwd", float("nan")), L,
                         "largest share of the step among this repo's kernels (profiles/); " + small % (attn_bytes / 1e6))
         roofline["attn_bwd_us_per_launch"] = round(kern_us.get("attn_bwd", float("nan")), 2)
+        if args.config == "ZINC" and not args.batch:
+            roofline["traffic"] = NCU_TRAFFIC[("attn_fwd", "ZINC")]     # L2-resident: DRAM sees less than the algorithmic bytes
         roofline_cheb = roof("cheb_fwd_%s_kernel<%d>" % ("warp" if nm <= 64 else "fused", dh), cheb_bytes,
                              kern_us.get("cheb_fwd", float("nan")), 1,
                              small % (cheb_bytes / 1e6) + "; roofline_sweep is the same kernel family on an HBM-sized "
@@ -448,7 +457,8 @@ def main():
         sweep = None
         if not args.no_sweep:
             try:
-                sweep = cheb_sweep(dev, hbm_gbs, F=dh if dh in (4, 8, 16, 32) else 16)
+                # always F = 16 (head dim of MUTAG / PATTERN / CLUSTER / molhiv; the ncu capture's shape)
+                sweep = cheb_sweep(dev, hbm_gbs, F=16, target_rows=args.sweep_rows)
             except torch.OutOfMemoryError as e:       # bounded sweep; never take the box down
                 sweep = {"error": "OOM: %s" % str(e)[:80]}
         cpu_baseline = None
