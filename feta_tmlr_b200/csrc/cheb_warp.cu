@@ -66,7 +66,8 @@ static inline size_t warp_region_bytes(int F, int K, int rows_cap, int nnz_cap, 
   const size_t t0 = (size_t)rows_cap * F * 4;        // x slab / even orders, dense (one bulk copy)
   const size_t csr = align_up((size_t)(nnz_cap + 8) * 4, 16);
   const size_t stage = t0 + (size_t)K * F * F * 4 + 2 * csr;
-  return align_up(16 + (mma ? 2 : 1) * ta + 2 * stage, 128);   // mma variant: second padded buffer (even orders)
+  (void)mma;
+  return align_up(16 + ta + 2 * stage, 128);
 }
 
 static WarpCfg warp_config(int F, int K, int max_nodes) {
@@ -75,7 +76,9 @@ static WarpCfg warp_config(int F, int K, int max_nodes) {
   if (!(F == 4 || F == 8 || F == 16) || max_nodes < 1 || max_nodes > 64) return c;
   if ((size_t)K * F * F * 4 > 16 * 1024) return c;
   c.rpl = max_nodes <= 32 ? 1 : 2;
-  c.rows_cap = (max_nodes + 15) / 16 * 16;  // buffers sized for the largest graph (whole 16-row MMA tiles)
+  // buffers sized for the largest graph; an MMA tile may read up to 8 rows past it -- that lands in the
+  // next region of the same warp (stage T0 / Theta), is never written and only feeds discarded output rows
+  c.rows_cap = (max_nodes + 7) / 8 * 8;
   c.nnz_cap = c.rows_cap * 4;
   c.per_warp = warp_region_bytes(F, K, c.rows_cap, c.nnz_cap, c.mma);
   int w = (int)((220 * 1024) / c.per_warp);
@@ -219,8 +222,7 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
   const uint32_t stage_bytes = TB + th_bytes + 2 * csr_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base);
   float* bufA = reinterpret_cast<float*>(base + 16);
-  float* bufB = reinterpret_cast<float*>(base + 16 + TA);          // USE_MMA only
-  unsigned char* stage0 = base + 16 + (USE_MMA ? 2 : 1) * TA;
+  unsigned char* stage0 = base + 16 + TA;
   const bool theta_contig = (sk == (int64_t)F * F);
 
   if (lane == 0) {
@@ -334,37 +336,37 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
       mma_order<F, MTMAX, F>(acc, T0, th, MT, lane);                    // k = 0 straight from the x slab
       float t[F];
       for (int k = 1; k < K; ++k) {
-        // buf_0 = T0 (dense), odd orders -> bufA, even orders >= 2 -> bufB; T_k overwrites own row of T_{k-2}
-        const float* src = (k == 1) ? T0 : ((k & 1) ? bufB : bufA);
-        float* dst = (k & 1) ? bufA : bufB;
+        // even orders live in the dense stage buffer T0, odd orders in the padded bufA; T_k overwrites the
+        // own row of T_{k-2} (nobody else reads it any more)
+        const bool odd = (k & 1) != 0;
 #pragma unroll
         for (int m = 0; m < RPL; ++m) {
           const int row = lane + 32 * m;
           if (row < n) {
-            if (k == 1) {
-              if (staged) gather_row_w<F, F, true>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-              else gather_row_w<F, F, false>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            if (odd) {
+              if (staged) gather_row_w<F, F, true>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              else gather_row_w<F, F, false>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
             } else {
-              if (staged) gather_row_w<F, LD, true>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-              else gather_row_w<F, LD, false>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              if (staged) gather_row_w<F, LD, true>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              else gather_row_w<F, LD, false>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
             }
+            float* drow = odd ? bufA + row * LD : T0 + row * F;
             if (k >= 2) {
-              const float* orow = (k == 2) ? T0 + row * F : dst + row * LD;
 #pragma unroll
               for (int q = 0; q < F / 4; ++q) {
-                const float4 o = *reinterpret_cast<const float4*>(orow + 4 * q);
+                const float4 o = *reinterpret_cast<const float4*>(drow + 4 * q);
                 t[4 * q] = fmaf(2.0f, t[4 * q], -o.x), t[4 * q + 1] = fmaf(2.0f, t[4 * q + 1], -o.y);
                 t[4 * q + 2] = fmaf(2.0f, t[4 * q + 2], -o.z), t[4 * q + 3] = fmaf(2.0f, t[4 * q + 3], -o.w);
               }
             }
 #pragma unroll
             for (int q = 0; q < F / 4; ++q)
-              *reinterpret_cast<float4*>(dst + row * LD + 4 * q) =
-                  make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+              *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
           }
         }
         __syncwarp();
-        mma_order<F, MTMAX, LD>(acc, dst, th + (size_t)k * F * F, MT, lane);
+        if (odd) mma_order<F, MTMAX, LD>(acc, bufA, th + (size_t)k * F * F, MT, lane);
+        else mma_order<F, MTMAX, F>(acc, T0, th + (size_t)k * F * F, MT, lane);
       }
       __syncwarp();   // all lanes are done reading bufA before it becomes the output staging slab
       const int g = lane >> 2, tq = lane & 3;
