@@ -62,11 +62,11 @@ struct WarpCfg {
 };
 
 static inline size_t warp_region_bytes(int F, int K, int rows_cap, int nnz_cap, bool mma) {
-  const size_t ta = (size_t)rows_cap * (F + 4) * 4;  // odd orders, padded rows (gather target)
+  // odd orders: padded rows (FFMA2 variant) or dense XOR-swizzled rows (MMA variant)
+  const size_t ta = (size_t)rows_cap * (mma ? F : F + 4) * 4;
   const size_t t0 = (size_t)rows_cap * F * 4;        // x slab / even orders, dense (one bulk copy)
   const size_t csr = align_up((size_t)(nnz_cap + 8) * 4, 16);
   const size_t stage = t0 + (size_t)K * F * F * 4 + 2 * csr;
-  (void)mma;
   return align_up(16 + ta + 2 * stage, 128);
 }
 
@@ -127,6 +127,36 @@ __device__ __forceinline__ void gather_row_w(float (&t)[F], const float* __restr
   for (int i = 0; i < F / 2; ++i) t[2 * i] = a2[i].x, t[2 * i + 1] = a2[i].y;
 }
 
+// ---- XOR-swizzled [rows, 16] fp32 slabs (MMA variant) ------------------------------------------------
+// A row is 64 B = 4 chunks of 16 B; chunk q of row r is stored at chunk position q ^ ((r >> 1) & 3).  Eight
+// consecutive rows then cover all 32 banks for a lane-per-row LDS.128/STS.128, and an m16n8k8 A-fragment
+// load (8 rows x 4 consecutive words) is conflict-free as well; a dense slab has 4-way conflicts for both.
+__device__ __forceinline__ int swz16(int r) { return ((r >> 1) & 3) << 2; }
+
+template <bool STAGED>
+__device__ __forceinline__ void gather_row_swz(float (&t)[16], const float* __restrict__ buf, int r0,
+                                               const int32_t* __restrict__ ci, const float* __restrict__ cv, int e0,
+                                               int e1) {
+  float2 a2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a2[i] = make_float2(0.f, 0.f);
+  for (int e = e0; e < e1; ++e) {
+    const int c = (STAGED ? ci[e] : __ldg(ci + e)) - r0;
+    const float w = STAGED ? cv[e] : __ldg(cv + e);
+    const float2 ww = make_float2(w, w);
+    const float* row = buf + c * 16;
+    const int sw = swz16(c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(row + ((4 * q) ^ sw));
+      a2[2 * q] = __ffma2_rn(ww, make_float2(a.x, a.y), a2[2 * q]);
+      a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a.z, a.w), a2[2 * q + 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[2 * i] = a2[i].x, t[2 * i + 1] = a2[i].y;
+}
+
 // ---- 3xTF32 on the (legacy, warp-level) tensor-core path: T_k . Theta_k as m16n8k8 MMAs -------------
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   // the tensor core reads only the top 19 bits of a tf32 operand (truncation), so "hi" is x itself and the
@@ -143,7 +173,8 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 // acc[mt][nt] += T[16mt .. 16mt+15, :] . Theta_k   for mt < MT, with hi/lo splits of both operands
-template <int F, int MTMAX, int ld>
+// Tb is an XOR-swizzled [rows, 16] slab (see swz16)
+template <int F, int MTMAX>
 __device__ __forceinline__ void mma_order(float (&acc)[MTMAX][F / 8][4], const float* __restrict__ Tb,
                                           const float* __restrict__ thk, int MT, int lane) {
   constexpr int NT = F / 8, KS = F / 8;
@@ -159,15 +190,18 @@ __device__ __forceinline__ void mma_order(float (&acc)[MTMAX][F / 8][4], const f
 #pragma unroll
   for (int mt = 0; mt < MTMAX; ++mt) {
     if (mt < MT) {
-      const float* r0 = Tb + (16 * mt + g) * ld;
-      const float* r1 = r0 + 8 * ld;
+      static_assert(F == 16, "swizzled slabs are 16 floats wide");
+      const float* r0 = Tb + (16 * mt + g) * F + tq;   // rows 16mt+g and +8 share the swizzle ((g >> 1) & 3)
+      const float* r1 = r0 + 8 * F;
+      const int sw = swz16(g);
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t ah[4], al[4];
-        split_tf32(r0[8 * ks + tq], ah[0], al[0]);
-        split_tf32(r1[8 * ks + tq], ah[1], al[1]);
-        split_tf32(r0[8 * ks + tq + 4], ah[2], al[2]);
-        split_tf32(r1[8 * ks + tq + 4], ah[3], al[3]);
+        const int c0 = (8 * ks) ^ sw, c1 = (8 * ks + 4) ^ sw;
+        split_tf32(r0[c0], ah[0], al[0]);
+        split_tf32(r1[c0], ah[1], al[1]);
+        split_tf32(r0[c1], ah[2], al[2]);
+        split_tf32(r1[c1], ah[3], al[3]);
         // the three split terms are issued nt-interleaved: consecutive MMAs hit different accumulators
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], ah, bh[nt][ks]);
@@ -198,7 +232,7 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
     int64_t sk, int64_t sg, const float* __restrict__ bias, float* __restrict__ out, int64_t R, int64_t G, int K,
     int nnz_cap, int rows_cap, int per_warp_bytes, int32_t* meta, int max_nodes) {
   constexpr int LD = F + 4;
-  const uint32_t TA = (uint32_t)rows_cap * LD * 4;  // padded odd-order buffer
+  const uint32_t TA = (uint32_t)rows_cap * (USE_MMA ? F : LD) * 4;  // odd-order buffer (padded / swizzled)
   const uint32_t TB = (uint32_t)rows_cap * F * 4;   // dense x slab / even-order buffer (per stage)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // device-side plan guard (same contract as the chunk kernel)
@@ -333,40 +367,55 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.0f;
       const int MT = (n + 15) >> 4;
-      mma_order<F, MTMAX, F>(acc, T0, th, MT, lane);                    // k = 0 straight from the x slab
+      {  // re-lay the bulk-copied (dense) x slab into the swizzled layout, in place: the permutation stays
+         // inside a row and a pass of 32 chunks covers 8 whole rows
+        float4 v[4 * RPL];
+        float4* T4 = reinterpret_cast<float4*>(T0);
+#pragma unroll
+        for (int p = 0; p < 4 * RPL; ++p) {
+          const int i = 32 * p + lane;
+          if (i < 4 * n) v[p] = T4[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 4 * RPL; ++p) {
+          const int i = 32 * p + lane;
+          if (i < 4 * n) T4[i ^ ((i >> 3) & 3)] = v[p];
+        }
+        __syncwarp();
+      }
+      mma_order<F, MTMAX>(acc, T0, th, MT, lane);                    // k = 0
       float t[F];
       for (int k = 1; k < K; ++k) {
-        // even orders live in the dense stage buffer T0, odd orders in the padded bufA; T_k overwrites the
+        // even orders live in the stage buffer T0, odd orders in bufA (both swizzled); T_k overwrites the
         // own row of T_{k-2} (nobody else reads it any more)
         const bool odd = (k & 1) != 0;
+        const float* src = odd ? T0 : bufA;
+        float* dst = odd ? bufA : T0;
 #pragma unroll
         for (int m = 0; m < RPL; ++m) {
           const int row = lane + 32 * m;
           if (row < n) {
-            if (odd) {
-              if (staged) gather_row_w<F, F, true>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-              else gather_row_w<F, F, false>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-            } else {
-              if (staged) gather_row_w<F, LD, true>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-              else gather_row_w<F, LD, false>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-            }
-            float* drow = odd ? bufA + row * LD : T0 + row * F;
+            if (staged) gather_row_swz<true>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            else gather_row_swz<false>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            float* drow = dst + row * F;
+            const int sw = swz16(row);
             if (k >= 2) {
 #pragma unroll
               for (int q = 0; q < F / 4; ++q) {
-                const float4 o = *reinterpret_cast<const float4*>(drow + 4 * q);
+                const float4 o = *reinterpret_cast<const float4*>(drow + ((4 * q) ^ sw));
                 t[4 * q] = fmaf(2.0f, t[4 * q], -o.x), t[4 * q + 1] = fmaf(2.0f, t[4 * q + 1], -o.y);
                 t[4 * q + 2] = fmaf(2.0f, t[4 * q + 2], -o.z), t[4 * q + 3] = fmaf(2.0f, t[4 * q + 3], -o.w);
               }
             }
 #pragma unroll
             for (int q = 0; q < F / 4; ++q)
-              *reinterpret_cast<float4*>(drow + 4 * q) = make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+              *reinterpret_cast<float4*>(drow + ((4 * q) ^ sw)) =
+                  make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
           }
         }
         __syncwarp();
-        if (odd) mma_order<F, MTMAX, LD>(acc, bufA, th + (size_t)k * F * F, MT, lane);
-        else mma_order<F, MTMAX, F>(acc, T0, th + (size_t)k * F * F, MT, lane);
+        mma_order<F, MTMAX>(acc, dst, th + (size_t)k * F * F, MT, lane);
       }
       __syncwarp();   // all lanes are done reading bufA before it becomes the output staging slab
       const int g = lane >> 2, tq = lane & 3;
@@ -489,7 +538,7 @@ int cheb_fwd_warp_try(const float* x, const int32_t* rowptr, const int32_t* coli
     return launch_warp<F_, R_, M_>(c, x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, meta, \
                                    max_nodes, st);
   FETA_WARP_CASE(4, 1, false) FETA_WARP_CASE(4, 2, false) FETA_WARP_CASE(8, 1, false) FETA_WARP_CASE(8, 2, false)
-  FETA_WARP_CASE(16, 1, false) FETA_WARP_CASE(16, 2, false) FETA_WARP_CASE(8, 1, true) FETA_WARP_CASE(8, 2, true)
+  FETA_WARP_CASE(16, 1, false) FETA_WARP_CASE(16, 2, false)
   FETA_WARP_CASE(16, 1, true) FETA_WARP_CASE(16, 2, true)
 #undef FETA_WARP_CASE
   return 1;
