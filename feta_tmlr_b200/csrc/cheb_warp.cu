@@ -140,17 +140,48 @@ __device__ __forceinline__ void gather_row_swz(float (&t)[16], const float* __re
   float2 a2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a2[i] = make_float2(0.f, 0.f);
-  for (int e = e0; e < e1; ++e) {
-    const int c = (STAGED ? ci[e] : __ldg(ci + e)) - r0;
-    const float w = STAGED ? cv[e] : __ldg(cv + e);
-    const float2 ww = make_float2(w, w);
-    const float* row = buf + c * 16;
-    const int sw = swz16(c);
+  if constexpr (STAGED) {
+    // two edges per trip: 8 independent LDS.128 in flight, half the loop overhead.  The slot one past the
+    // row's last edge is inside the staged slice (8 words of slack); its contents are replaced, not scaled.
+    for (int e = e0; e < e1; e += 2) {
+      const bool two = e + 1 < e1;
+      const int cA = ci[e] - r0;
+      const float wA = cv[e];
+      int cB = ci[e + 1] - r0;
+      float wB = cv[e + 1];
+      cB = two ? cB : cA;
+      wB = two ? wB : 0.0f;
+      const float* rowA = buf + cA * 16;
+      const float* rowB = buf + cB * 16;
+      const int swA = swz16(cA), swB = swz16(cB);
+      const float2 wwA = make_float2(wA, wA), wwB = make_float2(wB, wB);
+      float4 a[4], b[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 a = *reinterpret_cast<const float4*>(row + ((4 * q) ^ sw));
-      a2[2 * q] = __ffma2_rn(ww, make_float2(a.x, a.y), a2[2 * q]);
-      a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a.z, a.w), a2[2 * q + 1]);
+      for (int q = 0; q < 4; ++q) {
+        a[q] = *reinterpret_cast<const float4*>(rowA + ((4 * q) ^ swA));
+        b[q] = *reinterpret_cast<const float4*>(rowB + ((4 * q) ^ swB));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a2[2 * q] = __ffma2_rn(wwA, make_float2(a[q].x, a[q].y), a2[2 * q]);
+        a2[2 * q + 1] = __ffma2_rn(wwA, make_float2(a[q].z, a[q].w), a2[2 * q + 1]);
+        a2[2 * q] = __ffma2_rn(wwB, make_float2(b[q].x, b[q].y), a2[2 * q]);
+        a2[2 * q + 1] = __ffma2_rn(wwB, make_float2(b[q].z, b[q].w), a2[2 * q + 1]);
+      }
+    }
+  } else {
+    for (int e = e0; e < e1; ++e) {
+      const int c = __ldg(ci + e) - r0;
+      const float w = __ldg(cv + e);
+      const float2 ww = make_float2(w, w);
+      const float* row = buf + c * 16;
+      const int sw = swz16(c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = *reinterpret_cast<const float4*>(row + ((4 * q) ^ sw));
+        a2[2 * q] = __ffma2_rn(ww, make_float2(a.x, a.y), a2[2 * q]);
+        a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a.z, a.w), a2[2 * q + 1]);
+      }
     }
   }
 #pragma unroll
@@ -269,6 +300,12 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
   float bias_r[F];
 #pragma unroll
   for (int i = 0; i < F; ++i) bias_r[i] = bias ? __ldg(bias + i) : 0.0f;
+  float bias_m[(F + 7) / 8][2];  // MMA variant: the two output columns this lane owns in every n-tile
+#pragma unroll
+  for (int nt = 0; nt < (USE_MMA ? F / 8 : 0); ++nt) {
+    bias_m[nt][0] = bias ? __ldg(bias + 8 * nt + 2 * (lane & 3)) : 0.0f;
+    bias_m[nt][1] = bias ? __ldg(bias + 8 * nt + 2 * (lane & 3) + 1) : 0.0f;
+  }
 
   auto fetch_a = [&](int it, GraphDesc<RPL>& d) {  // stage "a": row range of the graph
     d.r0 = d.r1 = 0;
@@ -349,8 +386,10 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
     const float* th = reinterpret_cast<const float*>(st + TB);
     int a_lo, a_hi;
     const bool staged = staged_csr(d0, a_lo, a_hi);
-    const int32_t* ci = staged ? reinterpret_cast<const int32_t*>(st + TB + th_bytes) - a_lo : colidx;
-    const float* cv = staged ? reinterpret_cast<const float*>(st + TB + th_bytes + csr_bytes) - a_lo : vals;
+    // staged CSR slices stay typed as shared-memory pointers (a select against the global arrays would turn
+    // every access into a generic load)
+    const int32_t* ci_s = reinterpret_cast<const int32_t*>(st + TB + th_bytes) - a_lo;
+    const float* cv_s = reinterpret_cast<const float*>(st + TB + th_bytes + csr_bytes) - a_lo;
     const int n = d0.r1 - d0.r0;
     mbar_wait(smem_u32(&bars[s]), (uint32_t)((it >> 1) & 1));
     if (lane == 0) bulk_wait_read0();  // the previous graph's output store has drained bufA
@@ -396,8 +435,8 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
         for (int m = 0; m < RPL; ++m) {
           const int row = lane + 32 * m;
           if (row < n) {
-            if (staged) gather_row_swz<true>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-            else gather_row_swz<false>(t, src, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+            if (staged) gather_row_swz<true>(t, src, d0.r0, ci_s, cv_s, d0.e0[m], d0.e1[m]);
+            else gather_row_swz<false>(t, src, d0.r0, colidx, vals, d0.e0[m], d0.e1[m]);
             float* drow = dst + row * F;
             const int sw = swz16(row);
             if (k >= 2) {
@@ -425,7 +464,7 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
             const int col = 8 * nt + 2 * tq;
-            const float b0 = bias ? __ldg(bias + col) : 0.0f, b1 = bias ? __ldg(bias + col + 1) : 0.0f;
+            const float b0 = bias_m[nt][0], b1 = bias_m[nt][1];
             const int ra = 16 * mt + g, rb = ra + 8;
             if (ra < n) *reinterpret_cast<float2*>(bufA + ra * F + col) = make_float2(acc[mt][nt][0] + b0, acc[mt][nt][1] + b1);
             if (rb < n) *reinterpret_cast<float2*>(bufA + rb * F + col) = make_float2(acc[mt][nt][2] + b0, acc[mt][nt][3] + b1);
@@ -458,11 +497,11 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
           const int row = lane + 32 * m;
           if (row < n) {
             if (odd) {
-              if (staged) gather_row_w<F, F, true>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-              else gather_row_w<F, F, false>(t, T0, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              if (staged) gather_row_w<F, F, true>(t, T0, d0.r0, ci_s, cv_s, d0.e0[m], d0.e1[m]);
+              else gather_row_w<F, F, false>(t, T0, d0.r0, colidx, vals, d0.e0[m], d0.e1[m]);
             } else {
-              if (staged) gather_row_w<F, LD, true>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
-              else gather_row_w<F, LD, false>(t, bufA, d0.r0, ci, cv, d0.e0[m], d0.e1[m]);
+              if (staged) gather_row_w<F, LD, true>(t, bufA, d0.r0, ci_s, cv_s, d0.e0[m], d0.e1[m]);
+              else gather_row_w<F, LD, false>(t, bufA, d0.r0, colidx, vals, d0.e0[m], d0.e1[m]);
             }
             float* drow = odd ? bufA + row * LD : T0 + row * F;
             if (k >= 2) {
