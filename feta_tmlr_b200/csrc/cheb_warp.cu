@@ -66,8 +66,12 @@ static inline size_t warp_region_bytes(int F, int K, int rows_cap, int nnz_cap, 
   const size_t ta = (size_t)rows_cap * (mma ? F : F + 4) * 4;
   const size_t t0 = (size_t)rows_cap * F * 4;        // x slab / even orders, dense (one bulk copy)
   const size_t csr = align_up((size_t)(nnz_cap + 8) * 4, 16);
-  const size_t stage = t0 + (size_t)K * F * F * 4 + 2 * csr;
-  return align_up(16 + ta + 2 * stage, 128);
+  const size_t th = (size_t)K * F * F * 4;
+  // FFMA2 variant: Theta travels with the double-buffered stage.  MMA variant: ONE Theta buffer with its own
+  // barrier, refilled right after the last order's MMAs (the copy hides behind the epilogue and the next
+  // graph's first propagation) -- 4 KB less per warp, 16 warps per SM.
+  const size_t stage = t0 + (mma ? 0 : th) + 2 * csr;
+  return align_up(32 + ta + (mma ? th : 0) + 2 * stage, 128);
 }
 
 static WarpCfg warp_config(int F, int K, int max_nodes) {
@@ -81,8 +85,9 @@ static WarpCfg warp_config(int F, int K, int max_nodes) {
   c.rows_cap = (max_nodes + 7) / 8 * 8;
   c.nnz_cap = c.rows_cap * 4;
   c.per_warp = warp_region_bytes(F, K, c.rows_cap, c.nnz_cap, c.mma);
-  int w = (int)((220 * 1024) / c.per_warp);
-  if (w > (F >= 16 ? 12 : 16)) w = (F >= 16 ? 12 : 16);
+  int w = (int)((227 * 1024) / c.per_warp);
+  const int wmax = F >= 16 ? 12 : 16;
+  if (w > wmax) w = wmax;
   if (w < 4) return c;
   c.warps = w;
   c.smem = c.per_warp * w;
@@ -251,13 +256,14 @@ struct GraphDesc {  // scalars of one graph, fetched ahead of use
   int e0[RPL], e1[RPL];
 };
 
-template <int F>
+template <int F, bool USE_MMA>
 constexpr int warp_kernel_max_threads() {
-  return F >= 16 ? 384 : 512;   // F = 16: at most 12 warps fit shared memory -> ~170 registers/thread allowed
+  // FFMA2 variant at F = 16: at most 12 warps fit shared memory -> ~170 registers/thread allowed
+  return F >= 16 ? 384 : 512;   // 12 warps = 3 per scheduler -> 168 registers; 13..16 warps would cap at 128 (spills, measured slower)
 }
 
 template <int F, int RPL, bool USE_MMA>
-__global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp_kernel(
+__global__ void __launch_bounds__(warp_kernel_max_threads<F, USE_MMA>(), 1) cheb_fwd_warp_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
     const float* __restrict__ vals, const int32_t* __restrict__ graph_ptr, const float* __restrict__ theta,
     int64_t sk, int64_t sg, const float* __restrict__ bias, float* __restrict__ out, int64_t R, int64_t G, int K,
@@ -284,15 +290,18 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
   unsigned char* base = smem_raw + (size_t)warp * per_warp_bytes;
   const uint32_t csr_bytes = (uint32_t)(((nnz_cap + 8) * 4 + 15) / 16 * 16);
   const uint32_t th_bytes = (uint32_t)K * F * F * 4;
-  const uint32_t stage_bytes = TB + th_bytes + 2 * csr_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base);
-  float* bufA = reinterpret_cast<float*>(base + 16);
-  unsigned char* stage0 = base + 16 + TA;
+  const uint32_t th_stage = USE_MMA ? 0u : th_bytes;   // Theta bytes inside a stage (FFMA2 variant only)
+  const uint32_t stage_bytes = TB + th_stage + 2 * csr_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base);   // [0], [1]: stages; [2]: the single Theta buffer
+  float* bufA = reinterpret_cast<float*>(base + 32);
+  unsigned char* th_single = base + 32 + TA;            // MMA variant
+  unsigned char* stage0 = base + 32 + TA + (USE_MMA ? th_bytes : 0u);
   const bool theta_contig = (sk == (int64_t)F * F);
 
   if (lane == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
     mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -347,21 +356,39 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
     int a_lo, a_hi;
     const bool staged = staged_csr(d, a_lo, a_hi);
     const bool copy_csr = staged && (d.e_hi > d.e_lo);
-    const uint32_t bytes = (uint32_t)n * F * 4 + th_bytes + (copy_csr ? 2u * (uint32_t)(a_hi - a_lo) * 4u : 0u);
+    const uint32_t bytes = (uint32_t)n * F * 4 + th_stage + (copy_csr ? 2u * (uint32_t)(a_hi - a_lo) * 4u : 0u);
     fence_proxy_async();  // generic-proxy writes into this stage (even orders) before the TMA refills it
     __syncwarp();         // every lane is done with this stage (used two graphs ago)
     if (lane == 0) {  // one thread drives the TMA: 1 x-slab + 1 (or K) Theta + 2 CSR copies per graph
       mbar_arrive_expect_tx(bar, bytes);
       bulk_g2s(smem_u32(st), x + (size_t)d.r0 * F, (uint32_t)n * F * 4, bar);
-      if (theta_contig) {
-        bulk_g2s(smem_u32(st + TB), theta + g * sg, th_bytes, bar);
-      } else {
-        for (int k = 0; k < K; ++k)
-          bulk_g2s(smem_u32(st + TB + (size_t)k * F * F * 4), theta + g * sg + (int64_t)k * sk, F * F * 4, bar);
+      if constexpr (!USE_MMA) {
+        if (theta_contig) {
+          bulk_g2s(smem_u32(st + TB), theta + g * sg, th_bytes, bar);
+        } else {
+          for (int k = 0; k < K; ++k)
+            bulk_g2s(smem_u32(st + TB + (size_t)k * F * F * 4), theta + g * sg + (int64_t)k * sk, F * F * 4, bar);
+        }
       }
       if (copy_csr) {
-        bulk_g2s(smem_u32(st + TB + th_bytes), colidx + a_lo, (uint32_t)(a_hi - a_lo) * 4, bar);
-        bulk_g2s(smem_u32(st + TB + th_bytes + csr_bytes), vals + a_lo, (uint32_t)(a_hi - a_lo) * 4, bar);
+        bulk_g2s(smem_u32(st + TB + th_stage), colidx + a_lo, (uint32_t)(a_hi - a_lo) * 4, bar);
+        bulk_g2s(smem_u32(st + TB + th_stage + csr_bytes), vals + a_lo, (uint32_t)(a_hi - a_lo) * 4, bar);
+      }
+    }
+  };
+  // MMA variant: refill the single Theta buffer for graph `it`; the caller has synchronised the warp after
+  // the last read of the previous graph's Theta
+  auto issue_theta = [&](int it) {
+    if (it >= n_it) return;
+    if (lane == 0) {
+      const int64_t g = gw + (int64_t)it * stride;
+      const uint32_t bar = smem_u32(&bars[2]);
+      mbar_arrive_expect_tx(bar, th_bytes);
+      if (theta_contig) {
+        bulk_g2s(smem_u32(th_single), theta + g * sg, th_bytes, bar);
+      } else {
+        for (int k = 0; k < K; ++k)
+          bulk_g2s(smem_u32(th_single + (size_t)k * F * F * 4), theta + g * sg + (int64_t)k * sk, F * F * 4, bar);
       }
     }
   };
@@ -373,6 +400,7 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
   fetch_b(0, d0);
   fetch_b(1, d1);
   issue(0, d0);
+  if constexpr (USE_MMA) issue_theta(0);
 
   for (int it = 0; it < n_it; ++it) {
     fetch_a(it + 3, d3);
@@ -383,13 +411,13 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
     const int s = it & 1;
     unsigned char* st = stage0 + (size_t)s * stage_bytes;
     float* T0 = reinterpret_cast<float*>(st);
-    const float* th = reinterpret_cast<const float*>(st + TB);
+    const float* th = reinterpret_cast<const float*>(USE_MMA ? th_single : st + TB);
     int a_lo, a_hi;
     const bool staged = staged_csr(d0, a_lo, a_hi);
     // staged CSR slices stay typed as shared-memory pointers (a select against the global arrays would turn
     // every access into a generic load)
-    const int32_t* ci_s = reinterpret_cast<const int32_t*>(st + TB + th_bytes) - a_lo;
-    const float* cv_s = reinterpret_cast<const float*>(st + TB + th_bytes + csr_bytes) - a_lo;
+    const int32_t* ci_s = reinterpret_cast<const int32_t*>(st + TB + th_stage) - a_lo;
+    const float* cv_s = reinterpret_cast<const float*>(st + TB + th_stage + csr_bytes) - a_lo;
     const int n = d0.r1 - d0.r0;
     mbar_wait(smem_u32(&bars[s]), (uint32_t)((it >> 1) & 1));
     if (lane == 0) bulk_wait_read0();  // the previous graph's output store has drained bufA
@@ -423,7 +451,8 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
         }
         __syncwarp();
       }
-      mma_order<F, MTMAX>(acc, T0, th, MT, lane);                    // k = 0
+      // order of work: T_1 is propagated BEFORE the first filter application, so that the Theta copy (issued
+      // at the end of the previous graph) has the epilogue, the re-lay and one propagation to land
       float t[F];
       for (int k = 1; k < K; ++k) {
         // even orders live in the stage buffer T0, odd orders in bufA (both swizzled); T_k overwrites the
@@ -454,8 +483,18 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F>(), 1) cheb_fwd_warp
           }
         }
         __syncwarp();
+        if (k == 1) {
+          mbar_wait(smem_u32(&bars[2]), (uint32_t)(it & 1));
+          mma_order<F, MTMAX>(acc, T0, th, MT, lane);   // k = 0 (before order 2 overwrites the x slab)
+        }
         mma_order<F, MTMAX>(acc, dst, th + (size_t)k * F * F, MT, lane);
       }
+      if (K == 1) {
+        mbar_wait(smem_u32(&bars[2]), (uint32_t)(it & 1));
+        mma_order<F, MTMAX>(acc, T0, th, MT, lane);
+      }
+      __syncwarp();          // every lane has read its last Theta fragment
+      issue_theta(it + 1);
       __syncwarp();   // all lanes are done reading bufA before it becomes the output staging slab
       const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
