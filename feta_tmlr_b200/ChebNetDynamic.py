@@ -1,4 +1,5 @@
-"""Drop-in ``ChebConvDynamic`` (reference: transformer/ChebNetDynamic.py:29-198).
+"""Drop-in ``ChebConvDynamic`` (reference: transformer/ChebNetDynamic.py:29-198) and
+``ARMAConvDynamic`` (:201-358).
 
 Same constructor, ``forward`` signature, parameter names (``bias``; ``weight`` only in
 ``learn_only_filter_order_coeff`` mode) and output shape as the reference's PyG module, but the
@@ -70,7 +71,8 @@ class ChebConvDynamic(nn.Module):
         if hit is not None:
             self._plans.move_to_end(key)
             return hit
-        plan = ops.build_cheb_plan(edge_index, batch, num_rows, num_graphs, lambda_max, hints=hints)
+        plan = ops.build_cheb_plan(edge_index, batch, num_rows, num_graphs, lambda_max, hints=hints,
+                                   norm=getattr(self, '_plan_norm', ops.NORM_CHEB_SYM))
         plan._keep = (edge_index, batch)     # pins the storage so the identity key cannot be recycled
         self._plans[key] = plan
         while len(self._plans) > 4:
@@ -116,3 +118,79 @@ class ChebConvDynamic(nn.Module):
     def __repr__(self):
         return '{}({}, {}, K={}, normalization={})'.format(
             self.__class__.__name__, self.in_channels, self.out_channels, self.K, self.normalization)
+
+
+class ARMAConvDynamic(nn.Module):
+    """Drop-in for the reference's ``ARMAConvDynamic`` (transformer/ChebNetDynamic.py:201-358) as the
+    encoder instantiates it (``num_layers=1``, transformer/models.py:139).
+
+    Same constructor, parameter names and shapes (``init_weight [K,Fin,Fout]``, ``weight
+    [max(1,T-1),K,Fout,Fout]``, ``root_weight [T,K,Fin,Fout]``, ``bias [T,K,1,Fout]``) so reference
+    checkpoints load; ``forward(x, edge_index, filter_coeff [G, 2K], batch=...)`` is one fused kernel
+    (csrc/arma.cu) over a ``gcn_norm`` CSR plan.  Configurations the fused kernel does not cover raise.
+    """
+    get_plan = ChebConvDynamic.get_plan
+    __deepcopy__ = ChebConvDynamic.__deepcopy__
+
+    def __init__(self, in_channels, out_channels, num_stacks=1, num_layers=1, shared_weights=False,
+                 act='relu', dropout=0., bias=True, **kwargs):
+        aggr = kwargs.pop('aggr', 'add')
+        if aggr != 'add' or kwargs:
+            raise NotImplementedError("ARMAConvDynamic(b200): only aggr='add' is implemented")
+        super().__init__()
+        if num_layers != 1:
+            raise NotImplementedError("ARMAConvDynamic(b200): only num_layers=1 is implemented (the only value "
+                                      "the reference uses, transformer/models.py:139)")
+        if in_channels != out_channels:
+            raise ValueError("ARMAConvDynamic: in_channels must equal out_channels "
+                             "(_batch_multiply_coeff reshapes with shape[-2] twice, ChebNetDynamic.py:284)")
+        if not (act == 'relu' or isinstance(act, nn.ReLU)):
+            raise NotImplementedError("ARMAConvDynamic(b200): only the default ReLU activation is implemented")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_stacks, self.num_layers = num_stacks, num_layers
+        self.act = nn.ReLU()
+        self.shared_weights = shared_weights
+        self.dropout = dropout
+        K, T, F_in, F_out = num_stacks, num_layers, in_channels, out_channels
+        T = 1 if shared_weights else T
+        self.init_weight = nn.Parameter(torch.empty(K, F_in, F_out))
+        self.weight = nn.Parameter(torch.empty(max(1, T - 1), K, F_out, F_out))   # unused when num_layers == 1
+        self.root_weight = nn.Parameter(torch.empty(T, K, F_in, F_out))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(T, K, 1, F_out))
+        else:
+            self.register_parameter('bias', None)
+        self._plans = OrderedDict()
+        self._plan_norm = ops.NORM_GCN
+        self.plan_hints = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for w in (self.init_weight, self.weight, self.root_weight):    # glorot, ChebNetDynamic.py:268-272
+            stdv = math.sqrt(6.0 / (w.size(-2) + w.size(-1)))
+            w.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.fill_(0)
+
+    def forward(self, x, edge_index, filter_coeff, edge_weight=None, batch=None, plan=None):
+        """ChebNetDynamic.py:297-346.  ``plan`` (extension): a prebuilt NORM_GCN ``ops.ChebPlan``."""
+        if edge_weight is not None:
+            raise NotImplementedError("ARMAConvDynamic(b200): edge_weight is not implemented "
+                                      "(never passed by the reference, models.py:363)")
+        if batch is None:
+            raise NotImplementedError("ARMAConvDynamic(b200): pass `batch` (per-node filter_coeff rows without "
+                                      "a batch vector are not implemented)")
+        if filter_coeff.dim() != 2 or filter_coeff.size(1) != 2 * self.num_stacks:
+            raise ValueError("filter_coeff must be [G, 2*num_stacks]; got %s" % (tuple(filter_coeff.shape),))
+        R, G = x.size(0), filter_coeff.size(0)
+        if plan is None:
+            plan = self.get_plan(edge_index, batch, R, G, 2.0, hints=self.plan_hints)
+        x_root = None
+        if self.training and self.dropout > 0:
+            x_root = torch.nn.functional.dropout(x, p=self.dropout, training=True)    # :335
+        bias = None if self.bias is None else self.bias[0].reshape(self.num_stacks, self.out_channels)
+        return ops.arma_filter(x, filter_coeff, self.init_weight, self.root_weight[0], bias, plan, x_root=x_root)
+
+    def __repr__(self):
+        return '{}({}, {}, num_stacks={}, num_layers={})'.format(
+            self.__class__.__name__, self.in_channels, self.out_channels, self.num_stacks, self.num_layers)

@@ -7,7 +7,7 @@ Module layout mirrors the reference's ``transformer/`` package for the path only
 the C ABI of ``libfeta_b200.so`` (``include/feta_b200.h``); there is no CPU fallback.
 """
 from . import utils  # noqa: F401
-from .ChebNetDynamic import ChebConvDynamic  # noqa: F401
+from .ChebNetDynamic import ARMAConvDynamic, ChebConvDynamic  # noqa: F401
 from .layers import DiffTransformerEncoderLayer  # noqa: F401
 from .models import (DiffTransformerEncoderGenGCN, DiffGraphTransformerGenGCN,  # noqa: F401
                      DiffGraphTransformerGenGCNSBM, DiffGraphTransformerGenGCNMolHiv, GlobalAvg1D)

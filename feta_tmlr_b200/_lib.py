@@ -20,12 +20,18 @@ SIGNATURES = {
     "feta_cheb_plan_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "feta_cheb_plan_build": (c_int, [_P, c_int64, _P, c_int, c_int64, c_int64, c_float,
                                      _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "feta_graph_plan_build": (c_int, [_P, c_int64, _P, c_int, c_int64, c_int64, c_int, c_float,
+                                      _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "feta_cheb_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
     "feta_cheb_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P,
                               c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "feta_cheb_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64,
                               _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int,
                               _P, c_size_t, _P]),
+    "feta_arma_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                              c_int64, c_int64, c_int, c_int, c_int, _P]),
+    "feta_arma_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                              c_int64, c_int64, c_int, c_int, c_int, _P]),
     "feta_attn_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, c_int64, _P,
                               c_int, c_int, c_int, c_int, c_float, c_int, _P]),
     "feta_attn_bwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P,

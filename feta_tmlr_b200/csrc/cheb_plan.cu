@@ -20,7 +20,7 @@ __global__ void plan_init_meta_kernel(int32_t* meta) {
 
 __global__ void __launch_bounds__(kThreads) plan_count_kernel(const int64_t* __restrict__ ei, int64_t E,
                                                              int64_t R, int32_t* outdeg, int32_t* indeg,
-                                                             int32_t* meta) {
+                                                             int32_t* meta, bool keep_self) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = ei[e], t = ei[E + e];
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kThreads) plan_count_kernel(const int64_t* __r
       meta[6] = 1;  // out-of-range endpoint: reported by the host wrapper
       continue;
     }
-    if (s != t) {  // remove_self_loops, ChebNetDynamic.py:113
+    if (s != t || keep_self) {  // remove_self_loops, ChebNetDynamic.py:113 (gcn_norm keeps them)
       atomicAdd(&outdeg[s], 1);
       atomicAdd(&indeg[t], 1);
     }
@@ -39,11 +39,11 @@ __global__ void __launch_bounds__(kThreads) plan_fill_kernel(const int64_t* __re
                                                             int64_t R, const int32_t* __restrict__ rowptr,
                                                             const int32_t* __restrict__ rowptr_t,
                                                             int32_t* cursor, int32_t* cursor_t,
-                                                            int32_t* tmp, int32_t* tmp_t) {
+                                                            int32_t* tmp, int32_t* tmp_t, bool keep_self) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = ei[e], t = ei[E + e];
-    if (s < 0 || s >= R || t < 0 || t >= R || s == t) continue;
+    if (s < 0 || s >= R || t < 0 || t >= R || (s == t && !keep_self)) continue;
     tmp[rowptr[t] + atomicAdd(&cursor[t], 1)] = (int32_t)e;
     tmp_t[rowptr_t[s] + atomicAdd(&cursor_t[s], 1)] = (int32_t)e;
   }
@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(kThreads) plan_fill_kernel(const int64_t* __re
 // One thread per edge: its final slot inside the row is the number of row-mates with a smaller
 // edge id, which restores input order whatever order the atomics claimed the slots in.
 __global__ void __launch_bounds__(kThreads) plan_rank_kernel(
-    const int64_t* __restrict__ ei, int64_t E, int64_t R, float two_over_lambda,
-    const int32_t* __restrict__ outdeg, const int32_t* __restrict__ rowptr,
+    const int64_t* __restrict__ ei, int64_t E, int64_t R, float two_over_lambda, int norm_mode,
+    const int32_t* __restrict__ outdeg, const int32_t* __restrict__ indeg, const int32_t* __restrict__ rowptr,
     const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ tmp,
     const int32_t* __restrict__ tmp_t, int32_t* __restrict__ colidx, float* __restrict__ vals,
     int32_t* __restrict__ colidx_t, float* __restrict__ vals_t, int32_t* meta) {
@@ -61,12 +61,14 @@ __global__ void __launch_bounds__(kThreads) plan_rank_kernel(
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = ei[e], t = ei[E + e];
-    if (s < 0 || s >= R || t < 0 || t >= R || s == t) continue;
+    const bool gcn = norm_mode == FETA_NORM_GCN;
+    if (s < 0 || s >= R || t < 0 || t >= R || (s == t && !gcn)) continue;
     // get_laplacian('sym'): deg over the SOURCE index, deg^-1/2 with inf -> 0
-    const int32_t ds = outdeg[s], dt = outdeg[t];
+    // gcn_norm (ARMAConvDynamic, ChebNetDynamic.py:301-305): deg over the TARGET index, self-loops kept
+    const int32_t ds = gcn ? indeg[s] : outdeg[s], dt = gcn ? indeg[t] : outdeg[t];
     const float is = ds > 0 ? 1.0f / sqrtf((float)ds) : 0.0f;
     const float it = dt > 0 ? 1.0f / sqrtf((float)dt) : 0.0f;
-    const float w = -(is * it) * two_over_lambda;  // (2 * -w) / lambda_max, :122
+    const float w = gcn ? is * it : -(is * it) * two_over_lambda;  // (2 * -w) / lambda_max, :122
     {
       const int32_t a = rowptr[t], b = rowptr[t + 1];
       int32_t rank = 0;
@@ -183,7 +185,20 @@ extern "C" int feta_cheb_plan_build(const int64_t* edge_index, int64_t E, const 
                                     float* vals, int32_t* rowptr_t, int32_t* colidx_t, float* vals_t,
                                     int32_t* graph_ptr, int32_t* row_graph, int32_t* meta, void* workspace,
                                     size_t workspace_bytes, void* stream_) {
+  return feta_graph_plan_build(edge_index, E, batch, batch_dtype, R, G, FETA_NORM_CHEB_SYM, lambda_max, rowptr,
+                               colidx, vals, rowptr_t, colidx_t, vals_t, graph_ptr, row_graph, meta, workspace,
+                               workspace_bytes, stream_);
+}
+
+extern "C" int feta_graph_plan_build(const int64_t* edge_index, int64_t E, const void* batch, int batch_dtype,
+                                     int64_t R, int64_t G, int norm_mode, float lambda_max, int32_t* rowptr,
+                                     int32_t* colidx, float* vals, int32_t* rowptr_t, int32_t* colidx_t,
+                                     float* vals_t, int32_t* graph_ptr, int32_t* row_graph, int32_t* meta,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  FETA_REQUIRE(norm_mode == FETA_NORM_CHEB_SYM || norm_mode == FETA_NORM_GCN, "plan_build: bad norm_mode %d",
+               norm_mode);
+  const bool keep_self = norm_mode == FETA_NORM_GCN;
   FETA_REQUIRE(R >= 0 && E >= 0 && G >= 1, "plan_build: bad sizes R=%lld E=%lld G=%lld", (long long)R,
                (long long)E, (long long)G);
   FETA_REQUIRE(R < (1ll << 31) && E < (1ll << 31), "plan_build: R/E exceed int32 index range");
@@ -216,7 +231,7 @@ extern "C" int feta_cheb_plan_build(const int64_t* edge_index, int64_t E, const 
   // outdeg, indeg, cursor, cursor_t are contiguous arena blocks
   FETA_CUDA(cudaMemsetAsync(outdeg, 0, (size_t)((char*)tmp - (char*)outdeg), stream));
   if (E > 0) {
-    plan_count_kernel<<<grid_for(E), kThreads, 0, stream>>>(edge_index, E, R, outdeg, indeg, meta);
+    plan_count_kernel<<<grid_for(E), kThreads, 0, stream>>>(edge_index, E, R, outdeg, indeg, meta, keep_self);
     FETA_LAUNCH_CHECK();
   }
   int rc = exclusive_scan_i32(indeg, rowptr, R, 1, scratch, stream);
@@ -225,11 +240,11 @@ extern "C" int feta_cheb_plan_build(const int64_t* edge_index, int64_t E, const 
   if (rc) return rc;
   if (E > 0) {
     plan_fill_kernel<<<grid_for(E), kThreads, 0, stream>>>(edge_index, E, R, rowptr, rowptr_t, cursor, cursor_t,
-                                                          tmp, tmp_t);
+                                                          tmp, tmp_t, keep_self);
     FETA_LAUNCH_CHECK();
-    plan_rank_kernel<<<grid_for(E), kThreads, 0, stream>>>(edge_index, E, R, 2.0f / lambda_max, outdeg, rowptr,
-                                                          rowptr_t, tmp, tmp_t, colidx, vals, colidx_t, vals_t,
-                                                          meta);
+    plan_rank_kernel<<<grid_for(E), kThreads, 0, stream>>>(edge_index, E, R, 2.0f / lambda_max, norm_mode, outdeg,
+                                                          indeg, rowptr, rowptr_t, tmp, tmp_t, colidx, vals,
+                                                          colidx_t, vals_t, meta);
     FETA_LAUNCH_CHECK();
   }
   FETA_CUDA(cudaMemcpyAsync(meta + FETA_META_NNZ, rowptr + R, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));

@@ -117,8 +117,14 @@ class ChebPlan(object):
         return m
 
 
-def build_cheb_plan(edge_index, batch, num_rows, num_graphs, lambda_max=2.0, hints=None):
+NORM_CHEB_SYM, NORM_GCN = 0, 1      # FETA_NORM_* of include/feta_b200.h
+
+
+def build_cheb_plan(edge_index, batch, num_rows, num_graphs, lambda_max=2.0, hints=None, norm=NORM_CHEB_SYM):
     """Build the plan on the current stream.
+
+    ``norm`` -- NORM_CHEB_SYM: the scaled Laplacian of ``ChebConvDynamic.__norm__``; NORM_GCN: the
+    ``gcn_norm(add_self_loops=False)`` operator of ``ARMAConvDynamic.forward`` (ChebNetDynamic.py:301-305).
 
     ``hints`` -- optional dict ``{'max_nodes': int, 'block_diagonal': bool}`` supplied by a caller
     that already knows them on the host (e.g. the padded width Nmax of the mini-batch).  With
@@ -153,11 +159,11 @@ def build_cheb_plan(edge_index, batch, num_rows, num_graphs, lambda_max=2.0, hin
     p.meta = torch.empty(META_WORDS, **i32)
     ws_bytes = lib.feta_cheb_plan_workspace_bytes(R, E)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib.feta_cheb_plan_build(
+    check(lib.feta_graph_plan_build(
         _ptr(edge_index), E, _ptr(batch), _DT[batch.dtype] if batch is not None else 0, R, G,
-        float(lambda_max), _ptr(p.rowptr), _ptr(p.colidx), _ptr(p.vals), _ptr(p.rowptr_t),
+        int(norm), float(lambda_max), _ptr(p.rowptr), _ptr(p.colidx), _ptr(p.vals), _ptr(p.rowptr_t),
         _ptr(p.colidx_t), _ptr(p.vals_t), _ptr(p.graph_ptr), _ptr(p.row_graph), _ptr(p.meta),
-        _ptr(ws), ws_bytes, _stream()), "feta_cheb_plan_build")
+        _ptr(ws), ws_bytes, _stream()), "feta_graph_plan_build")
     p.num_rows, p.num_edges, p.num_graphs = R, E, G
     p._keep = None
     p.validated = False
@@ -255,6 +261,92 @@ class ChebFilterFn(torch.autograd.Function):
 
 def cheb_filter(x, theta, bias, plan):
     return ChebFilterFn.apply(x, theta, bias, plan)
+
+
+# =====================================================================================
+# N4: fused ARMA filter (ARMAConvDynamic, num_layers = 1)
+# =====================================================================================
+def _wgrad(dy, x):
+    """dW[out, in] = dy^T x and db[out] = colsum(dy) through feta_linear_wgrad."""
+    lib = _lib.load()
+    T, out_f = dy.shape
+    in_f = x.shape[1]
+    S = lib.feta_linear_wgrad_slices(T)
+    n_part = S * (out_f * in_f + out_f)
+    partial = torch.empty(n_part, dtype=torch.float32, device=dy.device)
+    dw = torch.empty((out_f, in_f), dtype=torch.float32, device=dy.device)
+    db = torch.empty(out_f, dtype=torch.float32, device=dy.device)
+    check(lib.feta_linear_wgrad(_ptr(dy), _ptr(x), _ptr(dw), _ptr(db), _ptr(partial), n_part,
+                                _ptr(_counters(dy.device)), T, out_f, in_f, _stream()), "feta_linear_wgrad")
+    return dw, db
+
+
+class ArmaFilterFn(torch.autograd.Function):
+    """out = 1/K sum_k relu(a[g,k] (A_hat x) W_k + b[g,k] x_root V_k + bias_k)  (ChebNetDynamic.py:297-346)."""
+
+    @staticmethod
+    def forward(ctx, x, x_root, coeff, init_weight, root_weight, bias, plan):
+        _need_cuda(x, coeff, init_weight, root_weight, bias)
+        lib = _lib.load()
+        x = _f32c(x)
+        same_root = x_root is None
+        xr = x if same_root else _f32c(x_root)
+        coeff = _f32c(coeff)
+        W, V = _f32c(init_weight), _f32c(root_weight)
+        b = None if bias is None else _f32c(bias)
+        K, F = W.shape[0], W.shape[1]
+        R, G = x.shape[0], coeff.shape[0]
+        if W.shape != (K, F, F) or V.shape != (K, F, F) or x.shape[1] != F:
+            raise ValueError("ARMAConvDynamic needs in_channels == out_channels (ChebNetDynamic.py:284); "
+                             "got x %s, init_weight %s, root_weight %s" % (tuple(x.shape), tuple(W.shape), tuple(V.shape)))
+        if coeff.shape[1] != 2 * K:
+            raise ValueError("filter_coeff must be [G, 2*num_stacks]; got %s" % (tuple(coeff.shape),))
+        if G != plan.num_graphs or R != plan.num_rows:
+            raise ValueError("plan was built for R=%d G=%d, got R=%d G=%d" % (plan.num_rows, plan.num_graphs, R, G))
+        if not plan.block_diagonal:
+            raise _lib.FetaError("ARMAConvDynamic: edges must stay inside their graph")
+        out = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        prop = torch.empty((R, F), dtype=torch.float32, device=x.device)
+        check(lib.feta_arma_fwd(_ptr(x), None if same_root else _ptr(xr), _ptr(plan.rowptr), _ptr(plan.colidx),
+                                _ptr(plan.vals), _ptr(plan.graph_ptr), _ptr(plan.row_graph), _ptr(plan.meta),
+                                _ptr(coeff), _ptr(W), _ptr(V), _ptr(b), _ptr(out), _ptr(prop), R, G, K, F,
+                                plan.max_nodes, _stream()), "feta_arma_fwd")
+        ctx.save_for_backward(prop, xr, coeff, W, V, b if b is not None else W.new_empty(0))
+        ctx.plan, ctx.same_root, ctx.has_bias = plan, same_root, b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        prop, xr, coeff, W, V, b = ctx.saved_tensors
+        plan = ctx.plan
+        K, F = W.shape[0], W.shape[1]
+        R, G = prop.shape[0], coeff.shape[0]
+        dout = _f32c(dout)
+        dev = dout.device
+        dx = torch.empty((R, F), dtype=torch.float32, device=dev)
+        dxr = None if ctx.same_root else torch.empty((R, F), dtype=torch.float32, device=dev)
+        dz = torch.empty((R, K * F), dtype=torch.float32, device=dev)
+        dza, dzb = torch.empty_like(dz), torch.empty_like(dz)
+        dcoeff = torch.zeros((G, 2 * K), dtype=torch.float32, device=dev)
+        check(lib.feta_arma_bwd(_ptr(dout), _ptr(prop), _ptr(xr), _ptr(plan.rowptr_t), _ptr(plan.colidx_t),
+                                _ptr(plan.vals_t), _ptr(plan.graph_ptr), _ptr(plan.row_graph), _ptr(plan.meta),
+                                _ptr(coeff), _ptr(W), _ptr(V), _ptr(b) if ctx.has_bias else None, _ptr(dx),
+                                _ptr(dxr), _ptr(dz), _ptr(dza), _ptr(dzb), _ptr(dcoeff), R, G, K, F,
+                                plan.max_nodes, _stream()), "feta_arma_bwd")
+        # [K*F, F] (row k*F + j, column f)  ->  [K, F(f), F(j)]
+        dW = dV = dbias = None
+        if ctx.needs_input_grad[3]:
+            dW = _wgrad(dza, prop)[0].view(K, F, F).transpose(1, 2).contiguous()
+        if ctx.needs_input_grad[4]:
+            dV = _wgrad(dzb, xr)[0].view(K, F, F).transpose(1, 2).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[5]:
+            dbias = _wgrad(dz, xr)[1].view(K, F)
+        return dx, dxr, dcoeff, dW, dV, dbias, None
+
+
+def arma_filter(x, coeff, init_weight, root_weight, bias, plan, x_root=None):
+    return ArmaFilterFn.apply(x, x_root, coeff, init_weight, root_weight, bias, plan)
 
 
 # =====================================================================================

@@ -96,6 +96,21 @@ int feta_cheb_plan_build(const int64_t* edge_index /* [2, E] */, int64_t num_edg
  * hints instead of synchronising on the meta words cannot fault the GPU, and finds out at
  * its next synchronisation point.
  * --------------------------------------------------------------------------------------- */
+/* The same builder with the normalisation chosen by `norm_mode`:
+ *   FETA_NORM_CHEB_SYM  the scaled Laplacian above (feta_cheb_plan_build == this mode);
+ *   FETA_NORM_GCN       ARMAConvDynamic.forward's gcn_norm(add_self_loops=False)
+ *                       (transformer/ChebNetDynamic.py:301-305): vals = d_s^-1/2 d_t^-1/2 with the degree
+ *                       counted over the TARGET index, input self-loops kept, lambda_max ignored. */
+#define FETA_NORM_CHEB_SYM 0
+#define FETA_NORM_GCN 1
+int feta_graph_plan_build(const int64_t* edge_index /* [2, E] */, int64_t num_edges,
+                          const void* batch /* [R] or NULL */, int batch_dtype, int64_t num_rows,
+                          int64_t num_graphs, int norm_mode, float lambda_max,
+                          int32_t* rowptr, int32_t* colidx, float* vals,
+                          int32_t* rowptr_t, int32_t* colidx_t, float* vals_t,
+                          int32_t* graph_ptr, int32_t* row_graph, int32_t* meta,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 size_t feta_cheb_workspace_bytes(int64_t num_rows, int fin, int fout, int K);
 int feta_cheb_fwd(const float* x /* [R, Fin] */, const int32_t* rowptr, const int32_t* colidx,
                   const float* vals, const int32_t* graph_ptr, const int32_t* row_graph,
@@ -115,6 +130,36 @@ int feta_cheb_bwd(const float* dout /* [R, Fout] */, const float* x, const int32
                   int64_t theta_stride_g, float* dx, float* dtheta, float* dbias, int64_t num_rows,
                   int64_t num_graphs, int K, int fin, int fout, int max_nodes, int block_diagonal,
                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * N4  ARMAConvDynamic.forward  (transformer/ChebNetDynamic.py:297-346; constructed with
+ *     num_layers = 1 at transformer/models.py:139; _batch_multiply_coeff :274-295)
+ *     out[r] = 1/K sum_k relu( a[g,k] (A_hat x)[r] W_k + b[g,k] x_root[r] V_k + bias_k )
+ * with coeff[g] = (a[g,0..K-1], b[g,0..K-1]) the per-graph row of the reference's filter_coeff
+ * (:313-316), W = init_weight [K,F,F], V = root_weight[0] [K,F,F], bias = bias[0] [K,F] (may be NULL)
+ * and A_hat the FETA_NORM_GCN plan (feta_graph_plan_build).  x_root is the dropout-ed copy of x
+ * (:335; NULL = x itself).  `prop` (may be NULL) receives A_hat x for the backward pass.
+ * One fused launch; requires a block-diagonal plan, F in {4, 8, 16} (the reference's reshape at
+ * :284 already forces in_channels == out_channels) and the largest graph to fit one CTA
+ * (FETA_EUNSUPPORTED otherwise).  plan_meta: device-side guard as for feta_cheb_fwd.
+ * --------------------------------------------------------------------------------------- */
+int feta_arma_fwd(const float* x /* [R, F] */, const float* x_root /* [R, F] or NULL */, const int32_t* rowptr,
+                  const int32_t* colidx, const float* vals, const int32_t* graph_ptr, const int32_t* row_graph,
+                  int32_t* plan_meta, const float* coeff /* [G, 2K] */, const float* init_weight,
+                  const float* root_weight, const float* bias, float* out /* [R, F] */,
+                  float* prop /* [R, F] or NULL */, int64_t num_rows, int64_t num_graphs, int K, int F,
+                  int max_nodes, void* stream);
+/* autograd of the above.  dx = A_hat^T d(A_hat x) (+ dx_root when `dx_root` is NULL, i.e. x_root was x);
+ * dcoeff [G, 2K] (every graph with at least one row is written; zero-fill for empty graphs is the
+ * caller's); dz / dza / dzb [R, K*F] = dz_k, a_k dz_k, b_k dz_k, from which
+ *   d init_weight[k] = prop^T dza[:, k],  d root_weight[k] = x_root^T dzb[:, k],  d bias[k] = colsum dz[:, k]
+ * (feta_linear_wgrad). */
+int feta_arma_bwd(const float* dout /* [R, F] */, const float* prop, const float* x_root,
+                  const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t,
+                  const int32_t* graph_ptr, const int32_t* row_graph, int32_t* plan_meta, const float* coeff,
+                  const float* init_weight, const float* root_weight, const float* bias, float* dx,
+                  float* dx_root /* or NULL */, float* dz, float* dza, float* dzb, float* dcoeff,
+                  int64_t num_rows, int64_t num_graphs, int K, int F, int max_nodes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * A6  kernel-biased attention core of DiffTransformerEncoderLayer (the layer transformer/models.py:4

@@ -81,13 +81,24 @@ def test_sass_is_blackwell_native():
     so = os.path.join(ROOT, "feta_tmlr_b200", "libfeta_b200.so")
     elf = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun",
-                           "_ZN4feta20cheb_fwd_warp_kernelILi16ELi2EEEvPKfPKiS4_S2_S4_S2_llS2_PflliiiiPii", so],
-                          capture_output=True, text=True).stdout
+    full = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    funcs = {}
+    for chunk in full.split("Function : ")[1:]:
+        funcs[chunk.split("\n", 1)[0].strip()] = chunk
+
+    def sass_of(*needles):
+        hits = [body for name, body in funcs.items() if all(n in name for n in needles)]
+        assert hits, needles
+        return "\n".join(hits)
+
+    # warp-per-graph Chebyshev forward: TMA bulk copies (UBLKCP) + mbarrier waits (SYNCS) + packed fp32x2 FMAs,
+    # and the F = 16 variant applies the filters on the tensor cores (3xTF32 HMMA.1688)
+    sass = sass_of("cheb_fwd_warp_kernelILi16ELi2ELb1E")
+    assert "UBLKCP" in sass and "FFMA2" in sass and "SYNCS" in sass and "HMMA.1688.F32.TF32" in sass
+    sass = sass_of("cheb_fwd_warp_kernelILi8ELi2ELb0E")
     assert "UBLKCP" in sass and "FFMA2" in sass and "SYNCS" in sass
     # tcgen05 attention forward: tensor-core MMA (UTC*MMA), TMEM loads / stores
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4feta18attn_fwd_tc_kernelILi16EEEvPKfS2_S2_llS2_PKhPfS5_llS5_iif",
-                           so], capture_output=True, text=True).stdout
+    sass = sass_of("attn_fwd_tc_kernelILi16E")
     assert "UTCHMMA" in sass and "LDTM" in sass and "STTM" in sass
 
 

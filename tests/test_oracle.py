@@ -197,3 +197,33 @@ def test_golden_vectors(name):
         out, _, coeff = m(px, ei, bi, fi, mask, pe, lap, deg, return_filter_coeff=True)
         assert torch.allclose(out, g['out'], rtol=1e-5, atol=1e-6)
         assert torch.allclose(coeff, g['coeff'], rtol=1e-5, atol=1e-6)
+
+
+def test_arma_oracle_matches_dense_closed_form():
+    """ARMAConvDynamic restatement (literal per-node weights + bmm) == dense closed form in fp64:
+    mean_k relu(a_k A_hat x W_k + b_k x V_k + bias_k), A_hat = D_in^-1/2 A^T-accumulate D_in^-1/2."""
+    from helpers import random_batch_graph
+    from oracle.arma import arma_conv_dynamic
+    sizes = [5, 1, 7, 3]
+    ei, batch, R = random_batch_graph(11, sizes, directed_extra=2)
+    K, F, G = 3, 4, len(sizes)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(R, F, generator=g, dtype=torch.float64)
+    coeff = torch.randn(G, 2 * K, generator=g, dtype=torch.float64)
+    W = torch.randn(K, F, F, generator=g, dtype=torch.float64)
+    V = torch.randn(1, K, F, F, generator=g, dtype=torch.float64)
+    bias = torch.randn(1, K, 1, F, generator=g, dtype=torch.float64)
+    out = arma_conv_dynamic(x, ei, coeff, batch.double(), W, None, V, bias, K)
+    A = torch.zeros(R, R, dtype=torch.float64)
+    for s, t in ei.t().tolist():
+        A[t, s] += 1.0                                   # out[col] += x[row]
+    deg = A.sum(1)                                       # degree over the target index
+    dis = torch.where(deg > 0, deg.pow(-0.5), torch.zeros_like(deg))
+    Ah = dis[:, None] * A * dis[None, :]
+    ref = torch.zeros(R, F, dtype=torch.float64)
+    for k in range(K):
+        a, b = coeff[batch, k][:, None], coeff[batch, K + k][:, None]
+        ref += torch.relu(a * (Ah @ x @ W[k]) + b * (x @ V[0, k]) + bias[0, k])
+    ref /= K
+    assert out.shape == (R, F)
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
