@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kThreads) plan_count_kernel(const int64_t* __r
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = ei[e], t = ei[E + e];
+    if (s == -1 && t == -1) continue;  // padding column of a fixed-width edge list
     if (s < 0 || s >= R || t < 0 || t >= R) {
       meta[6] = 1;  // out-of-range endpoint: reported by the host wrapper
       continue;

@@ -119,7 +119,7 @@ def collate_host(store, ids, device='cpu', static=None):
     e_src, e_owner = _ranges(store.edge_ptr[ids], elens)
     edge_indices = store.edge_index[:, e_src] + node_off[e_owner][None, :]           # :219
     if static is not None:
-        padded_e = np.zeros((2, int(static[1])), dtype=np.int64)
+        padded_e = np.full((2, int(static[1])), -1, dtype=np.int64)     # (-1, -1): ignored by the plan builder
         padded_e[:, :edge_indices.shape[1]] = edge_indices
         edge_indices = padded_e
     batch_indices = owner.astype(np.int64)                                           # :220

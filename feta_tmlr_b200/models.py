@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .ChebNetDynamic import ChebConvDynamic
+from .ChebNetDynamic import ARMAConvDynamic, ChebConvDynamic
 from .layers import DiffTransformerEncoderLayer
 
 
@@ -53,13 +53,16 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
                  **kwargs):
         kwargs.setdefault('enable_nested_tensor', False)
         super().__init__(*args, **kwargs)
-        if gnn_type != 'ChebConvDynamic':
-            raise NotImplementedError("gnn_type=%r: only 'ChebConvDynamic' is on the B200 hot path "
-                                      "(SURVEY.md section 2)" % gnn_type)
+        if gnn_type not in ('ChebConvDynamic', 'ARMAConvDynamic'):
+            raise NotImplementedError("gnn_type=%r: only 'ChebConvDynamic' and 'ARMAConvDynamic' are on the "
+                                      "B200 hot path (SURVEY.md section 2)" % gnn_type)
         self.num_coefficients = num_coefficients
         dh = d_model // num_heads
         self.order = self.num_coefficients                                          # models.py:127,130
-        if learn_only_filter_order_coeff:
+        if gnn_type == 'ARMAConvDynamic':                                           # :135-139
+            self.num_coefficients = self.num_coefficients * 2
+            self.spectral_gnns = ARMAConvDynamic(dh, dh, num_stacks=self.order, num_layers=1)
+        elif learn_only_filter_order_coeff:
             self.spectral_gnns = ChebConvDynamic(dh, dh, self.num_coefficients,
                                                  normalization=laplacian_norm,
                                                  learn_only_filter_order_coeff=True)
@@ -120,6 +123,9 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
                eigenvalues=None, x=None, plan=None):
         if x is None:
             x = ops.gather_rows(graph_signal, feature_indices)                      # :347
+        if self.gnn_type == 'ARMAConvDynamic':
+            filter_coeff = filter_coeff.reshape((-1, self.order * 2))               # :361-363
+            return spectral_gnn(x, edge_index, filter_coeff, batch=batch, plan=plan)
         if not self.learn_only_filter_order_coeff:
             filter_coeff = filter_coeff.reshape((-1, self.order, self.filter_in_channels,
                                                  self.filter_out_channels)).permute([1, 0, 2, 3])   # :357
@@ -184,8 +190,7 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
     # slot (b, i) is treated as a node of graph b: padded slots carry x = 0, no edges, and are
     # masked out of the coefficient pooling and of the scattered-back result, so real nodes get
     # bit-for-bit the same arithmetic as forward().  `edge_index` holds the reference's packed
-    # node ids, padded to a fixed width with (0, 0) self loops (dropped by remove_self_loops,
-    # ChebNetDynamic.py:113).
+    # node ids, padded to a fixed width with (-1, -1) columns, which the plan builder ignores.
     def static_context(self, edge_index, masks, nmax):
         ctx = BatchContext()
         B, H = masks.shape[0], self.num_heads
@@ -199,16 +204,20 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         ctx.seg_lo = (g * nmax).to(torch.int32)
         ctx.seg_hi = (g * nmax + lens.repeat(H)).to(torch.int32)
         # packed node id -> padded slot id  (b * nmax + i)
+        pad = edge_index < 0                                                        # (-1, -1) padding columns
         b_of = torch.searchsorted(node_ptr, edge_index, right=True).clamp_(max=B - 1)
         first = node_ptr - lens
         ei = edge_index - first[b_of] + b_of * nmax
         if self.tile_edges_per_head:
             heads = torch.arange(H, device=dev, dtype=torch.int64)
             ei = (ei.view(2, 1, -1) + (heads * B * nmax).view(1, H, 1)).reshape(2, -1)
+            pad = pad.view(2, 1, -1).expand(2, H, -1).reshape(2, -1)
+        ei = ei.masked_fill(pad, -1)
         ctx.edge_index = ei
         ctx.batch_all_heads = torch.arange(H * B * nmax, device=dev, dtype=torch.int64) // nmax
         ctx.plan = ops.build_cheb_plan(ei, ctx.batch_all_heads, H * B * nmax, H * B, 2.0,
-                                       hints={'max_nodes': int(nmax), 'block_diagonal': True})
+                                       hints={'max_nodes': int(nmax), 'block_diagonal': True},
+                                       norm=getattr(self.spectral_gnns, '_plan_norm', ops.NORM_CHEB_SYM))
         ctx.real = (~masks).t().unsqueeze(-1).to(torch.float32)                     # [nmax, B, 1]
         return ctx
 

@@ -142,4 +142,6 @@ def build_model(name, module, **overrides):
              'node': ('DiffGraphTransformerGenGCNSBM', 'OracleDiffGraphTransformerGenGCNSBM'),
              'molhiv': ('DiffGraphTransformerGenGCNMolHiv', 'OracleDiffGraphTransformerGenGCNMolHiv')}[cfg['head']]
     cls = getattr(module, names[0], None) or getattr(module, names[1])
+    if 'gnn_type' in cfg:
+        kw['gnn_type'] = cfg['gnn_type']
     return cls(**kw)

@@ -68,7 +68,9 @@ int64_t feta_launch_count(void);
  * matrix grouped by SOURCE (the *_t arrays, used by the backward pass).  The +1/-1 self-loop
  * pair of the reference cancels and is not stored.  graph_ptr[g]..graph_ptr[g+1] is the row
  * range of the g-th run of equal `batch` values; row_graph[r] is that run index.
- * Pass batch == NULL for a single graph covering all rows.
+ * Pass batch == NULL for a single graph covering all rows.  A column (-1, -1) of edge_index is
+ * padding (fixed-width edge lists of CUDA-graph replays) and is ignored; any other endpoint
+ * outside [0, R) drops the edge and sets meta[FETA_META_BAD_INDEX].
  * --------------------------------------------------------------------------------------- */
 size_t feta_cheb_plan_workspace_bytes(int64_t num_rows, int64_t num_edges);
 int feta_cheb_plan_build(const int64_t* edge_index /* [2, E] */, int64_t num_edges,

@@ -5,7 +5,10 @@ golden vector for this operator and PyG 1.7 is not installable here; the restate
 reference lines literally (per-node weight materialisation, ``_batch_multiply_coeff`` bmm, PyG-1.7
 ``gcn_norm(add_self_loops=False)`` and ``propagate``).
 """
+import math
+
 import torch
+from torch import nn
 
 from .pyg17 import gcn_norm, propagate_add
 
@@ -54,3 +57,34 @@ def arma_conv_dynamic(x, edge_index, filter_coeff, batch, init_weight, weight, r
             out = out + bias[0 if shared_weights else t]                                      # :340-341
         out = torch.relu(out)                                                                 # :343-344
     return out.mean(dim=-3)                                                                   # :346
+
+
+class OracleARMAConvDynamic(nn.Module):
+    """Module shell with the reference's parameter names and shapes (ChebNetDynamic.py:244-272)."""
+
+    def __init__(self, in_channels, out_channels, num_stacks=1, num_layers=1, shared_weights=False,
+                 dropout=0., bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_stacks, self.num_layers = num_stacks, num_layers
+        self.shared_weights, self.dropout = shared_weights, dropout
+        K, T, F_in, F_out = num_stacks, num_layers, in_channels, out_channels
+        T = 1 if shared_weights else T
+        self.init_weight = nn.Parameter(torch.empty(K, F_in, F_out))                # :257
+        self.weight = nn.Parameter(torch.empty(max(1, T - 1), K, F_out, F_out))     # :258
+        self.root_weight = nn.Parameter(torch.empty(T, K, F_in, F_out))             # :259
+        if bias:
+            self.bias = nn.Parameter(torch.empty(T, K, 1, F_out))                   # :262
+        else:
+            self.register_parameter('bias', None)
+        for w in (self.init_weight, self.weight, self.root_weight):                 # glorot, :269-271
+            stdv = math.sqrt(6.0 / (w.size(-2) + w.size(-1)))
+            w.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.fill_(0)                                                 # :272
+
+    def forward(self, x, edge_index, filter_coeff, edge_weight=None, batch=None):
+        assert edge_weight is None
+        return arma_conv_dynamic(x, edge_index, filter_coeff, batch, self.init_weight, self.weight,
+                                 self.root_weight, self.bias, self.num_stacks, self.num_layers,
+                                 self.shared_weights)

@@ -32,7 +32,7 @@ class OracleGCNConv(nn.Module):
 
 
 class OracleEncoderGenGCN(nn.Module):
-    """``DiffTransformerEncoderGenGCN`` -- models.py:103-368 (gnn_type='ChebConvDynamic')."""
+    """``DiffTransformerEncoderGenGCN`` -- models.py:103-368 (gnn_type 'ChebConvDynamic' / 'ARMAConvDynamic')."""
 
     def __init__(self, d_model, num_heads, encoder_layer, num_layers, norm=None,
                  num_coefficients=4, laplacian_norm='sym', gnn_type='ChebConvDynamic',
@@ -42,11 +42,15 @@ class OracleEncoderGenGCN(nn.Module):
         self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
         self.num_layers = num_layers
         self.norm = norm
-        assert gnn_type == 'ChebConvDynamic'
+        assert gnn_type in ('ChebConvDynamic', 'ARMAConvDynamic')
         self.num_coefficients = num_coefficients
         self.order = num_coefficients                                                  # :127,130
         dh = d_model // num_heads
-        if learn_only_filter_order_coeff:
+        if gnn_type == 'ARMAConvDynamic':                                              # :135-139
+            from .arma import OracleARMAConvDynamic
+            self.num_coefficients = self.num_coefficients * 2
+            self.spectral_gnns = OracleARMAConvDynamic(dh, dh, num_stacks=self.order, num_layers=1)
+        elif learn_only_filter_order_coeff:
             self.spectral_gnns = OracleChebConvDynamic(dh, dh, self.num_coefficients,
                                                        normalization=laplacian_norm,
                                                        learn_only_filter_order_coeff=True)
@@ -124,6 +128,9 @@ class OracleEncoderGenGCN(nn.Module):
     # models.py:346-368
     def filter(self, filter_coeff, graph_signal, edge_index, feature_indices, batch, spectral_gnn):
         x = graph_signal[feature_indices[:, 0].long(), feature_indices[:, 1].long(), :]  # :347
+        if self.gnn_type == 'ARMAConvDynamic':                                           # :361-363
+            filter_coeff = filter_coeff.reshape((-1, self.order * 2))
+            return spectral_gnn(x, edge_index, filter_coeff, batch=batch)
         if not self.learn_only_filter_order_coeff:                                       # :356-357
             filter_coeff = filter_coeff.reshape(
                 (-1, self.order, self.filter_in_channels, self.filter_out_channels)

@@ -34,6 +34,7 @@ def _loss(name, out, labels):
 @pytest.mark.parametrize("name,B,over", [
     ("MUTAG", 6, {}), ("ZINC", 8, dict(layers=3)), ("PATTERN", 3, {}), ("CLUSTER", 3, {}),
     ("MOLHIV", 8, {}), ("ZINC", 6, dict(layers=2, batch_norm=True)),
+    ("ZINC", 6, dict(layers=2, gnn_type='ARMAConvDynamic')), ("PATTERN", 3, dict(gnn_type='ARMAConvDynamic')),
 ])
 def test_model_forward_backward_parity(cuda, name, B, over):
     cfg, graphs, store, batch = make_batch(name, B, seed=1)
@@ -100,8 +101,9 @@ def test_checkpoint_roundtrip_and_deepcopy(cuda, tmp_path):
     assert "encoder.spectral_gnns.bias" in m.state_dict()
 
 
-@pytest.mark.parametrize("name,B", [("ZINC", 6), ("PATTERN", 3), ("MOLHIV", 5), ("CLUSTER", 3)])
-def test_static_shape_forward_matches_packed_forward(cuda, name, B):
+@pytest.mark.parametrize("name,B,over", [("ZINC", 6, {}), ("PATTERN", 3, {}), ("MOLHIV", 5, {}), ("CLUSTER", 3, {}),
+                                         ("ZINC", 6, dict(gnn_type='ARMAConvDynamic'))])
+def test_static_shape_forward_matches_packed_forward(cuda, name, B, over):
     """forward_static (padded domain, CUDA-graph friendly) == forward (reference layout)."""
     import feta_tmlr_b200.models as fmodels
     from feta_tmlr_b200 import data as fdata, engine
@@ -111,7 +113,7 @@ def test_static_shape_forward_matches_packed_forward(cuda, name, B):
     sb = fdata.collate_host(store, np.arange(B), static=(nmax_cap, e_cap))
     assert sb[0].shape[1] == nmax_cap and sb[6].shape == (2, e_cap)
     torch.manual_seed(0)
-    m = synthetic.build_model(name, fmodels, layers=2).to(cuda)
+    m = synthetic.build_model(name, fmodels, layers=2, **over).to(cuda)
     g = to_dev(batch[:9], cuda)
     ref = m(g[0], g[6], g[7], g[8], g[1], g[2], g[3], g[4])[0]
     s = to_dev(sb[:9], cuda)
