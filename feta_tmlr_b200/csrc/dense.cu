@@ -82,11 +82,18 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float* 
   }
 }
 
-// dW[e] = sum_s partial[s, e] over float4 elements; slices summed in order (deterministic), loads unrolled
+// dW[e] = sum_s partial[s, e] (and db[e] = sum_s pdb[s, e], same launch) over float4 elements; slices summed in
+// order (deterministic), loads unrolled
 __global__ void __launch_bounds__(128) slices_reduce4_kernel(const float4* __restrict__ partial, int S, int64_t n4,
-                                                            float4* __restrict__ out) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n4) return;
+                                                            float4* __restrict__ out,
+                                                            const float4* __restrict__ partial2, int64_t n4b,
+                                                            float4* __restrict__ out2) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n4) {   // tail threads: the bias slices
+    e -= n4;
+    if (e >= n4b) return;
+    partial = partial2, out = out2, n4 = n4b;
+  }
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   int k = 0;
   for (; k + 8 <= S; k += 8) {
@@ -274,14 +281,11 @@ extern "C" int feta_linear_wgrad(const float* dY, const float* X, float* dW, flo
   dim3 grid((unsigned)(out_tiles * in_tiles), (unsigned)S);
   wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(dY, X, partial, pdb, (int)T, out, in, kWgTokensPerCta, in_tiles);
   FETA_LAUNCH_CHECK();
-  slices_reduce4_kernel<<<(unsigned)ceil_div((int64_t)out * in / 4, 128), 128, 0, st>>>(
-      reinterpret_cast<const float4*>(partial), S, (int64_t)out * in / 4, reinterpret_cast<float4*>(dW));
+  const int64_t n4 = (int64_t)out * in / 4, n4b = db ? out / 4 : 0;
+  slices_reduce4_kernel<<<(unsigned)ceil_div(n4 + n4b, 128), 128, 0, st>>>(
+      reinterpret_cast<const float4*>(partial), S, n4, reinterpret_cast<float4*>(dW),
+      reinterpret_cast<const float4*>(pdb), n4b, reinterpret_cast<float4*>(db));
   FETA_LAUNCH_CHECK();
-  if (db) {
-    slices_reduce4_kernel<<<(unsigned)ceil_div(out / 4, 128), 128, 0, st>>>(
-        reinterpret_cast<const float4*>(pdb), S, out / 4, reinterpret_cast<float4*>(db));
-    FETA_LAUNCH_CHECK();
-  }
   return FETA_OK;
 }
 

@@ -389,6 +389,9 @@ class DiffAttentionFn(torch.autograd.Function):
         ctx.save_for_backward(qkv, mask_u8, attn, rowflag)
         ctx.cfg = (H, float(scale), bool(share_qk))
         ctx.mark_non_differentiable(rowflag)
+        # the coefficient path detaches `attn` (models.py:282): without this autograd would hand backward an
+        # attn-sized tensor of zeros per layer (a fill kernel + 4*H*N^2 bytes read by attn_bwd)
+        ctx.set_materialize_grads(False)
         return attn, o_heads, rowflag
 
     @staticmethod
