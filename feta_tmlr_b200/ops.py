@@ -685,6 +685,35 @@ def _counters(device):
     return t
 
 
+# Weight gradients are off the critical path of the backward pass (nothing reads them before the
+# optimizer / gradient all-reduce), so they run on a per-device side stream: inside a captured step that
+# is a parallel branch of the CUDA graph, overlapping the ~70-CTA reduction kernels with the main chain.
+# The side stream is joined once per backward pass by an autograd-engine callback.
+WGRAD_SIDE_STREAM = _os.environ.get("FETA_WGRAD_SIDE_STREAM", "1") == "1"
+_SIDE = {}
+_JOIN_PENDING = set()
+
+
+def _side_stream(device):
+    st = _SIDE.get(device)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE[device] = st
+    return st
+
+
+def _queue_side_join(device):
+    if device in _JOIN_PENDING:
+        return
+    _JOIN_PENDING.add(device)
+
+    def _join():
+        _JOIN_PENDING.discard(device)
+        torch.cuda.current_stream(device).wait_stream(_side_stream(device))
+
+    torch.autograd.Variable._execution_engine.queue_callback(_join)
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b.  Forward and dX are library GEMMs; dW / db (reductions over the ~5k-token axis
     the libraries under-parallelise here) go through feta_linear_wgrad."""
@@ -716,9 +745,20 @@ class LinearFn(torch.autograd.Function):
                 partial = torch.empty(n_part, dtype=torch.float32, device=dy.device)
                 dw = torch.empty((out_f, in_f), dtype=torch.float32, device=dy.device)
                 db = torch.empty(out_f, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-                check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
-                                            _ptr(_counters(dy.device)), T, out_f, in_f, _stream()),
-                      "feta_linear_wgrad")
+                cnt = _counters(dy.device)
+                if WGRAD_SIDE_STREAM:
+                    main = torch.cuda.current_stream(dy.device)
+                    side = _side_stream(dy.device)
+                    side.wait_stream(main)                      # dy, x (and the buffers above) are ready
+                    check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
+                                                _ptr(cnt), T, out_f, in_f, side.cuda_stream), "feta_linear_wgrad")
+                    for t in (dy2, x2, partial, dw, db):        # allocator: not reusable until `side` passed here
+                        if t is not None:
+                            t.record_stream(side)
+                    _queue_side_join(dy.device)
+                else:
+                    check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
+                                                _ptr(cnt), T, out_f, in_f, _stream()), "feta_linear_wgrad")
         return dx, dw, db
 
 
