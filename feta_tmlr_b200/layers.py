@@ -45,19 +45,28 @@ class DiffMultiheadAttention(nn.Module):
         if bias:
             nn.init.constant_(self.out_proj.bias, 0.0)
 
-    def forward(self, src, pe=None, key_padding_mask=None):
-        """src [Nmax, B, d] -> (out [Nmax, B, d], attn [B, H, Nmax, Nmax], heads [B, Nmax, H, dh])."""
+    def forward(self, src, pe=None, key_padding_mask=None, with_residual=False):
+        """src [Nmax, B, d] -> (out [Nmax, B, d], attn [B, H, Nmax, Nmax], heads [B, Nmax, H, dh]).
+        ``with_residual``: a 4th output, ``src`` routed through the in-projection's autograd node (its
+        gradient is then folded into the in-projection's dX GEMM, ops.LinearFn)."""
         if self.dropout > 0.0 and self.training:
             raise NotImplementedError("DiffTransformerEncoderLayer(b200): attention-weight dropout > 0 is "
                                       "not implemented in the fused kernel (all reference drivers "
                                       "default to --dropout 0.0)")
         N, B, E = src.shape
-        qkv = ops.linear(src, self.in_proj_weight, self.in_proj_bias)        # library GEMM (+ own wgrad)
+        res = None
+        if with_residual:
+            qkv, res = ops.linear_res(src, self.in_proj_weight, self.in_proj_bias)
+        else:
+            qkv = ops.linear(src, self.in_proj_weight, self.in_proj_bias)    # library GEMM (+ own wgrad)
         attn, o_sf = ops.diff_attention(qkv, pe, key_padding_mask, self.num_heads,
                                         float(self.head_dim) ** -0.5, self.share_qk)
         # the kernel writes O seq-first, so concat-heads -> out_proj needs no copy; `heads` is the
         # [B, Nmax, H, dh] view the FeTA encoder consumes (models.py:179)
-        return self.out_proj(o_sf.view(N, B, E)), attn, o_sf.permute(1, 0, 2, 3)
+        out = self.out_proj(o_sf.view(N, B, E))
+        if with_residual:
+            return out, attn, o_sf.permute(1, 0, 2, 3), res
+        return out, attn, o_sf.permute(1, 0, 2, 3)
 
 
 class DiffTransformerEncoderLayer(nn.Module):
@@ -86,12 +95,21 @@ class DiffTransformerEncoderLayer(nn.Module):
         self.scaling = None
 
     def forward(self, src, pe=None, degree=None, src_mask=None, src_key_padding_mask=None,
-                need_heads=False):
+                need_heads=False, rowscale=None):
+        """``rowscale`` (extension): the seq-first ``degree.t().contiguous()`` precomputed once per forward by
+        the encoder instead of once per layer."""
         if src_mask is not None:
             raise NotImplementedError("src_mask (attn_mask) is never passed by the reference "
                                       "(models.py:166) and is not implemented")
-        src2, attn, heads = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask)
-        if degree is not None:
+        fused = not self.batch_norm
+        if fused:
+            src2, attn, heads, src = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask,
+                                                    with_residual=True)
+        else:
+            src2, attn, heads = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask)
+        if rowscale is not None:
+            pass
+        elif degree is not None:
             rowscale = degree.transpose(0, 1).contiguous()                      # [Nmax, B]
         else:
             if pe is None:
@@ -111,7 +129,8 @@ class DiffTransformerEncoderLayer(nn.Module):
         else:                                    # residual add fused into the LayerNorm kernels
             src = ops.add_layer_norm(src, self.dropout1(src2), self.norm1.weight, self.norm1.bias, self.norm1.eps,
                                      bscale=rowscale.reshape(-1))       # degree * src2 fused in
-            src2 = self.linear2(self.dropout(F.relu(self.linear1(src))))
+            h, src = ops.linear_res(src, self.linear1.weight, self.linear1.bias, relu=True)   # ReLU in the epilogue
+            src2 = self.linear2(self.dropout(h))
             src = ops.add_layer_norm(src, self.dropout2(src2), self.norm2.weight, self.norm2.bias, self.norm2.eps)
         if need_heads:
             return src, attn, heads

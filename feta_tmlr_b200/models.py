@@ -146,10 +146,11 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         num_layers = len(self.layers)
         ctx = None
         attn = None
+        rowscale = None if degree is None else degree.transpose(0, 1).contiguous()   # once, not per layer
         for layer_num, mod in enumerate(self.layers):
             output, attn, out_each_head = mod(output, pe=pe, degree=degree, src_mask=mask,
                                               src_key_padding_mask=src_key_padding_mask,
-                                              need_heads=True)
+                                              need_heads=True, rowscale=rowscale)
             if self.last_layer_filter and layer_num + 1 != num_layers:              # :169-171
                 continue
             if ctx is None:
@@ -230,9 +231,10 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         num_layers = len(self.layers)
         ctx = None
         attn = None
+        rowscale = None if degree is None else degree.transpose(0, 1).contiguous()
         for layer_num, mod in enumerate(self.layers):
             output, attn, out_each_head = mod(output, pe=pe, degree=degree, src_key_padding_mask=masks,
-                                              need_heads=True)
+                                              need_heads=True, rowscale=rowscale)
             if self.last_layer_filter and layer_num + 1 != num_layers:
                 continue
             if ctx is None:

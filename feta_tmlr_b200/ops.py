@@ -719,19 +719,40 @@ class LinearFn(torch.autograd.Function):
     the libraries under-parallelise here) go through feta_linear_wgrad."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
+    def forward(ctx, x, weight, bias, relu, with_res):
+        """``relu``: the activation runs in the GEMM epilogue (cuBLASLt RELU_BIAS).  ``with_res``: also return
+        ``x`` itself as a second output to be used as the residual input of the following add+LayerNorm, so
+        that backward receives the residual gradient and folds it into the dX GEMM (beta = 1) instead of
+        leaving a separate accumulation kernel to autograd."""
         ctx.has_bias = bias is not None
-        return torch.nn.functional.linear(x, weight, bias)
+        ctx.relu = bool(relu)
+        ctx.set_materialize_grads(False)
+        if relu and bias is not None and x.is_cuda:
+            y = torch._addmm_activation(bias, x.reshape(-1, x.shape[-1]), weight.t()).view(*x.shape[:-1], weight.shape[0])
+        else:
+            y = torch.nn.functional.linear(x, weight, bias)
+            if relu:
+                y = torch.relu_(y)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        if with_res:
+            return y, x
+        return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dres=None):
         lib = _lib.load()
-        x, weight = ctx.saved_tensors
+        x, weight, y = ctx.saved_tensors
         out_f, in_f = weight.shape
         dx = dw = db = None
+        if dy is None:                                            # only the residual branch was used
+            return dres, None, None, None, None
+        if ctx.relu:
+            dy = torch.ops.aten.threshold_backward(dy, y, 0)
         if ctx.needs_input_grad[0]:
-            dx = dy.matmul(weight)
+            if dres is not None:                                  # dX = dres + dY W, one GEMM
+                dx = torch.addmm(dres.reshape(-1, in_f), dy.reshape(-1, out_f), weight).view(x.shape)
+            else:
+                dx = dy.matmul(weight)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dy2 = _f32c(dy.reshape(-1, out_f))
             x2 = _f32c(x.reshape(-1, in_f))
@@ -759,12 +780,18 @@ class LinearFn(torch.autograd.Function):
                 else:
                     check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
                                                 _ptr(cnt), T, out_f, in_f, _stream()), "feta_linear_wgrad")
-        return dx, dw, db
+        return dx, dw, db, None, None
 
 
-def linear(x, weight, bias=None):
+def linear(x, weight, bias=None, relu=False):
     _need_cuda(x, weight, bias)
-    return LinearFn.apply(x, weight, bias)
+    return LinearFn.apply(x, weight, bias, relu, False)
+
+
+def linear_res(x, weight, bias=None, relu=False):
+    """(linear(x), x): the second output is ``x`` for the residual connection (see LinearFn.forward)."""
+    _need_cuda(x, weight, bias)
+    return LinearFn.apply(x, weight, bias, relu, True)
 
 
 class AddLayerNormFn(torch.autograd.Function):
