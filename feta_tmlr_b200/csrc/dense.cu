@@ -154,28 +154,33 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_fwd_kernel(
   }
 }
 
+// dz (critical path) + per-CTA partial sums of dgamma / dbeta.  PER = ceil(D / 32) columns per lane.  With
+// FOLD the last CTA to finish also folds the partials (fixed order, self-re-arming counter); without it the
+// fold is a separate launch (ln_fold_kernel) that the host puts on the weight-gradient side stream, so the
+// parameter gradients never sit on the critical path of the backward pass.
+template <int PER, bool FOLD>
 __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ bscale,
     float* __restrict__ dz, float* __restrict__ db_scaled, float* __restrict__ partial /* [grid, 2, D] */,
     float* __restrict__ dgamma, float* __restrict__ dbeta, int32_t* __restrict__ counter, int64_t T, int D) {
-  __shared__ float sg[kLnWarps][kLnMaxPerLane * 32];
-  __shared__ float sb[kLnWarps][kLnMaxPerLane * 32];
+  __shared__ float sg[kLnWarps][PER * 32];
+  __shared__ float sb[kLnWarps][PER * 32];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float dg[kLnMaxPerLane], db[kLnMaxPerLane], gm[kLnMaxPerLane];
+  float dg[PER], db[PER], gm[PER];
 #pragma unroll
-  for (int j = 0; j < kLnMaxPerLane; ++j) {
+  for (int j = 0; j < PER; ++j) {
     dg[j] = db[j] = 0.0f;
     const int c = lane + 32 * j;
     gm[j] = c < D ? gamma[c] : 0.0f;
   }
   for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < T; row += (int64_t)gridDim.x * kLnWarps) {
     const float mu = mean[row], rs = rstd[row];
-    float g[kLnMaxPerLane], xh[kLnMaxPerLane];
+    float g[PER], xh[PER];
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-    for (int j = 0; j < kLnMaxPerLane; ++j) {
+    for (int j = 0; j < PER; ++j) {
       const int c = lane + 32 * j;
       g[j] = xh[j] = 0.0f;
       if (c < D) {
@@ -188,20 +193,27 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
         db[j] += d;
       }
     }
-    s1 = warp_sum(s1) / (float)D;
-    s2 = warp_sum(s2) / (float)D;
+    // the two row sums travel through the shuffles together
 #pragma unroll
-    for (int j = 0; j < kLnMaxPerLane; ++j) {
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 /= (float)D;
+    s2 /= (float)D;
+    const float bs = db_scaled ? bscale[row] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
       const int c = lane + 32 * j;
       if (c < D) {
         const float v = rs * (g[j] - s1 - xh[j] * s2);
         dz[row * D + c] = v;
-        if (db_scaled) db_scaled[row * D + c] = v * bscale[row];   // gradient of the scaled branch
+        if (db_scaled) db_scaled[row * D + c] = v * bs;   // gradient of the scaled branch
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < kLnMaxPerLane; ++j) {
+  for (int j = 0; j < PER; ++j) {
     sg[warp][lane + 32 * j] = dg[j];
     sb[warp][lane + 32 * j] = db[j];
   }
@@ -216,6 +228,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
     partial[((size_t)blockIdx.x * 2 + 0) * D + c] = a;
     partial[((size_t)blockIdx.x * 2 + 1) * D + c] = b;
   }
+  if constexpr (!FOLD) return;
   // last block folds the per-block partials (fixed order) and re-arms the counter
   __threadfence();
   __syncthreads();
@@ -227,29 +240,28 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // 256 threads = (256 / Dp) slices x Dp columns; slices combined through shared memory
-  const int nblk = gridDim.x;
-  float* red = &sg[0][0];                       // reuse: 2 * 256 floats needed
-  const int Dp = D <= 32 ? 32 : (D <= 64 ? 64 : (D <= 128 ? 128 : 256));
-  const int nsl = blockDim.x / Dp, sl = threadIdx.x / Dp, c = threadIdx.x % Dp;
-  float a = 0.0f, b = 0.0f;
-  if (c < D)
-    for (int k = sl; k < nblk; k += nsl) {
-      a += __ldcg(partial + ((size_t)k * 2 + 0) * D + c);
-      b += __ldcg(partial + ((size_t)k * 2 + 1) * D + c);
-    }
-  __syncthreads();
-  red[threadIdx.x] = a;
-  red[256 + threadIdx.x] = b;
-  __syncthreads();
-  if (sl == 0 && c < D) {
-    for (int k = 1; k < nsl; ++k) {
-      a += red[k * Dp + c];
-      b += red[256 + k * Dp + c];
-    }
-    dgamma[c] = a;
-    dbeta[c] = b;
+  // one warp per (column, which) item, lanes stride the CTA partials (same tree as ln_fold_kernel)
+  for (int item = warp; item < 2 * D; item += kLnWarps) {
+    const int which = item / D, c = item - which * D;
+    float a = 0.0f;
+    for (int k = lane; k < (int)gridDim.x; k += 32) a += __ldcg(partial + ((size_t)k * 2 + which) * D + c);
+    a = warp_sum(a);
+    if (lane == 0) (which ? dbeta : dgamma)[c] = a;
   }
+}
+
+// dgamma[c] = sum_k partial[k, 0, c], dbeta[c] = sum_k partial[k, 1, c]: one warp per (column, which), lanes
+// stride the CTA partials, fixed-shape tree => deterministic
+__global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ partial, int nblk, int D,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // 0 .. 2D-1
+  if (item >= 2 * D) return;
+  const int which = item / D, c = item - which * D;
+  float a = 0.0f;
+  for (int k = lane; k < nblk; k += 32) a += __ldg(partial + ((size_t)k * 2 + which) * D + c);
+  a = warp_sum(a);
+  if (lane == 0) (which ? dbeta : dgamma)[c] = a;
 }
 
 }  // namespace feta
@@ -304,8 +316,21 @@ extern "C" int feta_add_layernorm_fwd(const float* a, const float* b, const floa
 }
 
 extern "C" int feta_add_layernorm_bwd_blocks(int64_t T) {
-  int64_t b = ceil_div(T > 0 ? T : 1, kLnWarps * 8);
-  return (int)(b < kNumSMs ? b : kNumSMs);
+  int64_t b = ceil_div(T > 0 ? T : 1, kLnWarps * 2);   // two rows per warp: enough CTAs to fill the GPU
+  return (int)(b < 4 * kNumSMs ? b : 4 * kNumSMs);
+}
+
+template <int PER>
+static void launch_ln_bwd(bool fold, int nblk, cudaStream_t st, const float* dy, const float* z, const float* mean,
+                          const float* rstd, const float* gamma, const float* bscale, float* dz, float* db_scaled,
+                          float* partial, float* dgamma, float* dbeta, int32_t* counter, int64_t T, int D) {
+  if (fold)
+    add_layernorm_bwd_kernel<PER, true><<<nblk, kLnWarps * 32, 0, st>>>(dy, z, mean, rstd, gamma, bscale, dz, db_scaled,
+                                                                        partial, dgamma, dbeta, counter, T, D);
+  else
+    add_layernorm_bwd_kernel<PER, false><<<nblk, kLnWarps * 32, 0, st>>>(dy, z, mean, rstd, gamma, bscale, dz,
+                                                                         db_scaled, partial, dgamma, dbeta, counter, T,
+                                                                         D);
 }
 
 extern "C" int feta_add_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
@@ -315,12 +340,24 @@ extern "C" int feta_add_layernorm_bwd(const float* dy, const float* z, const flo
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(T >= 0 && D >= 1 && D <= kLnMaxPerLane * 32, "add_layernorm: D=%d not in [1, %d]", D,
                kLnMaxPerLane * 32);
-  FETA_REQUIRE(dgamma && dbeta && partial && counter && (T == 0 || (dy && z && mean && rstd && gamma && dz)),
+  const bool fold = dgamma != nullptr;
+  FETA_REQUIRE(partial && (!fold || (dbeta && counter)) && (T == 0 || (dy && z && mean && rstd && gamma && dz)),
                "add_layernorm_bwd: NULL pointer argument");
   FETA_REQUIRE(!db_scaled || bscale, "add_layernorm_bwd: db_scaled needs bscale");
   const int nblk = feta_add_layernorm_bwd_blocks(T);
-  add_layernorm_bwd_kernel<<<nblk, kLnWarps * 32, 0, st>>>(dy, z, mean, rstd, gamma, bscale, dz, db_scaled, partial,
-                                                           dgamma, dbeta, counter, T, D);
+  if (D <= 32) launch_ln_bwd<1>(fold, nblk, st, dy, z, mean, rstd, gamma, bscale, dz, db_scaled, partial, dgamma, dbeta, counter, T, D);
+  else if (D <= 64) launch_ln_bwd<2>(fold, nblk, st, dy, z, mean, rstd, gamma, bscale, dz, db_scaled, partial, dgamma, dbeta, counter, T, D);
+  else if (D <= 128) launch_ln_bwd<4>(fold, nblk, st, dy, z, mean, rstd, gamma, bscale, dz, db_scaled, partial, dgamma, dbeta, counter, T, D);
+  else launch_ln_bwd<8>(fold, nblk, st, dy, z, mean, rstd, gamma, bscale, dz, db_scaled, partial, dgamma, dbeta, counter, T, D);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+
+extern "C" int feta_add_layernorm_bwd_fold(const float* partial, int64_t T, int D, float* dgamma, float* dbeta,
+                                           void* stream_) {
+  FETA_REQUIRE(partial && dgamma && dbeta && D >= 1 && D <= kLnMaxPerLane * 32, "add_layernorm_bwd_fold: bad argument");
+  const int nblk = feta_add_layernorm_bwd_blocks(T);
+  ln_fold_kernel<<<(unsigned)ceil_div(2 * D, 8), 256, 0, (cudaStream_t)stream_>>>(partial, nblk, D, dgamma, dbeta);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }

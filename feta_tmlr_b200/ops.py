@@ -835,9 +835,22 @@ class AddLayerNormFn(torch.autograd.Function):
         dg = torch.empty(D, dtype=torch.float32, device=z.device)
         db = torch.empty(D, dtype=torch.float32, device=z.device)
         cnt = _counters(z.device)
-        check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale),
-                                         _ptr(dz), _ptr(dbs), _ptr(dg), _ptr(db), _ptr(partial),
-                                         cnt.data_ptr() + 256 * 4, T, D, _stream()), "feta_add_layernorm_bwd")
+        if WGRAD_SIDE_STREAM:       # dz on the critical path; the dgamma / dbeta fold on the side stream
+            check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale),
+                                             _ptr(dz), _ptr(dbs), None, None, _ptr(partial), None, T, D, _stream()),
+                  "feta_add_layernorm_bwd")
+            main = torch.cuda.current_stream(z.device)
+            side = _side_stream(z.device)
+            side.wait_stream(main)
+            check(lib.feta_add_layernorm_bwd_fold(_ptr(partial), T, D, _ptr(dg), _ptr(db), side.cuda_stream),
+                  "feta_add_layernorm_bwd_fold")
+            for t in (partial, dg, db):
+                t.record_stream(side)
+            _queue_side_join(z.device)
+        else:
+            check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale),
+                                             _ptr(dz), _ptr(dbs), _ptr(dg), _ptr(db), _ptr(partial),
+                                             cnt.data_ptr() + 256 * 4, T, D, _stream()), "feta_add_layernorm_bwd")
         grad_b = None
         if ctx.has_b:
             grad_b = dbs if dbs is not None else dz

@@ -208,6 +208,9 @@ int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t stride
  *     NULL), dgamma, dbeta; `partial` needs feta_add_layernorm_bwd_blocks(T) * 2 * D floats;
  *     `counter`: one int32, ZERO on entry, left zero on exit (the last CTA folds the per-block partials
  *     and re-arms it; reusable by the next call on the same stream, not by concurrent streams).
+ *     With dgamma == NULL (dbeta, counter ignored) only dz / db_scaled / `partial` are produced and the
+ *     parameter gradients come from a later feta_add_layernorm_bwd_fold(partial, T, D, dgamma, dbeta) --
+ *     which a caller can put on another stream, off the critical path of the backward pass.
  * --------------------------------------------------------------------------------------- */
 int feta_linear_wgrad_slices(int64_t T);
 int feta_linear_wgrad(const float* dY, const float* X, float* dW, float* db, float* partial, size_t partial_floats,
@@ -218,6 +221,7 @@ int feta_add_layernorm_bwd_blocks(int64_t T);
 int feta_add_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
                            const float* bscale, float* dz, float* db_scaled, float* dgamma, float* dbeta,
                            float* partial, int32_t* counter, int64_t T, int D, void* stream);
+int feta_add_layernorm_bwd_fold(const float* partial, int64_t T, int D, float* dgamma, float* dbeta, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * A4  DiffTransformerEncoderGenGCN.get_filter_coefficients (transformer/models.py:240-287).

@@ -1,0 +1,72 @@
+"""GPU parity of the layer-glue kernels (csrc/dense.cu): weight-gradient reduction, residual-add LayerNorm and
+the residual-folding Linear, against plain PyTorch (fp64 on the CPU) -- with the parameter gradients on the side
+stream (default) and on the launching stream."""
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(params=[True, False], ids=["side_stream", "main_stream"])
+def side(request):
+    from feta_tmlr_b200 import ops
+    old = ops.WGRAD_SIDE_STREAM
+    ops.WGRAD_SIDE_STREAM = request.param
+    yield request.param
+    ops.WGRAD_SIDE_STREAM = old
+
+
+@pytest.mark.parametrize("T,D", [(1, 16), (37, 64), (4352, 64), (10752, 128), (300, 200), (5000, 256)])
+@pytest.mark.parametrize("scaled", [False, True])
+def test_add_layer_norm_parity(cuda, side, T, D, scaled):
+    from feta_tmlr_b200 import ops
+    g = torch.Generator().manual_seed(T + D)
+    a, b = torch.randn(T, D, generator=g), torch.randn(T, D, generator=g)
+    gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    bs = torch.rand(T, generator=g) + 0.5 if scaled else None
+    go = torch.randn(T, D, generator=g)
+    ref_in = [t.double().requires_grad_() for t in (a, b, gamma, beta)]
+    z = ref_in[0] + (ref_in[1] if bs is None else bs.double().unsqueeze(1) * ref_in[1])
+    ref = torch.nn.functional.layer_norm(z, (D,), ref_in[2], ref_in[3], 1e-5)
+    ref.backward(go.double())
+    dev_in = [t.to(cuda).requires_grad_() for t in (a, b, gamma, beta)]
+    out = ops.add_layer_norm(dev_in[0], dev_in[1], dev_in[2], dev_in[3], 1e-5,
+                             bscale=None if bs is None else bs.to(cuda))
+    out.backward(go.to(cuda))
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) <= TOL
+    for d, r in zip(dev_in, ref_in):
+        assert rel_err(d.grad, r.grad) <= TOL
+
+
+@pytest.mark.parametrize("T,fin,fout", [(1, 8, 8), (4352, 64, 192), (4352, 128, 64), (10752, 64, 128), (777, 20, 36)])
+@pytest.mark.parametrize("relu,with_res", [(False, False), (True, True), (False, True)])
+def test_linear_parity(cuda, side, T, fin, fout, relu, with_res):
+    """y = x W^T + b (optionally ReLU in the epilogue), dW / db through feta_linear_wgrad, and the residual
+    output whose gradient is folded into the dX GEMM."""
+    from feta_tmlr_b200 import ops
+    g = torch.Generator().manual_seed(T + fin)
+    x = torch.randn(T, fin, generator=g)
+    W, b = torch.randn(fout, fin, generator=g) * 0.2, torch.randn(fout, generator=g)
+    go, gr = torch.randn(T, fout, generator=g), torch.randn(T, fin, generator=g)
+    xr, Wr, br = (t.double().requires_grad_() for t in (x, W, b))
+    ref = torch.nn.functional.linear(xr, Wr, br)
+    if relu:
+        ref = torch.relu(ref)
+    ((ref * go.double()).sum() + ((xr * gr.double()).sum() if with_res else 0)).backward()
+    xd, Wd, bd = (t.to(cuda).requires_grad_() for t in (x, W, b))
+    if with_res:
+        y, res = ops.linear_res(xd, Wd, bd, relu=relu)
+        assert res.data_ptr() == xd.data_ptr()
+        ((y * go.to(cuda)).sum() + (res * gr.to(cuda)).sum()).backward()
+    else:
+        y = ops.linear(xd, Wd, bd, relu=relu)
+        (y * go.to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(y, ref) <= TOL
+    assert rel_err(xd.grad, xr.grad) <= TOL
+    assert rel_err(Wd.grad, Wr.grad) <= TOL
+    assert rel_err(bd.grad, br.grad) <= TOL
