@@ -38,6 +38,9 @@ SIGNATURES = {
                               c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, _P]),
     "feta_linear_wgrad_slices": (c_int, [c_int64]),
     "feta_linear_wgrad": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_int64, c_int, c_int, _P]),
+    "feta_linear_tc_supported": (c_int, [c_int, c_int]),
+    "feta_linear_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "feta_linear_dx": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "feta_add_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, _P]),
     "feta_add_layernorm_bwd_blocks": (c_int, [c_int64]),
     "feta_add_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),

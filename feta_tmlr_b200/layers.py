@@ -129,8 +129,12 @@ class DiffTransformerEncoderLayer(nn.Module):
         else:                                    # residual add fused into the LayerNorm kernels
             src = ops.add_layer_norm(src, self.dropout1(src2), self.norm1.weight, self.norm1.bias, self.norm1.eps,
                                      bscale=rowscale.reshape(-1))       # degree * src2 fused in
-            h, src = ops.linear_res(src, self.linear1.weight, self.linear1.bias, relu=True)   # ReLU in the epilogue
-            src2 = self.linear2(self.dropout(h))
+            # ReLU in linear1's epilogue; with the tensor-core GEMMs its backward mask moves into linear2's dX
+            # epilogue (otherwise linear1's backward applies it, one threshold kernel)
+            dff, dm = self.linear1.weight.shape
+            fm = ops.linear_tc_enabled(dm, dff) and ops.linear_tc_enabled(dff, dm)
+            h, src = ops.linear_res(src, self.linear1.weight, self.linear1.bias, relu=True, grad_premasked=fm)
+            src2 = ops.linear(self.dropout(h), self.linear2.weight, self.linear2.bias, mask_input_grad=fm)
             src = ops.add_layer_norm(src, self.dropout2(src2), self.norm2.weight, self.norm2.bias, self.norm2.eps)
         if need_heads:
             return src, attn, heads

@@ -690,6 +690,15 @@ def _counters(device):
 # is a parallel branch of the CUDA graph, overlapping the ~70-CTA reduction kernels with the main chain.
 # The side stream is joined once per backward pass by an autograd-engine callback.
 WGRAD_SIDE_STREAM = _os.environ.get("FETA_WGRAD_SIDE_STREAM", "1") == "1"
+# Opt-in: the layer's projections through csrc/dense_tc.cu (3xTF32 mma.sync GEMMs with fused ReLU-mask /
+# residual-gradient epilogues) instead of the library sgemm.  Measured SLOWER on B200 (ZINC shape, in-graph:
+# 7.0-13.4 us vs 4.3-7.9 us per GEMM -- three legacy TF32 MMAs per product run at about the SIMT fp32 rate),
+# so the default stays the library GEMM; kept, with parity tests, as the base of a tcgen05 version.
+LINEAR_TENSOR_CORES = _os.environ.get("FETA_LINEAR_TC", "0") == "1"
+
+
+def linear_tc_enabled(in_f, out_f):
+    return bool(LINEAR_TENSOR_CORES and _lib.load().feta_linear_tc_supported(int(in_f), int(out_f)))
 _SIDE = {}
 _JOIN_PENDING = set()
 
@@ -719,21 +728,36 @@ class LinearFn(torch.autograd.Function):
     the libraries under-parallelise here) go through feta_linear_wgrad."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, with_res):
-        """``relu``: the activation runs in the GEMM epilogue (cuBLASLt RELU_BIAS).  ``with_res``: also return
-        ``x`` itself as a second output to be used as the residual input of the following add+LayerNorm, so
-        that backward receives the residual gradient and folds it into the dX GEMM (beta = 1) instead of
-        leaving a separate accumulation kernel to autograd."""
+    def forward(ctx, x, weight, bias, relu, with_res, mask_input_grad, grad_premasked):
+        """``relu``: the activation runs in the GEMM epilogue.  ``with_res``: also return ``x`` itself as a
+        second output to be used as the residual input of the following add+LayerNorm, so that backward
+        receives the residual gradient and folds it into the dX GEMM instead of leaving a separate
+        accumulation kernel to autograd.  ``mask_input_grad``: ``x`` is a ReLU output, so dX is multiplied by
+        ``[x > 0]`` in the dX epilogue -- and the layer that produced ``x`` is called with
+        ``grad_premasked`` so that it does not apply the ReLU mask again."""
+        lib = _lib.load()
         ctx.has_bias = bias is not None
         ctx.relu = bool(relu)
+        ctx.mask_in = bool(mask_input_grad)
+        ctx.premasked = bool(grad_premasked)
         ctx.set_materialize_grads(False)
-        if relu and bias is not None and x.is_cuda:
-            y = torch._addmm_activation(bias, x.reshape(-1, x.shape[-1]), weight.t()).view(*x.shape[:-1], weight.shape[0])
+        out_f, in_f = weight.shape
+        ctx.tc = bool(LINEAR_TENSOR_CORES and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+                      and lib.feta_linear_tc_supported(in_f, out_f))
+        if ctx.tc:
+            x2 = _f32c(x.reshape(-1, in_f))
+            w = _f32c(weight)
+            bc = None if bias is None else _f32c(bias)
+            y = torch.empty(x.shape[:-1] + (out_f,), dtype=torch.float32, device=x.device)
+            check(lib.feta_linear_fwd(_ptr(x2), _ptr(w), _ptr(bc), _ptr(y), x2.shape[0], in_f, out_f, int(ctx.relu),
+                                      _stream()), "feta_linear_fwd")
+        elif relu and bias is not None and x.is_cuda:
+            y = torch._addmm_activation(bias, x.reshape(-1, in_f), weight.t()).view(*x.shape[:-1], out_f)
         else:
             y = torch.nn.functional.linear(x, weight, bias)
             if relu:
                 y = torch.relu_(y)
-        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.save_for_backward(x, weight, y if (relu and not grad_premasked) else None)
         if with_res:
             return y, x
         return y
@@ -745,14 +769,23 @@ class LinearFn(torch.autograd.Function):
         out_f, in_f = weight.shape
         dx = dw = db = None
         if dy is None:                                            # only the residual branch was used
-            return dres, None, None, None, None
-        if ctx.relu:
+            return dres, None, None, None, None, None, None
+        if ctx.relu and not ctx.premasked:
             dy = torch.ops.aten.threshold_backward(dy, y, 0)
         if ctx.needs_input_grad[0]:
-            if dres is not None:                                  # dX = dres + dY W, one GEMM
-                dx = torch.addmm(dres.reshape(-1, in_f), dy.reshape(-1, out_f), weight).view(x.shape)
+            if ctx.tc:
+                dy2 = _f32c(dy.reshape(-1, out_f))
+                x2 = _f32c(x.reshape(-1, in_f)) if ctx.mask_in else None
+                dr = None if dres is None else _f32c(dres.reshape(-1, in_f))
+                dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+                check(lib.feta_linear_dx(_ptr(dy2), _ptr(_f32c(weight)), _ptr(dr), _ptr(x2), _ptr(dx), dy2.shape[0],
+                                         in_f, out_f, _stream()), "feta_linear_dx")
             else:
                 dx = dy.matmul(weight)
+                if ctx.mask_in:
+                    dx = dx * (x > 0)
+                if dres is not None:
+                    dx = dx + dres
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dy2 = _f32c(dy.reshape(-1, out_f))
             x2 = _f32c(x.reshape(-1, in_f))
@@ -780,18 +813,18 @@ class LinearFn(torch.autograd.Function):
                 else:
                     check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
                                                 _ptr(cnt), T, out_f, in_f, _stream()), "feta_linear_wgrad")
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def linear(x, weight, bias=None, relu=False):
+def linear(x, weight, bias=None, relu=False, mask_input_grad=False, grad_premasked=False):
     _need_cuda(x, weight, bias)
-    return LinearFn.apply(x, weight, bias, relu, False)
+    return LinearFn.apply(x, weight, bias, relu, False, mask_input_grad, grad_premasked)
 
 
-def linear_res(x, weight, bias=None, relu=False):
+def linear_res(x, weight, bias=None, relu=False, grad_premasked=False):
     """(linear(x), x): the second output is ``x`` for the residual connection (see LinearFn.forward)."""
     _need_cuda(x, weight, bias)
-    return LinearFn.apply(x, weight, bias, relu, True)
+    return LinearFn.apply(x, weight, bias, relu, True, False, grad_premasked)
 
 
 class AddLayerNormFn(torch.autograd.Function):

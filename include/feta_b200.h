@@ -224,6 +224,22 @@ int feta_add_layernorm_bwd(const float* dy, const float* z, const float* mean, c
 int feta_add_layernorm_bwd_fold(const float* partial, int64_t T, int D, float* dgamma, float* dbeta, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * A6 (layer glue)  the layer's projections on the tensor cores (csrc/dense_tc.cu): F.linear of the
+ * in/out projections and the FFN of the layer transformer/models.py:4 imports, and its input gradient.
+ * m16n8k8 TF32 MMAs with both operands split hi + lo (three MMAs per product): fp32-grade accuracy.
+ *   feta_linear_fwd:  Y[T,out] = act(X[T,in] . W[out,in]^T + bias)   (bias may be NULL; relu != 0: ReLU)
+ *   feta_linear_dx:   dX[T,in] = (dY[T,out] . W[out,in]) * [mask_src > 0] + dres
+ *                     mask_src [T,in] (may be NULL): the ReLU output this layer consumed;
+ *                     dres [T,in] (may be NULL): gradient of the residual connection that branches off X.
+ * Shapes: in, out multiples of 8, <= 256 (feta_linear_tc_supported); other shapes: use a library GEMM.
+ * --------------------------------------------------------------------------------------- */
+int feta_linear_tc_supported(int in, int out);
+int feta_linear_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out, int relu,
+                    void* stream);
+int feta_linear_dx(const float* dY, const float* W, const float* dres, const float* mask_src, float* dX, int64_t T,
+                   int in, int out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * A4  DiffTransformerEncoderGenGCN.get_filter_coefficients (transformer/models.py:240-287).
  * With x == 1 the all-pairs GCNConv of :280-282 is  s_j * colsum(W) + b  with a per-node scalar
  *     loop_j = a_jj != 0 ? a_jj : 1;  deg_j = sum_{i != j} a_ij + loop_j;

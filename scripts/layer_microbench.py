@@ -67,6 +67,18 @@ def main():
         y = ops.linear(x, w)
         torch.autograd.grad(y, w, dy3)
     t("in_proj_fwd_wgrad", lin_fb)
+    P = ops._ptr
+    st = torch.cuda.current_stream().cuda_stream
+    y3 = torch.empty(nmax, B, 3 * d, device=dev)
+    y1 = torch.empty(nmax, B, d, device=dev)
+    y2 = torch.empty(nmax, B, 2 * d, device=dev)
+    t("tc_in_proj_fwd", lambda: lib.feta_linear_fwd(P(x), P(W3), None, P(y3), T, d, 3 * d, 0, torch.cuda.current_stream().cuda_stream))
+    t("tc_out_proj_fwd", lambda: lib.feta_linear_fwd(P(x), P(W), P(bd), P(y1), T, d, d, 0, torch.cuda.current_stream().cuda_stream))
+    t("tc_ffn1_relu_fwd", lambda: lib.feta_linear_fwd(P(x), P(W1), P(b1), P(y2), T, d, 2 * d, 1, torch.cuda.current_stream().cuda_stream))
+    t("tc_ffn2_fwd", lambda: lib.feta_linear_fwd(P(h), P(W2), P(bd), P(y1), T, 2 * d, d, 0, torch.cuda.current_stream().cuda_stream))
+    t("tc_in_proj_dx", lambda: lib.feta_linear_dx(P(dy3), P(W3), P(x), None, P(y1), T, d, 3 * d, torch.cuda.current_stream().cuda_stream))
+    t("tc_ffn2_dx", lambda: lib.feta_linear_dx(P(x), P(W2), None, P(h), P(y2), T, 2 * d, d, torch.cuda.current_stream().cuda_stream))
+    t("tc_ffn1_dx", lambda: lib.feta_linear_dx(P(h), P(W1), P(x), None, P(y1), T, d, 2 * d, torch.cuda.current_stream().cuda_stream))
     t("attn_fwd", lambda: ops.diff_attention(qkv, pe, mask, H, scale))
 
     def attn_fb():

@@ -44,7 +44,7 @@ def test_add_layer_norm_parity(cuda, side, T, D, scaled):
 
 @pytest.mark.parametrize("T,fin,fout", [(1, 8, 8), (4352, 64, 192), (4352, 128, 64), (10752, 64, 128), (777, 20, 36)])
 @pytest.mark.parametrize("relu,with_res", [(False, False), (True, True), (False, True)])
-def test_linear_parity(cuda, side, T, fin, fout, relu, with_res):
+def test_linear_parity(cuda, side, tc, T, fin, fout, relu, with_res):
     """y = x W^T + b (optionally ReLU in the epilogue), dW / db through feta_linear_wgrad, and the residual
     output whose gradient is folded into the dX GEMM."""
     from feta_tmlr_b200 import ops
@@ -70,3 +70,46 @@ def test_linear_parity(cuda, side, T, fin, fout, relu, with_res):
     assert rel_err(xd.grad, xr.grad) <= TOL
     assert rel_err(Wd.grad, Wr.grad) <= TOL
     assert rel_err(bd.grad, br.grad) <= TOL
+
+
+@pytest.fixture(params=[True, False], ids=["tensor_cores", "library_gemm"])
+def tc(request):
+    from feta_tmlr_b200 import ops
+    old = ops.LINEAR_TENSOR_CORES
+    ops.LINEAR_TENSOR_CORES = request.param
+    yield request.param
+    ops.LINEAR_TENSOR_CORES = old
+
+
+@pytest.mark.parametrize("T,d,dff", [(1, 8, 16), (4352, 64, 128), (10752, 64, 128), (37, 128, 256), (90, 24, 40)])
+def test_ffn_chain_parity(cuda, tc, T, d, dff):
+    """linear1 (+ReLU epilogue, gradient pre-masked) -> linear2 (ReLU mask in its dX epilogue) with the residual
+    routed through linear1: forward and every gradient against fp64 PyTorch."""
+    from feta_tmlr_b200 import ops
+    g = torch.Generator().manual_seed(T + d)
+    x = torch.randn(T, d, generator=g)
+    W1, b1 = torch.randn(dff, d, generator=g) * 0.2, torch.randn(dff, generator=g) * 0.1
+    W2, b2 = torch.randn(d, dff, generator=g) * 0.2, torch.randn(d, generator=g) * 0.1
+    go = torch.randn(T, d, generator=g)
+    ref_in = [t.double().requires_grad_() for t in (x, W1, b1, W2, b2)]
+    ref = ref_in[0] + torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(ref_in[0], ref_in[1], ref_in[2])),
+                                                  ref_in[3], ref_in[4])
+    ref.backward(go.double())
+    dv = [t.to(cuda).requires_grad_() for t in (x, W1, b1, W2, b2)]
+    h, res = ops.linear_res(dv[0], dv[1], dv[2], relu=True, grad_premasked=True)
+    out = res + ops.linear(h, dv[3], dv[4], mask_input_grad=True)
+    out.backward(go.to(cuda))
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) <= TOL
+    for a, r in zip(dv, ref_in):
+        assert rel_err(a.grad, r.grad) <= TOL
+
+
+def test_linear_tc_accuracy_is_fp32_grade(cuda):
+    """3xTF32 (hi.hi + hi.lo + lo.hi) must sit at fp32 round-off, far below plain TF32's ~1e-3."""
+    from feta_tmlr_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x, W = torch.randn(4352, 64, generator=g), torch.randn(192, 64, generator=g)
+    ref = x.double() @ W.double().t()
+    y = ops.linear(x.to(cuda), W.to(cuda))
+    assert rel_err(y, ref) < 2e-6
