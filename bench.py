@@ -198,8 +198,8 @@ def cheb_algorithmic_bytes(R, F, nnz, G, K):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu --set full captures
-# (profiles/r1_cheb_fwd_ncu.md capture r1d: F=16, 3.0M rows; profiles/r1_attention_ncu.md: ZINC attention fwd)
-NCU_TRAFFIC = {("cheb_sweep", 16, 3_000_000): 747_484_416 + 174_554_880,
+# (profiles/r1_cheb_fwd_ncu.md capture v6: F=16, 3.0M rows; profiles/r1_attention_ncu.md: ZINC attention fwd)
+NCU_TRAFFIC = {("cheb_sweep", 16, 3_000_000): 747_573_504 + 175_733_248,
                ("attn_fwd", "ZINC"): 2_729_984}
 
 
