@@ -282,6 +282,167 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(
   }
 }
 
+// ------------------------------------------------------------------ backward, register-tiled (dh 8 / 16) --
+// Same contract and round structure as attn_bwd_kernel, restructured around its instruction mix (1 shared
+// load per FMA there): Q/K/V/dO rows sit row-major with stride DH+4 (conflict-free 128-bit row loads), a
+// lane owns key j and reads V_j / K_j as float4s, dQ_i is a thread-tiled reduction over key slices, and every
+// thread keeps ITS (key, 4-channel) entries of dK / dV in registers for the whole kernel -- per round of
+// RND rows a thread does 24 FMAs per 8 shared loads instead of 2 per 4.  Deterministic (fixed order).
+template <int DH, int NCH, int THREADS>
+__global__ void __launch_bounds__(THREADS) attn_bwd_tiled_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
+    const uint8_t* __restrict__ mask, const float* __restrict__ attn, const float* __restrict__ rowflag,
+    const float* __restrict__ d_o, int64_t osn, int64_t osb, const float* __restrict__ d_attn,
+    float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int64_t dsn, int64_t dsb, int H, int nmax,
+    float scale) {
+  constexpr int LD = DH + 4, C4 = DH / 4, JT = THREADS / C4, EMAX = (32 * NCH + JT - 1) / JT;
+  constexpr int RND = THREADS / 32;   // rows per round (one per warp)
+  extern __shared__ float smem[];
+  __shared__ int s_neff;
+  __shared__ int s_valid[RND];
+  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+  const uint8_t* mk = mask + (size_t)b * nmax;
+  const int n = block_n_eff(mk, nmax, &s_neff);
+  const int npad = nmax | 1;
+  float* Ks = smem;                               // [nmax][LD]
+  float* Vs = Ks + (size_t)nmax * LD;
+  float* Qs = Vs + (size_t)nmax * LD;
+  float* dOs = Qs + (size_t)nmax * LD;
+  float* Pb = dOs + (size_t)nmax * LD;            // [RND][npad]
+  float* dSb = Pb + (size_t)RND * npad;           // [RND][npad]
+
+  const int64_t base_in = (int64_t)b * sb + h * DH;
+  for (int idx = threadIdx.x; idx < nmax * C4; idx += blockDim.x) {
+    const int j = idx / C4, c = (idx - j * C4) * 4;
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk, qq = kk, dd = kk;
+    if (j < n) {
+      kk = __ldg(reinterpret_cast<const float4*>(k + base_in + (int64_t)j * sn + c));
+      vv = __ldg(reinterpret_cast<const float4*>(v + base_in + (int64_t)j * sn + c));
+      qq = __ldg(reinterpret_cast<const float4*>(q + base_in + (int64_t)j * sn + c));
+      dd = __ldg(reinterpret_cast<const float4*>(d_o + (int64_t)j * osn + (int64_t)b * osb + h * DH + c));
+    }
+    *reinterpret_cast<float4*>(Ks + j * LD + c) = kk;
+    *reinterpret_cast<float4*>(Vs + j * LD + c) = vv;
+    *reinterpret_cast<float4*>(Qs + j * LD + c) = qq;
+    *reinterpret_cast<float4*>(dOs + j * LD + c) = dd;
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pr = Pb + (size_t)warp * npad;
+  float* ds = dSb + (size_t)warp * npad;
+  // this thread's dK / dV entries: keys jt, jt + JT, ..., channels 4*c4 .. 4*c4+3
+  const int c4 = threadIdx.x % C4, jt = threadIdx.x / C4;
+  float4 accK[EMAX], accV[EMAX];
+#pragma unroll
+  for (int e = 0; e < EMAX; ++e) accK[e] = accV[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int base = 0; base < n; base += RND) {
+    const int i = base + warp;
+    const bool valid = (i < n) && (mk[i] == 0);
+    if (lane == 0) s_valid[warp] = valid;
+    if (valid) {
+      // ---- phase A: dP, delta, dS for row i
+      float dor[DH];
+#pragma unroll
+      for (int c = 0; c < C4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(dOs + i * LD + 4 * c);
+        dor[4 * c] = t.x, dor[4 * c + 1] = t.y, dor[4 * c + 2] = t.z, dor[4 * c + 3] = t.w;
+      }
+      const float* arow = attn + (((size_t)b * H + h) * nmax + i) * nmax;
+      const float* garow = d_attn ? d_attn + (((size_t)b * H + h) * nmax + i) * nmax : nullptr;
+      float p[NCH], dp[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int j = lane + 32 * ch;
+        p[ch] = j < n ? __ldg(arow + j) : 0.0f;
+        dp[ch] = (garow && j < n) ? __ldg(garow + j) : 0.0f;
+      }
+      float delta = 0.0f;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int j = lane + 32 * ch;
+        if (j < n) {
+          float a = dp[ch];
+#pragma unroll
+          for (int c = 0; c < C4; ++c) {
+            const float4 t = *reinterpret_cast<const float4*>(Vs + j * LD + 4 * c);
+            a = fmaf(dor[4 * c], t.x, a), a = fmaf(dor[4 * c + 1], t.y, a);
+            a = fmaf(dor[4 * c + 2], t.z, a), a = fmaf(dor[4 * c + 3], t.w, a);
+          }
+          dp[ch] = a;
+          delta = fmaf(p[ch], a, delta);
+        }
+      }
+      delta = warp_sum(delta) * __ldg(rowflag + ((size_t)b * H + h) * nmax + i);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int j = lane + 32 * ch;
+        if (j < n) {
+          pr[j] = p[ch];
+          ds[j] = p[ch] * (dp[ch] - delta);
+        }
+      }
+      __syncwarp();
+      // dQ_i = scale * sum_j dS[j] K[j]: lanes = (4-channel group, key slice)
+      {
+        constexpr int NS = 32 / C4;
+        const int lc = lane % C4, js = lane / C4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = js; j < n; j += NS) {
+          const float w = ds[j];
+          const float4 t = *reinterpret_cast<const float4*>(Ks + j * LD + 4 * lc);
+          a.x = fmaf(w, t.x, a.x), a.y = fmaf(w, t.y, a.y), a.z = fmaf(w, t.z, a.z), a.w = fmaf(w, t.w, a.w);
+        }
+#pragma unroll
+        for (int o = 16; o >= C4; o >>= 1) {
+          a.x += __shfl_xor_sync(0xffffffffu, a.x, o), a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+          a.z += __shfl_xor_sync(0xffffffffu, a.z, o), a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+        }
+        if (js == 0)
+          *reinterpret_cast<float4*>(dq + (int64_t)i * dsn + (int64_t)b * dsb + h * DH + 4 * lc) =
+              make_float4(a.x * scale, a.y * scale, a.z * scale, a.w * scale);
+      }
+    }
+    __syncthreads();
+    // ---- phase B: fold the round's rows into this thread's dK / dV entries
+#pragma unroll
+    for (int w = 0; w < RND; ++w) {
+      if (s_valid[w]) {
+        const int iw = base + w;
+        const float4 qv = *reinterpret_cast<const float4*>(Qs + iw * LD + 4 * c4);
+        const float4 gv = *reinterpret_cast<const float4*>(dOs + iw * LD + 4 * c4);
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) {
+          const int j = jt + JT * e;
+          if (j < n) {
+            const float sj = dSb[w * npad + j], pj = Pb[w * npad + j];
+            accK[e].x = fmaf(sj, qv.x, accK[e].x), accK[e].y = fmaf(sj, qv.y, accK[e].y);
+            accK[e].z = fmaf(sj, qv.z, accK[e].z), accK[e].w = fmaf(sj, qv.w, accK[e].w);
+            accV[e].x = fmaf(pj, gv.x, accV[e].x), accV[e].y = fmaf(pj, gv.y, accV[e].y);
+            accV[e].z = fmaf(pj, gv.z, accV[e].z), accV[e].w = fmaf(pj, gv.w, accV[e].w);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // write dK, dV for every position (zeros for padding) and dQ = 0 for padded queries
+#pragma unroll
+  for (int e = 0; e < EMAX; ++e) {
+    const int j = jt + JT * e;
+    if (j < nmax) {
+      const int64_t o = (int64_t)j * dsn + (int64_t)b * dsb + h * DH + 4 * c4;
+      const bool real = (j < n) && (mk[j] == 0);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(dk + o) =
+          real ? make_float4(accK[e].x * scale, accK[e].y * scale, accK[e].z * scale, accK[e].w * scale) : z;
+      *reinterpret_cast<float4*>(dv + o) = real ? accV[e] : z;
+      if (!real) *reinterpret_cast<float4*>(dq + o) = z;
+    }
+  }
+}
+
 static size_t attn_fwd_smem(int dh, int nmax) {
   const int npad = nmax | 1;
   return ((size_t)dh * npad + (size_t)nmax * dh + (size_t)kAttnWarps * npad + nmax) * sizeof(float);
@@ -305,11 +466,39 @@ static int launch_attn_fwd(const float* q, const float* k, const float* v, int64
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
+constexpr int kAttnBwdTiledThreads = 512;   // 16 rows per round: half the barriers, twice the warps per SM
+static size_t attn_bwd_tiled_smem(int dh, int nmax) {
+  const int npad = nmax | 1;
+  return (4 * (size_t)nmax * (dh + 4) + 2 * (size_t)(kAttnBwdTiledThreads / 32) * npad) * sizeof(float);
+}
+// the register-tiled kernel needs float4-aligned per-head slices and fits dh in {8, 16}, nmax <= 256
+static bool attn_bwd_tiled_ok(int dh, int nmax, const void* q, const void* k, const void* v, const void* d_o,
+                              const void* dq, const void* dk, const void* dv, int64_t sn, int64_t sb, int64_t osn,
+                              int64_t osb, int64_t dsn, int64_t dsb) {
+  // graphs of <= 64 nodes: the one-LDS-per-FMA kernel is as fast (ZINC shape 17.1 vs 18.4 us) -- latency bound
+  if (!(dh == 8 || dh == 16) || nmax <= 64 || nmax > 256 || getenv("FETA_ATTN_BWD_LEGACY") != nullptr) return false;
+  const uintptr_t ptrs = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)d_o | (uintptr_t)dq | (uintptr_t)dk |
+                         (uintptr_t)dv;
+  const int64_t strides = sn | sb | osn | osb | dsn | dsb;
+  return (ptrs % 16) == 0 && (strides % 4) == 0 && attn_bwd_tiled_smem(dh, nmax) <= 220 * 1024;
+}
+
 template <int DH, int NCH>
 static int launch_attn_bwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
                            const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o,
                            int64_t osn, int64_t osb, const float* d_attn, float* dq, float* dk, float* dv, int64_t dsn,
                            int64_t dsb, int B, int H, int nmax, float scale, cudaStream_t st) {
+  if constexpr ((DH == 8 || DH == 16) && NCH >= 4 && NCH <= 8) {
+    if (attn_bwd_tiled_ok(DH, nmax, q, k, v, d_o, dq, dk, dv, sn, sb, osn, osb, dsn, dsb)) {
+      const size_t smem_t = attn_bwd_tiled_smem(DH, nmax);
+      FETA_CUDA(cudaFuncSetAttribute(attn_bwd_tiled_kernel<DH, NCH, kAttnBwdTiledThreads>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      attn_bwd_tiled_kernel<DH, NCH, kAttnBwdTiledThreads><<<(unsigned)(B * H), kAttnBwdTiledThreads, smem_t, st>>>(
+          q, k, v, sn, sb, mask, attn, rowflag, d_o, osn, osb, d_attn, dq, dk, dv, dsn, dsb, H, nmax, scale);
+      FETA_LAUNCH_CHECK();
+      return FETA_OK;
+    }
+  }
   const size_t smem = attn_bwd_smem(DH, nmax);
   FETA_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attn_bwd_kernel<DH, NCH><<<(unsigned)(B * H), kAttnThreads, smem, st>>>(q, k, v, sn, sb, mask, attn, rowflag, d_o,
