@@ -149,6 +149,119 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
   }
 }
 
+// Forward for graphs of > 64 nodes at dh 8 / 16 (PATTERN / CLUSTER / molhiv shapes): K and V row-major with a
+// padded stride (one 128-bit load per 4 FMAs in QK^T and PV instead of one 32-bit load per FMA) -- the kernel
+// is instruction bound, so this is where its time goes.  Same contract and row mapping as attn_fwd_kernel.
+template <int DH, int NCH>
+__global__ void __launch_bounds__(kAttnThreads) attn_fwd_tiled_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
+    const float* __restrict__ pe, const uint8_t* __restrict__ mask, float* __restrict__ attn,
+    float* __restrict__ o_heads, int64_t osn, int64_t osb, float* __restrict__ rowflag, int H, int nmax,
+    float scale, int rows_per_cta) {
+  extern __shared__ float smem[];
+  __shared__ int s_neff;
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int i0 = blockIdx.x * rows_per_cta;
+  const uint8_t* mk = mask + (size_t)b * nmax;
+  const int n = block_n_eff(mk, nmax, &s_neff);
+  const int npad = nmax | 1;
+  constexpr int LD = DH + 4, C4 = DH / 4;   // rows padded to DH + 4 floats: conflict-free 128-bit row loads
+  float* Ks = smem;                         // [nmax][LD]
+  float* Vs = Ks + (size_t)nmax * LD;       // [nmax][LD]
+  float* prow = Vs + (size_t)nmax * LD;     // [warps][npad]
+  float* pen = prow + (size_t)kAttnWarps * npad;  // [nmax] 0 or -inf key penalty
+
+  const float* kb = k + (int64_t)b * sb + h * DH;
+  const float* vb = v + (int64_t)b * sb + h * DH;
+  for (int idx = threadIdx.x; idx < n * C4; idx += blockDim.x) {
+    const int j = idx / C4, c = (idx - j * C4) * 4;
+    *reinterpret_cast<float4*>(Ks + j * LD + c) = __ldg(reinterpret_cast<const float4*>(kb + (int64_t)j * sn + c));
+    *reinterpret_cast<float4*>(Vs + j * LD + c) = __ldg(reinterpret_cast<const float4*>(vb + (int64_t)j * sn + c));
+  }
+  for (int j = threadIdx.x; j < nmax; j += blockDim.x) pen[j] = mk[j] ? -INFINITY : 0.0f;
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pr = prow + (size_t)warp * npad;
+  for (int ii = warp; ii < rows_per_cta; ii += kAttnWarps) {
+    const int i = i0 + ii;
+    if (i >= nmax) break;
+    float* arow = attn + (((size_t)b * H + h) * nmax + i) * nmax;
+    float* orow = o_heads + (int64_t)i * osn + (int64_t)b * osb + h * DH;
+    if (mk[i]) {  // padded query: defined as zero (never consumed by the model)
+      for (int j = lane; j < nmax; j += 32) arow[j] = 0.0f;
+      if (lane < DH) orow[lane] = 0.0f;
+      if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = 0.0f;
+      continue;
+    }
+    float qr[DH];
+    const float* qp = q + (int64_t)i * sn + (int64_t)b * sb + h * DH;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) qr[c] = __ldg(qp + c) * scale;  // q * scaling before the product
+    float s[NCH];
+    float m = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int j = lane + 32 * ch;
+      float a = -INFINITY;
+      if (j < n) {
+        a = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C4; ++c) {
+          const float4 t4 = *reinterpret_cast<const float4*>(Ks + j * LD + 4 * c);
+          a = fmaf(qr[4 * c], t4.x, a), a = fmaf(qr[4 * c + 1], t4.y, a);
+          a = fmaf(qr[4 * c + 2], t4.z, a), a = fmaf(qr[4 * c + 3], t4.w, a);
+        }
+        a += pen[j];
+      }
+      s[ch] = a;
+      m = fmaxf(m, a);
+    }
+    m = warp_max(m);
+    float sum = 0.0f;
+    const float* perow = pe ? pe + ((size_t)b * nmax + i) * nmax : nullptr;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int j = lane + 32 * ch;
+      float e = 0.0f;
+      if (j < n && s[ch] != -INFINITY) {
+        e = expf(s[ch] - m);
+        if (perow) e *= __ldg(perow + j);
+      }
+      s[ch] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float denom = fmaxf(sum, 1e-6f);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int j = lane + 32 * ch;
+      const float p = s[ch] / denom;
+      if (j < nmax) arow[j] = p;
+      if (j < n) pr[j] = p;
+    }
+    if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = sum > 1e-6f ? 1.0f : 0.0f;
+    __syncwarp();
+    {  // O_i = sum_j P[j] V[j]: lanes = (4-channel group, key slice), one 128-bit V load per 4 FMAs
+      constexpr int NS = 32 / C4;
+      const int lc = lane % C4, js = lane / C4;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = js; j < n; j += NS) {
+        const float w = pr[j];
+        const float4 t4 = *reinterpret_cast<const float4*>(Vs + j * LD + 4 * lc);
+        o.x = fmaf(w, t4.x, o.x), o.y = fmaf(w, t4.y, o.y), o.z = fmaf(w, t4.z, o.z), o.w = fmaf(w, t4.w, o.w);
+      }
+#pragma unroll
+      for (int sh = 16; sh >= C4; sh >>= 1) {
+        o.x += __shfl_xor_sync(0xffffffffu, o.x, sh), o.y += __shfl_xor_sync(0xffffffffu, o.y, sh);
+        o.z += __shfl_xor_sync(0xffffffffu, o.z, sh), o.w += __shfl_xor_sync(0xffffffffu, o.w, sh);
+      }
+      if (js == 0) *reinterpret_cast<float4*>(orow + 4 * lc) = o;
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------ backward ------------
 // One CTA per (graph, head).  Rows are processed in rounds of 8 (one per warp): phase A builds
 // dS_i and dQ_i for the warp's row, phase B lets every thread fold the round's 8 rows into the
@@ -452,10 +565,28 @@ static size_t attn_bwd_smem(int dh, int nmax) {
   return ((size_t)dh * npad + 5 * (size_t)nmax * dh + 2 * (size_t)kAttnWarps * npad) * sizeof(float);
 }
 
+static size_t attn_fwd_tiled_smem(int dh, int nmax) {
+  const int npad = nmax | 1;
+  return (2 * (size_t)nmax * (dh + 4) + (size_t)kAttnWarps * npad + nmax) * sizeof(float);
+}
+
 template <int DH, int NCH>
 static int launch_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
                            const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag,
                            int B, int H, int nmax, float scale, cudaStream_t st) {
+  if constexpr ((DH == 8 || DH == 16) && NCH >= 4 && NCH <= 8) {
+    const uintptr_t ptrs = (uintptr_t)k | (uintptr_t)v | (uintptr_t)o_heads;
+    if ((ptrs % 16) == 0 && ((sn | sb | osn | osb) % 4) == 0 && getenv("FETA_ATTN_FWD_LEGACY") == nullptr) {
+      const size_t smem_t = attn_fwd_tiled_smem(DH, nmax);
+      FETA_CUDA(cudaFuncSetAttribute(attn_fwd_tiled_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_t));
+      dim3 grid_t((unsigned)ceil_div(nmax, kRowsPerCta), (unsigned)(B * H));
+      attn_fwd_tiled_kernel<DH, NCH><<<grid_t, kAttnThreads, smem_t, st>>>(q, k, v, sn, sb, pe, mask, attn, o_heads, osn,
+                                                                           osb, rowflag, H, nmax, scale, kRowsPerCta);
+      FETA_LAUNCH_CHECK();
+      return FETA_OK;
+    }
+  }
   const size_t smem = attn_fwd_smem(DH, nmax);
   FETA_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // small graphs: one CTA per (graph, head) so K/V are staged once; larger ones: 32-row tiles
