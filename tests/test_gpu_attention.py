@@ -104,12 +104,22 @@ def test_attention_no_pe_and_pe_diag_scaling(cuda, tensor_cores):
     assert rel_err(go, oo) < TOL
 
 
-def test_attention_large_graph_pattern_shape(cuda, tensor_cores):
-    o, m = _pair(cuda, 64, 4, seed=13)
-    src, pe, degree, mask = _inputs(5, 3, 188, 64, lens=[188, 44, 120], with_pe=False)
+@pytest.mark.parametrize("legacy", [False, True], ids=["tiled", "one_lds_per_fma"])
+@pytest.mark.parametrize("d,with_pe", [(64, False), (32, True)])
+def test_attention_large_graph_pattern_shape(cuda, tensor_cores, monkeypatch, legacy, d, with_pe):
+    """Graphs of > 64 nodes go through the register-tiled forward / backward kernels (dh 16 and 8); the
+    environment switches route the same shapes through the general kernels."""
+    if legacy:
+        monkeypatch.setenv("FETA_ATTN_FWD_LEGACY", "1")
+        monkeypatch.setenv("FETA_ATTN_BWD_LEGACY", "1")
+    o, m = _pair(cuda, d, 4, seed=13)
+    src, pe, degree, mask = _inputs(5, 3, 188, d, lens=[188, 44, 120], with_pe=with_pe)
+    if with_pe:
+        pe = pe.clone()
     so, sg = src.clone().requires_grad_(), src.to(cuda).requires_grad_()
-    oo, oa, oh = o(so, pe=None, degree=degree, src_key_padding_mask=mask, need_heads=True)
-    go, ga, gh = m(sg, pe=None, degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda), need_heads=True)
+    oo, oa, oh = o(so, pe=pe, degree=degree, src_key_padding_mask=mask, need_heads=True)
+    go, ga, gh = m(sg, pe=None if pe is None else pe.to(cuda), degree=degree.to(cuda),
+                   src_key_padding_mask=mask.to(cuda), need_heads=True)
     assert rel_err(go, oo) < TOL and rel_err(ga, oa) < TOL and rel_err(gh, oh) < TOL
     (oo.sum() + oh.square().sum()).backward()
     (go.sum() + gh.square().sum()).backward()
