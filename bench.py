@@ -129,7 +129,9 @@ def make_pool(name, cfg, B, n_batches, seed, static=False):
     graphs = synthetic.make_dataset(name, B * n_batches, seed=seed)
     store = fdata.GraphStore(graphs, kind=cfg['kind'], n_tags=cfg['n_tags'])
     caps = engine.static_caps(store, B) if static else None
-    return [fdata.collate_host(store, np.arange(i * B, (i + 1) * B), static=caps)[:9] for i in range(n_batches)]
+    # static (CUDA-graph) batches ship the edge list as int32: half the host->device bytes of the step
+    return [fdata.collate_host(store, np.arange(i * B, (i + 1) * B), static=caps,
+                               edge_dtype=np.int32 if static else None)[:9] for i in range(n_batches)]
 
 
 def call_model(model, b):

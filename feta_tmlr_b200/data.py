@@ -79,14 +79,16 @@ def _ranges(starts, lens):
     return np.arange(total, dtype=np.int64) - out_ptr[owner] + starts[owner], owner
 
 
-def collate_host(store, ids, device='cpu', static=None):
+def collate_host(store, ids, device='cpu', static=None, edge_dtype=None):
     """Vectorised restatement of GraphDataset_*.collate_fn (data.py:161-225 / :277-344 / :394-460).
 
     ``static=(nmax_cap, e_cap)`` (extension, for engine.GraphedTrainStep): pad the node axis to
     ``nmax_cap`` instead of the batch maximum, pad ``edge_indices`` to ``e_cap`` columns with
-    (0, 0) self loops, and (node-level labels) return labels as ``[B, nmax_cap]`` with -100 in
-    padded slots -- every returned shape but batch_indices / feature_indices is then batch
-    independent."""
+    (-1, -1) columns (ignored by the plan builder), and (node-level labels) return labels as
+    ``[B, nmax_cap]`` with -100 in padded slots -- every returned shape but batch_indices /
+    feature_indices is then batch independent.  ``edge_dtype=np.int32`` (static only): ship the edge list
+    as int32 -- it is ~95 % of a PATTERN-shape mini-batch's host->device bytes -- and let
+    ``forward_static`` widen it on the device."""
     ids = np.asarray(ids, dtype=np.int64)
     B = len(ids)
     lens, elens = store.sizes(ids)
@@ -121,7 +123,7 @@ def collate_host(store, ids, device='cpu', static=None):
     if static is not None:
         padded_e = np.full((2, int(static[1])), -1, dtype=np.int64)     # (-1, -1): ignored by the plan builder
         padded_e[:, :edge_indices.shape[1]] = edge_indices
-        edge_indices = padded_e
+        edge_indices = padded_e if edge_dtype is None else padded_e.astype(edge_dtype)
     batch_indices = owner.astype(np.int64)                                           # :220
     feature_indices = np.stack([owner, local], axis=1).astype(np.int64)              # :218
     if store.kind == 'sbm':

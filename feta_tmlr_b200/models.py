@@ -197,6 +197,8 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         B, H = masks.shape[0], self.num_heads
         dev = masks.device
         ctx.N, ctx.B, ctx.nmax, ctx.H = B * nmax, B, nmax, H
+        if edge_index.dtype != torch.int64:                                         # int32 over the wire
+            edge_index = edge_index.long()
         lens = (~masks).sum(dim=1)
         node_ptr = torch.cumsum(lens, dim=0)                                        # packed end offsets
         starts = (torch.arange(B, device=dev) * nmax)

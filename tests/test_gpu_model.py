@@ -142,7 +142,8 @@ def test_graphed_train_step_matches_eager(cuda):
     graphs = synthetic.make_dataset(name, 4 * B, seed=9)
     store = fdata.GraphStore(graphs, kind=cfg['kind'], n_tags=cfg['n_tags'])
     caps = engine.static_caps(store, B)
-    batches = [fdata.collate_host(store, np.arange(i * B, (i + 1) * B), static=caps) for i in range(4)]
+    batches = [fdata.collate_host(store, np.arange(i * B, (i + 1) * B), static=caps, edge_dtype=np.int32)
+               for i in range(4)]                                            # int32 edges over the wire
     torch.manual_seed(0)
     m1 = synthetic.build_model(name, fmodels, layers=2).to(cuda)
     m2 = copy.deepcopy(m1)
