@@ -319,7 +319,7 @@ def main():
 
     if use_graph:
         from feta_tmlr_b200 import engine
-        eng = engine.GraphedTrainStep(model, lf, pool_dev[0], lr=1e-3, device=dev)
+        eng = engine.GraphedTrainStep(model, lf, pool_dev[0], lr=1e-3, device=dev, double_buffer=True)
         bucket = eng.bucket
         step = eng.step                                   # copies the batch into static buffers + 1 graph launch
         launches_per_step = eng.launches_per_step
@@ -376,8 +376,8 @@ def main():
 
     def e2e_step(i):
         hb = pool_pinned[i % n_pool]
-        if use_graph:
-            loss = step(hb)                               # H2D straight into the graph's static buffers
+        if use_graph:                                     # H2D straight into the graph's static buffers; the copy of
+            loss = eng.step(hb, prefetch=pool_pinned[(i + 1) % n_pool])   # the NEXT batch overlaps this step
         else:
             loss = step(tuple(None if t is None else t.to(dev, non_blocking=True) for t in hb))
         d2h[0] = float(loss.detach().cpu())              # device -> host read of the step's result

@@ -24,39 +24,56 @@ def static_caps(store, batch_size, nmax_cap=None, slack=1.15):
 
 
 class GraphedTrainStep(object):
-    """``step(host_batch)`` copies the batch into static device buffers and replays the graph."""
+    """``step(host_batch)`` copies the batch into static device buffers and replays the graph.
 
-    def __init__(self, model, loss_fn, example_batch, lr=1e-3, device=None, warmup=3):
+    ``double_buffer=True``: two sets of static input buffers, one captured graph per set (shared memory
+    pool), used alternately; ``step(batch, prefetch=next_batch)`` then issues the host->device copy of the
+    NEXT mini-batch on a copy stream while the current step's graph runs, so the copy leaves the critical
+    path of an end-to-end step (it is still paid for every step)."""
+
+    def __init__(self, model, loss_fn, example_batch, lr=1e-3, device=None, warmup=3, double_buffer=False):
         self.model = model
         self.loss_fn = loss_fn
         dev = device or next(model.parameters()).device
         self.device = dev
-        px, mask, pe, lap, deg, labels, ei = example_batch[:7]
-        self.static = [None if t is None else torch.empty_like(t, device=dev) for t in
-                       (px, mask, pe, lap, deg, labels, ei)]
+        self.nsets = 2 if double_buffer else 1
+        self.sets = [[None if t is None else torch.empty_like(t, device=dev) for t in example_batch[:7]]
+                     for _ in range(self.nsets)]
+        self.static = self.sets[0]
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
                                                            torch.distributed.is_initialized()) else 1
         self.bucket = ddp.FlatGradBucket(self.params, attach=False)
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, fused=True, capturable=True)
+        self.losses = [None] * self.nsets
         self.loss = None
         self.launches_per_step = 0
-        self._load(example_batch)
+        self.cur = 0
+        self.copy_stream = torch.cuda.Stream(device=dev) if double_buffer else None
+        self._staged = None                       # (batch object, its H2D-complete event)
+        self._done = [None] * self.nsets          # event after the last replay that read set s
+        for s in range(self.nsets):
+            self._load(example_batch, s)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                                # warm-up outside capture
             for _ in range(warmup):
-                self._body()
+                self._body(0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            self._body()
-        self.launches_per_step = _lib.launch_count() - n0           # feta kernels inside one replay
+        self.graphs = []
+        for s in range(self.nsets):
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g, pool=self.graphs[0].pool() if s else None):
+                self._body(s)
+            if s == 0:
+                self.launches_per_step = _lib.launch_count() - n0   # feta kernels inside one replay
+            self.graphs.append(g)
+        self.graph = self.graphs[0]
 
-    def _body(self):
-        px, mask, pe, lap, deg, labels, ei = self.static
+    def _body(self, s=0):
+        px, mask, pe, lap, deg, labels, ei = self.sets[s]
         for p in self.params:
             p.grad = None                       # autograd then WRITES each gradient (no += kernels)
         out = self.model.forward_static(px, ei, mask, pe, lap, deg)
@@ -69,21 +86,46 @@ class GraphedTrainStep(object):
             for p, v in live:
                 p.grad = v
         self.opt.step()
-        self.loss = loss.detach()
+        self.losses[s] = loss.detach()
+        self.loss = self.losses[s]
 
-    def _load(self, batch):
-        for dst, src in zip(self.static, batch[:7]):
+    def _load(self, batch, s=0):
+        for dst, src in zip(self.sets[s], batch[:7]):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)
 
-    def step(self, batch=None):
-        """``batch``: a static-shape collate tuple (host pinned or device tensors); None = reuse."""
+    def step(self, batch=None, prefetch=None):
+        """``batch``: a static-shape collate tuple (host pinned or device tensors); None = reuse.
+        ``prefetch`` (double_buffer only): the batch the NEXT call will be given."""
+        s = self.cur
+        main = torch.cuda.current_stream(self.device)
         if batch is not None:
-            self._load(batch)
-        self.graph.replay()
+            if self._staged is not None and self._staged[0] is batch:
+                main.wait_event(self._staged[1])        # its copy was issued during the previous step
+            else:
+                self._load(batch, s)
+        self._staged = None
+        self.graphs[s].replay()
+        self.loss = self.losses[s]
+        if self.nsets == 2:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._done[s] = ev
+            o = 1 - s
+            if prefetch is not None:
+                cs = self.copy_stream
+                if self._done[o] is not None:
+                    cs.wait_event(self._done[o])        # the last replay that read buffer set `o`
+                with torch.cuda.stream(cs):
+                    self._load(prefetch, o)
+                    ev2 = torch.cuda.Event()
+                    ev2.record(cs)
+                self._staged = (prefetch, ev2)
+            self.cur = o
         return self.loss
 
     def plan_guard_tripped(self):
         """Synchronising check of the device-side plan guard (see include/feta_b200.h)."""
-        plans = list(self.model.encoder.spectral_gnns._plans.values())
+        enc = self.model.encoder
+        plans = list(enc.spectral_gnns._plans.values()) + list(getattr(enc, '_static_plans', []))
         return any(p.meta_host()[7] for p in plans)

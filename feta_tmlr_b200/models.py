@@ -222,6 +222,11 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
                                        hints={'max_nodes': int(nmax), 'block_diagonal': True},
                                        norm=getattr(self.spectral_gnns, '_plan_norm', ops.NORM_CHEB_SYM))
         ctx.real = (~masks).t().unsqueeze(-1).to(torch.float32)                     # [nmax, B, 1]
+        # kept so that engine.GraphedTrainStep.plan_guard_tripped() can read the guard word of the plans its
+        # captured graphs rebuild in place on every replay
+        sp = self.__dict__.setdefault('_static_plans', [])
+        sp.append(ctx.plan)
+        del sp[:-4]
         return ctx
 
     def forward_static(self, src, pe, edge_index, degree, masks):

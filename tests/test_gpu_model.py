@@ -132,7 +132,8 @@ def test_static_shape_forward_matches_packed_forward(cuda, name, B, over):
             assert rel_err(p.grad, gref[k]) < 1e-4, k
 
 
-def test_graphed_train_step_matches_eager(cuda):
+@pytest.mark.parametrize("double_buffer", [False, True])
+def test_graphed_train_step_matches_eager(cuda, double_buffer):
     """One CUDA-graph replay per step == the eager step (same weights after 3 steps)."""
     import copy
     import feta_tmlr_b200.models as fmodels
@@ -159,8 +160,14 @@ def test_graphed_train_step_matches_eager(cuda):
         loss.backward()
         opt.step()
         losses_ref.append(float(loss.detach()))
-    eng = engine.GraphedTrainStep(m2, lf, batches[0], lr=1e-3, device=cuda, warmup=3)
-    losses = [float(eng.step(None))] + [float(eng.step(b)) for b in batches[1:]]   # capture ran batch 0 once
+    eng = engine.GraphedTrainStep(m2, lf, batches[0], lr=1e-3, device=cuda, warmup=3, double_buffer=double_buffer)
+    if double_buffer:        # two graphs over two buffer sets; the next batch's H2D copy overlaps the current step
+        pinned = [tuple(None if t is None else t.pin_memory() for t in b) for b in batches]
+        losses = [float(eng.step(None, prefetch=pinned[1]))]
+        for i in range(1, 4):
+            losses.append(float(eng.step(pinned[i], prefetch=pinned[i + 1] if i + 1 < 4 else None)))
+    else:
+        losses = [float(eng.step(None))] + [float(eng.step(b)) for b in batches[1:]]   # replay 0 = batch 0 again
     assert eng.launches_per_step > 10 and not eng.plan_guard_tripped()
     assert np.allclose(losses, losses_ref[4:] if False else losses_ref[-len(losses):], rtol=2e-4), (losses, losses_ref)
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
