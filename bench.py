@@ -447,7 +447,8 @@ def main():
                     "launches_per_step": launches_per_step_, "note": note}
         small = ("%.2f MB per launch: L2-resident, instruction/latency bound at the BASELINE shape (SURVEY.md F5); "
                  "timed as CUDA-graph replays of the kernel alone on one of the step's batches")
-        roofline = roof("attn_fwd_kernel<%d>" % dh, attn_bytes, kern_us.get("attn_fwd", float("nan")), L,
+        attn_name = "attn_fwd_tiled_kernel<%d>" if (nm > 64 and dh in (8, 16)) else "attn_fwd_kernel<%d>"
+        roofline = roof(attn_name % dh, attn_bytes, kern_us.get("attn_fwd", float("nan")), L,
                         "largest share of the step among this repo's kernels (profiles/); " + small % (attn_bytes / 1e6))
         roofline["attn_bwd_us_per_launch"] = round(kern_us.get("attn_bwd", float("nan")), 2)
         if args.config == "ZINC" and not args.batch:

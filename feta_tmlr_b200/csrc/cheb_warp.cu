@@ -1,7 +1,7 @@
 // A1/A3: warp-per-graph, TMA-staged, persistent forward of ChebConvDynamic for batches of small
 // graphs (every graph <= 64 rows): the HBM-roofline variant of csrc/cheb.cu.
 //
-// Why a second kernel: ncu on the chunk kernel (profiles/r1_cheb_fwd_chunk_sweep.md) showed 53 %
+// Why a second kernel: ncu on the chunk kernel (profiles/r1_cheb_fwd_ncu.md) showed 53 %
 // long-scoreboard stalls (Theta / CSR read through L1 in the inner loop) and 38 % barrier stalls
 // (idle threads + block-wide __syncthreads per Chebyshev order).  Here
 //   * one WARP owns one graph at a time (lane = row, up to RPL rows per lane), so the only
@@ -11,8 +11,14 @@
 //     one graph ahead; the scalars that size those copies (graph_ptr / rowptr reads) are fetched
 //     two and three graphs ahead, so no global-load latency sits on the critical path;
 //   * the filter is applied with packed fp32x2 FMAs (FFMA2) against Theta rows broadcast from
-//     shared memory; the output slab goes back with one cp.async.bulk store per graph;
+//     shared memory (F = 4, 8), or -- F = 16, where those broadcasts saturated the shared-memory
+//     pipe -- as m16n8k8 TF32 MMAs with both operands split hi + lo (three MMAs per product,
+//     fp32-grade accuracy) over XOR-swizzled 16-float slabs (conflict-free lane-per-row float4
+//     accesses AND A-fragment loads); that variant keeps ONE Theta buffer with its own barrier and
+//     propagates T_1 before the first filter application so the refill hides behind other work;
+//   * the output slab goes back with one cp.async.bulk store per graph;
 //   * the grid is persistent: 148 CTAs, each warp strides over the graph list.
+// Measured history and the ncu captures behind each step: profiles/r1_cheb_fwd_ncu.md.
 #include <stdlib.h>
 
 #include "common.cuh"

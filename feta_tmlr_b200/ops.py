@@ -186,8 +186,6 @@ def _theta_layout(theta):
     K, G, fi, fo = theta.shape
     ok = theta.stride(3) == 1 and theta.stride(2) == fo and theta.stride(0) % 4 == 0 \
         and theta.stride(1) % 4 == 0 and theta.data_ptr() % 16 == 0
-    if G == 1 and ok:
-        pass
     if not ok:
         theta = theta.contiguous()
     return theta, theta.stride(0), theta.stride(1)

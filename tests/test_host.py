@@ -45,6 +45,28 @@ def test_collate_single_node_and_edgeless_graphs():
     assert fi.tolist() == [[0, 0], [1, 0], [1, 1], [1, 2]]
 
 
+@pytest.mark.parametrize("name", ["ZINC", "PATTERN"])
+def test_collate_static_shapes_pad_with_ignored_columns(name):
+    """static=(nmax_cap, e_cap): fixed shapes for CUDA-graph replays; the real part equals the reference tuple,
+    edge padding is (-1, -1) (ignored by the plan builder), node-level labels pad with -100, and the int32 edge
+    option carries the same values."""
+    from feta_tmlr_b200 import data as fdata
+    cfg, graphs, store, ref = make_batch(name, 6, seed=3)
+    nmax = ref[0].shape[1]
+    E = ref[6].shape[1]
+    st = fdata.collate_host(store, np.arange(6), static=(nmax + 5, E + 37))
+    st32 = fdata.collate_host(store, np.arange(6), static=(nmax + 5, E + 37), edge_dtype=np.int32)
+    assert st[0].shape[1] == nmax + 5 and st[6].shape == (2, E + 37) and st[6].dtype == torch.int64
+    assert torch.equal(st[0][:, :nmax], ref[0]) and bool((st[0][:, nmax:] == 0).all())
+    assert torch.equal(st[1][:, :nmax], ref[1]) and bool(st[1][:, nmax:].all())
+    assert torch.equal(st[6][:, :E], ref[6]) and bool((st[6][:, E:] == -1).all())
+    assert st32[6].dtype == torch.int32 and torch.equal(st32[6].long(), st[6])
+    if cfg['head'] == 'node':
+        assert st[5].shape == (6, nmax + 5) and torch.equal(st[5][~st[1]], ref[5]) and bool((st[5][st[1]] == -100).all())
+    with pytest.raises(ValueError):
+        fdata.collate_host(store, np.arange(6), static=(nmax - 1, E))
+
+
 def _header_functions():
     src = open(os.path.join(ROOT, "include", "feta_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
