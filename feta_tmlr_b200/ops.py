@@ -698,7 +698,7 @@ LINEAR_TENSOR_CORES = _os.environ.get("FETA_LINEAR_TC", "0") == "1"
 def linear_tc_enabled(in_f, out_f):
     return bool(LINEAR_TENSOR_CORES and _lib.load().feta_linear_tc_supported(int(in_f), int(out_f)))
 _SIDE = {}
-_JOIN_PENDING = set()
+_JOIN_TASK = {}          # device -> id of the autograd graph task that already queued its join
 
 
 def _side_stream(device):
@@ -710,12 +710,14 @@ def _side_stream(device):
 
 
 def _queue_side_join(device):
-    if device in _JOIN_PENDING:
+    """Once per backward pass (keyed by the engine's graph-task id, so a pass that died with an exception cannot
+    leave a stale 'already queued' mark): main.wait_stream(side) when the pass completes."""
+    task = torch._C._current_graph_task_id()
+    if task >= 0 and _JOIN_TASK.get(device) == task:
         return
-    _JOIN_PENDING.add(device)
+    _JOIN_TASK[device] = task
 
     def _join():
-        _JOIN_PENDING.discard(device)
         torch.cuda.current_stream(device).wait_stream(_side_stream(device))
 
     torch.autograd.Variable._execution_engine.queue_callback(_join)
