@@ -23,6 +23,44 @@ def static_caps(store, batch_size, nmax_cap=None, slack=1.15):
     return nmax, (e_cap + 63) // 64 * 64
 
 
+class FlatAdam(object):
+    """Adam / AdamW (decoupled ``weight_decay``) over flat buffers: parameters are re-pointed to views of one
+    flat fp32 tensor laid out like ``bucket.flat`` (the flat gradient buffer), moments are flat too, and a step is
+    ``feta_adam_step`` -- one elementwise kernel instead of torch's four multi-tensor launches.  Same update rule
+    as ``torch.optim.Adam`` / ``AdamW`` (experiments/run_transformer_gengcn.py:302, ..._SBM_cv.py:371).
+    The step counter and ``lr`` are device scalars (CUDA-graph safe; ``set_lr`` needs no re-capture)."""
+
+    def __init__(self, bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.bucket = bucket
+        flat_g = bucket.flat
+        self.flat_p = torch.empty_like(flat_g)
+        off = 0
+        with torch.no_grad():
+            for p in bucket.params:
+                n = p.numel()
+                view = self.flat_p[off:off + n].view_as(p)
+                view.copy_(p)
+                p.data = view                                  # the module now reads / is updated through the flat buffer
+                off += n
+        self.exp_avg = torch.zeros_like(flat_g)
+        self.exp_avg_sq = torch.zeros_like(flat_g)
+        self.step_count = torch.zeros(1, dtype=torch.float32, device=flat_g.device)
+        self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=flat_g.device)
+        self.betas, self.eps, self.weight_decay = (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
+
+    def step(self, grad_scale=1.0):
+        """Consumes ``bucket.flat`` (gradients; slots of parameters without a gradient must hold zeros)."""
+        lib = _lib.load()
+        st = torch.cuda.current_stream(self.flat_p.device).cuda_stream
+        _lib.check(lib.feta_adam_step(self.flat_p.data_ptr(), self.bucket.flat.data_ptr(), self.exp_avg.data_ptr(),
+                                      self.exp_avg_sq.data_ptr(), self.flat_p.numel(), self.lr.data_ptr(),
+                                      self.betas[0], self.betas[1], self.eps, self.weight_decay, float(grad_scale),
+                                      self.step_count.data_ptr(), st), "feta_adam_step")
+
+
 class GraphedTrainStep(object):
     """``step(host_batch)`` copies the batch into static device buffers and replays the graph.
 
@@ -31,7 +69,8 @@ class GraphedTrainStep(object):
     NEXT mini-batch on a copy stream while the current step's graph runs, so the copy leaves the critical
     path of an end-to-end step (it is still paid for every step)."""
 
-    def __init__(self, model, loss_fn, example_batch, lr=1e-3, device=None, warmup=3, double_buffer=False):
+    def __init__(self, model, loss_fn, example_batch, lr=1e-3, device=None, warmup=3, double_buffer=False,
+                 flat_adam=True, weight_decay=0.0):
         self.model = model
         self.loss_fn = loss_fn
         dev = device or next(model.parameters()).device
@@ -44,7 +83,16 @@ class GraphedTrainStep(object):
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
                                                            torch.distributed.is_initialized()) else 1
         self.bucket = ddp.FlatGradBucket(self.params, attach=False)
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, fused=True, capturable=True)
+        # flat_adam: one-kernel Adam over flat parameter / gradient / moment buffers (FlatAdam);
+        # otherwise torch's fused multi-tensor Adam (4 launches per step)
+        self.flat_adam = bool(flat_adam)
+        if self.flat_adam:
+            self.opt = FlatAdam(self.bucket, lr=lr, weight_decay=weight_decay)
+        elif weight_decay:
+            self.opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=weight_decay, fused=True,
+                                         capturable=True)
+        else:
+            self.opt = torch.optim.Adam(model.parameters(), lr=lr, fused=True, capturable=True)
         self.losses = [None] * self.nsets
         self.loss = None
         self.launches_per_step = 0
@@ -79,13 +127,20 @@ class GraphedTrainStep(object):
         out = self.model.forward_static(px, ei, mask, pe, lap, deg)
         loss = self.loss_fn(out, labels)
         loss.backward()
-        if self.world > 1:                      # one flat all-reduce; the optimizer reads the flat views
-            live = [(p, v) for p, v in zip(self.params, self.bucket.views) if p.grad is not None]
+        if self.flat_adam:                      # gradients -> flat buffer (one multi-tensor copy), one SUM all-reduce,
+            live = [(p, v) for p, v in zip(self.params, self.bucket.views) if p.grad is not None]   # one Adam kernel
             torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])
-            self.bucket.all_reduce_mean()
-            for p, v in live:
-                p.grad = v
-        self.opt.step()
+            if self.world > 1:
+                torch.distributed.all_reduce(self.bucket.flat, op=torch.distributed.ReduceOp.SUM)
+            self.opt.step(grad_scale=1.0 / self.world)      # the 1/world of the mean is folded into the update
+        else:
+            if self.world > 1:                  # one flat all-reduce; the optimizer reads the flat views
+                live = [(p, v) for p, v in zip(self.params, self.bucket.views) if p.grad is not None]
+                torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])
+                self.bucket.all_reduce_mean()
+                for p, v in live:
+                    p.grad = v
+            self.opt.step()
         self.losses[s] = loss.detach()
         self.loss = self.losses[s]
 

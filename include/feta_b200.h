@@ -240,6 +240,21 @@ int feta_linear_dx(const float* dY, const float* W, const float* dres, const flo
                    int in, int out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Optimizer step of the measured training step: `optim.Adam(model.parameters(), lr=args.lr)`
+ * (experiments/run_transformer_gengcn.py:302) / `optim.AdamW(..., weight_decay=)`
+ * (experiments/run_transformer_gengcn_SBM_cv.py:371) over ONE flat fp32 buffer each for parameters,
+ * gradients and the two moments (n elements, 16-byte aligned):
+ *     step += 1;  g' = grad_scale * g;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;
+ *     p = p (1 - lr wd) - lr / (1 - b1^step) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)
+ * `step` (one float, starts at 0) and `lr` (one float) live on the device: graph-replay safe, and a
+ * scheduler changes the rate without re-capture.  weight_decay is decoupled (AdamW); 0 = Adam.
+ * grad_scale folds the 1/world_size of the gradient mean.  Two launches (tick + update).
+ * --------------------------------------------------------------------------------------- */
+int feta_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   const float* lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                   float* step, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * A4  DiffTransformerEncoderGenGCN.get_filter_coefficients (transformer/models.py:240-287).
  * With x == 1 the all-pairs GCNConv of :280-282 is  s_j * colsum(W) + b  with a per-node scalar
  *     loop_j = a_jj != 0 ? a_jj : 1;  deg_j = sum_{i != j} a_ij + loop_j;
