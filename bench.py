@@ -481,8 +481,10 @@ def main():
                            "l2": "inputs rotate through a pool of %d distinct device-resident batches "
                                  "(%.0f MB > 126 MB L2)" % (n_pool, n_pool * per_batch / 1e6),
                            "edges": "reference-faithful un-tiled edge_index (SURVEY.md F4)",
-                           "execution": ("whole training step captured once as ONE CUDA graph over static shapes "
-                                         "(engine.GraphedTrainStep), replayed per mini-batch") if use_graph else
+                           "execution": ("whole training step (forward, loss, backward, gradient all-reduce, flat Adam) "
+                                         "captured as ONE CUDA graph over static shapes (engine.GraphedTrainStep; two "
+                                         "graphs over two input-buffer sets so the next batch's H2D copy overlaps), "
+                                         "replayed per mini-batch") if use_graph else
                            "eager PyTorch autograd over C-ABI kernels, current stream"},
                 "clocks": clocks,
                 "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
