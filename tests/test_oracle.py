@@ -199,13 +199,15 @@ def test_golden_vectors(name):
         assert torch.allclose(coeff, g['coeff'], rtol=1e-5, atol=1e-6)
 
 
-def test_arma_oracle_matches_dense_closed_form():
+@pytest.mark.parametrize("seed,sizes,self_loops", [(11, [5, 1, 7, 3], True), (12, [1, 1, 2], True), (13, [9, 4], False),
+                                                   (14, [3, 6, 1, 1, 8], True)])
+def test_arma_oracle_matches_dense_closed_form(seed, sizes, self_loops):
     """ARMAConvDynamic restatement (literal per-node weights + bmm) == dense closed form in fp64:
-    mean_k relu(a_k A_hat x W_k + b_k x V_k + bias_k), A_hat = D_in^-1/2 A^T-accumulate D_in^-1/2."""
+    mean_k relu(a_k A_hat x W_k + b_k x V_k + bias_k), A_hat = D_in^-1/2 A^T-accumulate D_in^-1/2 -- with isolated
+    nodes (degree 0 -> 0, not inf), kept self-loops, multi-edges and directed extras."""
     from helpers import random_batch_graph
     from oracle.arma import arma_conv_dynamic
-    sizes = [5, 1, 7, 3]
-    ei, batch, R = random_batch_graph(11, sizes, directed_extra=2)
+    ei, batch, R = random_batch_graph(seed, sizes, directed_extra=2, self_loops=self_loops)
     K, F, G = 3, 4, len(sizes)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(R, F, generator=g, dtype=torch.float64)
