@@ -97,6 +97,11 @@ class ChebConvDynamic(nn.Module):
             if lambda_max.numel() != 1:
                 raise NotImplementedError("ChebConvDynamic(b200): per-graph lambda_max is not implemented")
             lambda_max = float(lambda_max)
+        if float(lambda_max) != 2.0:
+            # __norm__ (:115-127) leaves a diagonal of 2/lambda_max - 1 (the +1 loops of get_laplacian scaled,
+            # then add_self_loops(-1)); it vanishes only at lambda_max = 2, which is all the plan stores.
+            raise NotImplementedError("ChebConvDynamic(b200): lambda_max != 2.0 is not implemented (the reference "
+                                      "drivers never pass it: models.py:360 -> None -> 2.0)")
         if batch is None:
             raise NameError("ChebConvDynamic.forward: `weight` is unbound when batch is None "
                             "(ChebNetDynamic.py:146-166) -- pass `batch`")

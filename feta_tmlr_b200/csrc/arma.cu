@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(512) arma_fwd_kernel(
     int64_t R, int K, int C, int cap, int32_t* meta, int64_t G, int max_nodes) {
   constexpr int LD = F + 4;
   extern __shared__ float4 smem_f4[];
-  if (!plan_guard_ok(meta, G, max_nodes)) return;
+  if (!plan_guard_ok(meta, G, max_nodes)) { nan_fill(out, R * F); nan_fill(prop, R * F); return; }
   float* buf0 = reinterpret_cast<float*>(smem_f4);
   float* buf1 = buf0 + (size_t)cap * LD;
   float* ws = buf1 + (size_t)cap * LD;
@@ -143,7 +143,11 @@ __global__ void __launch_bounds__(256) arma_bwd_kernel(
     int max_nodes) {
   constexpr int LD = F + 4;
   extern __shared__ float4 smem_f4[];
-  if (!plan_guard_ok(meta, G, max_nodes)) return;
+  if (!plan_guard_ok(meta, G, max_nodes)) {
+    nan_fill(dx, R * F); nan_fill(dx_root, R * F); nan_fill(dcoeff, G * 2 * K);
+    nan_fill(dz, R * K * F); nan_fill(dza, R * K * F); nan_fill(dzb, R * K * F);
+    return;
+  }
   float* buf0 = reinterpret_cast<float*>(smem_f4);
   float* part = buf0 + (size_t)cap * LD;   // [cap, 2K] per-row coefficient partials
   float* ws = part + (size_t)cap * 2 * K;

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(fused_max_threads<F>()) cheb_fwd_fused_kernel(
     float* __restrict__ out, int64_t R, int K, int C, int cap, int32_t* meta, int64_t G, int max_nodes) {
   constexpr int LD = F + 4;
   extern __shared__ float4 smem_f4[];
-  if (!plan_guard_ok(meta, G, max_nodes)) return;
+  if (!plan_guard_ok(meta, G, max_nodes)) { nan_fill(out, R * F); return; }
   float* buf0 = reinterpret_cast<float*>(smem_f4);
   float* buf1 = buf0 + (size_t)cap * LD;
 
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(fused_max_threads<F>()) cheb_bwd_dx_fused_kern
     float* __restrict__ dx, int64_t R, int K, int C, int cap, int32_t* meta, int64_t G, int max_nodes) {
   constexpr int LD = F + 4;
   extern __shared__ float4 smem_f4[];
-  if (!plan_guard_ok(meta, G, max_nodes)) return;
+  if (!plan_guard_ok(meta, G, max_nodes)) { nan_fill(dx, R * F); return; }
   float* buf0 = reinterpret_cast<float*>(smem_f4);
   float* buf1 = buf0 + (size_t)cap * LD;
 
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(fused_max_threads<F>()) cheb_bwd_dtheta_fused_
     int C, int cap, int32_t* meta, int64_t G, int max_nodes) {
   constexpr int LD = F + 4, NG = F * F / 4;
   extern __shared__ float4 smem_f4[];
-  if (!plan_guard_ok(meta, G, max_nodes)) return;
+  if (!plan_guard_ok(meta, G, max_nodes)) { nan_fill_theta(dtheta, sk, sg, K, G, F * F); return; }
   float* buf0 = reinterpret_cast<float*>(smem_f4);
   float* buf1 = buf0 + (size_t)cap * LD;
   float* sD = buf1 + (size_t)cap * LD;

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "graph_tile.cuh"
 
 namespace feta {
 
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(warp_kernel_max_threads<F, USE_MMA>(), 1) cheb
                     meta[FETA_META_BAD_INDEX] == 0;
     if (!ok) {
       if (threadIdx.x == 0) meta[FETA_META_GUARD] = 1;
+      nan_fill(out, R * F);     // a refused launch leaves NaN, never uninitialised memory
       return;
     }
   }

@@ -30,6 +30,25 @@ __device__ __forceinline__ bool plan_guard_ok(int32_t* meta, int64_t G, int max_
   return ok;
 }
 
+// A refused launch must not leave its (torch.empty) outputs as uninitialised memory that flows into the loss:
+// every output is filled with NaN so the failure is visible downstream without a device->host read.
+__device__ __forceinline__ void nan_fill(float* __restrict__ p, int64_t n) {
+  if (p == nullptr) return;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = qnan;
+}
+__device__ __forceinline__ void nan_fill_theta(float* __restrict__ p, int64_t sk, int64_t sg, int K, int64_t G,
+                                               int FF) {
+  if (p == nullptr) return;
+  const float qnan = __int_as_float(0x7fc00000);
+  const int64_t n = (int64_t)K * G * FF;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t kg = i / FF;
+    p[(kg / G) * sk + (kg % G) * sg + (i - kg * FF)] = qnan;
+  }
+}
+
 // coalesced copy of a [n, F] row-major global slab into shared memory with row stride LD
 template <int F>
 __device__ __forceinline__ void slab_to_smem(float* __restrict__ dst, const float* __restrict__ src, int n) {

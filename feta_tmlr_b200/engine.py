@@ -9,7 +9,7 @@ once, over static shapes (B, Nmax_cap, E_cap), and replays it for every mini-bat
 """
 import torch
 
-from . import _lib, ddp
+from . import _lib, ddp, ops
 
 
 def static_caps(store, batch_size, nmax_cap=None, slack=1.15):
@@ -126,7 +126,8 @@ class GraphedTrainStep(object):
             p.grad = None                       # autograd then WRITES each gradient (no += kernels)
         out = self.model.forward_static(px, ei, mask, pe, lap, deg)
         loss = self.loss_fn(out, labels)
-        loss.backward()
+        with ops.wgrad_side_stream(True):       # safe here: every p.grad is None and is read only after the pass
+            loss.backward()
         if self.flat_adam:                      # gradients -> flat buffer (one multi-tensor copy), one SUM all-reduce,
             live = [(p, v) for p, v in zip(self.params, self.bucket.views) if p.grad is not None]   # one Adam kernel
             torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])

@@ -684,10 +684,38 @@ def _counters(device):
 
 
 # Weight gradients are off the critical path of the backward pass (nothing reads them before the
-# optimizer / gradient all-reduce), so they run on a per-device side stream: inside a captured step that
+# optimizer / gradient all-reduce), so they CAN run on a per-device side stream: inside a captured step that
 # is a parallel branch of the CUDA graph, overlapping the ~70-CTA reduction kernels with the main chain.
 # The side stream is joined once per backward pass by an autograd-engine callback.
-WGRAD_SIDE_STREAM = _os.environ.get("FETA_WGRAD_SIDE_STREAM", "1") == "1"
+#
+# This is only safe when nothing on the main stream touches those gradients before the join -- autograd
+# believes they were produced on the main stream, so an AccumulateGrad that adds into an existing ``p.grad``
+# (gradient accumulation, ``zero_grad(set_to_none=False)``, ``FlatGradBucket(attach=True)``) would race with
+# the side kernels.  It is therefore OFF unless a caller that guarantees ``p.grad is None`` at backward time
+# and consumes the gradients only after the pass opts in with ``wgrad_side_stream(True)``
+# (engine.GraphedTrainStep does); FETA_WGRAD_SIDE_STREAM=0 vetoes it everywhere.
+_SIDE_ALLOWED = _os.environ.get("FETA_WGRAD_SIDE_STREAM", "1") == "1"
+WGRAD_SIDE_STREAM = False
+
+
+class wgrad_side_stream(object):
+    """Context manager / switch: ``with ops.wgrad_side_stream(True): loss.backward()``."""
+
+    def __init__(self, on=True):
+        self.on = bool(on) and _SIDE_ALLOWED
+
+    def __enter__(self):
+        global WGRAD_SIDE_STREAM
+        self.prev = WGRAD_SIDE_STREAM
+        WGRAD_SIDE_STREAM = self.on
+        return self
+
+    def __exit__(self, *exc):
+        global WGRAD_SIDE_STREAM
+        WGRAD_SIDE_STREAM = self.prev
+        return False
+
+
 # Opt-in: the layer's projections through csrc/dense_tc.cu (3xTF32 mma.sync GEMMs with fused ReLU-mask /
 # residual-gradient epilogues) instead of the library sgemm.  Measured SLOWER on B200 (ZINC shape, in-graph:
 # 7.0-13.4 us vs 4.3-7.9 us per GEMM -- three legacy TF32 MMAs per product run at about the SIMT fp32 rate),

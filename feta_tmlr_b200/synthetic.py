@@ -142,6 +142,7 @@ def build_model(name, module, **overrides):
              'node': ('DiffGraphTransformerGenGCNSBM', 'OracleDiffGraphTransformerGenGCNSBM'),
              'molhiv': ('DiffGraphTransformerGenGCNMolHiv', 'OracleDiffGraphTransformerGenGCNMolHiv')}[cfg['head']]
     cls = getattr(module, names[0], None) or getattr(module, names[1])
-    if 'gnn_type' in cfg:
-        kw['gnn_type'] = cfg['gnn_type']
+    for k in ('gnn_type', 'last_layer_filter', 'learn_only_filter_order_coeff'):
+        if k in cfg:
+            kw[k] = cfg[k]
     return cls(**kw)

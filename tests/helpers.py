@@ -82,3 +82,117 @@ def to_dev(batch, dev):
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference-generated fixtures (tests/golden/make_golden_from_reference.py)
+# ---------------------------------------------------------------------------------------------------
+def det_init(module, seed):
+    """Deterministic, library-independent parameter values (NumPy legacy MT19937 stream, which NumPy keeps
+    frozen): glorot-uniform over the last two dims for matrices, 1 +- 0.1 for norm scales, +-0.1 for every
+    other vector.  The generator and the tests both call this, so fixtures never store weights."""
+    import math
+    rs = np.random.RandomState(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            shape = tuple(p.shape)
+            if p.dim() >= 2:
+                a = math.sqrt(6.0 / (shape[-2] + shape[-1]))
+                v = rs.uniform(-a, a, size=shape)
+            elif 'norm' in name and name.endswith('weight'):
+                v = 1.0 + 0.1 * rs.uniform(-1, 1, size=shape)
+            else:
+                v = 0.1 * rs.uniform(-1, 1, size=shape)
+            p.copy_(torch.from_numpy(v.astype(np.float32)).to(p.dtype))
+    return module
+
+
+BIG_GRAD = 1 << 12          # gradients with more entries than this are stored as summaries
+
+
+def grad_summary(g):
+    """Compact stand-in for a large 2-D gradient: row sums, column sums, 4 rows and 4 columns."""
+    g = g.detach()
+    r = torch.linspace(0, g.shape[0] - 1, 4).long()
+    c = torch.linspace(0, g.shape[1] - 1, 4).long()
+    return dict(summary=True, shape=tuple(g.shape), rowsum=g.sum(1), colsum=g.sum(0), rows=g[r], cols=g[:, c],
+                absmax=g.abs().max())
+
+
+def check_grad(got, want, tol, name=""):
+    """``want``: a tensor or a ``grad_summary`` dict (fixture side).  Relative to the largest entry."""
+    got = got.detach().double().cpu()
+    if isinstance(want, dict):
+        s = grad_summary(got)
+        for k in ("rowsum", "colsum", "rows", "cols"):
+            ref = want[k].double()
+            scale = max(float(ref.abs().max()), float(want['absmax']), 1e-30)     # a summary can be all ~0
+            err = float((s[k].double() - ref).abs().max()) / scale
+            assert err < tol, (name, k, err)
+        return
+    want = want.double()
+    err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
+    assert err < tol, (name, err)
+
+
+def graphs_from_fixture(glist):
+    """Stored compact graphs -> the dict form synthetic.make_graph produces."""
+    out = []
+    for g in glist:
+        d = dict(x=g['x'].numpy(), edge_index=g['edge_index'].numpy().astype(np.int64), y=g['y'].numpy())
+        n = d['x'].shape[0]
+        d['degree'] = fdata.degree_scaling(d['edge_index'], n)
+        d['pe'] = g['pe'].numpy() if g.get('pe') is not None else None
+        d['lap_pe'] = g['lap_pe'].numpy() if g.get('lap_pe') is not None else None
+        if g.get('edge_attr') is not None:
+            d['edge_attr'] = g['edge_attr'].numpy()
+        out.append(d)
+    return out
+
+
+def pack_tree(obj, f32=False):
+    """Shrink a fixture tree for storage: integer tensors go to the narrowest dtype that holds them (original
+    dtype recorded), fp64 tensors go to fp32 when ``f32`` (used for gradients: 6e-8 rounding vs a 1e-4 gate)."""
+    if torch.is_tensor(obj):
+        if obj.dtype in (torch.int64, torch.int32):
+            lo, hi = (int(obj.min()), int(obj.max())) if obj.numel() else (0, 0)
+            for dt, bound in ((torch.int8, 127), (torch.int16, 32767), (torch.int32, 2 ** 31 - 1)):
+                if -bound <= lo and hi <= bound and dt != obj.dtype:
+                    return dict(__packed__=str(obj.dtype), data=obj.to(dt))
+            return obj
+        if f32 and obj.dtype == torch.float64:
+            return obj.float()
+        return obj.clone()
+    if isinstance(obj, dict):
+        return {k: pack_tree(v, f32 or k in ('grads', 'dx', 'dcoeff', 'dbias', 'dweight', 'coeff')) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [pack_tree(v, f32) for v in obj]
+    return obj
+
+
+def unpack_tree(obj):
+    if isinstance(obj, dict):
+        if '__packed__' in obj:
+            return obj['data'].to(getattr(torch, obj['__packed__'].split('.')[-1]))
+        return {k: unpack_tree(v) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [unpack_tree(v) for v in obj]
+    return obj
+
+
+def save_fixture(obj, path):
+    import gzip
+    import io
+    buf = io.BytesIO()
+    torch.save(pack_tree(obj), buf)
+    with gzip.open(path, 'wb', compresslevel=9) as f:
+        f.write(buf.getvalue())
+
+
+def load_fixture(name):
+    import gzip
+    import io
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name)
+    with gzip.open(path, 'rb') as f:
+        return unpack_tree(torch.load(io.BytesIO(f.read()), weights_only=False))

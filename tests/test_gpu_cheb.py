@@ -179,3 +179,27 @@ def test_cheb_rejects_unsupported(cuda):
     m = ChebConvDynamic(4, 4, 2).to(cuda)
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 4), torch.zeros(2, 0, dtype=torch.long), torch.zeros(2, 1, 4, 4), batch=torch.zeros(2))
+    m = ChebConvDynamic(4, 4, 2).to(cuda)
+    with pytest.raises(NotImplementedError):                          # __norm__ keeps a diagonal unless lambda_max = 2
+        m(torch.zeros(2, 4, device=cuda), torch.zeros(2, 0, dtype=torch.long, device=cuda),
+          torch.zeros(2, 1, 4, 4, device=cuda), batch=torch.zeros(2, device=cuda), lambda_max=3.0)
+
+
+@pytest.mark.parametrize("sizes", [[5, 9, 7], [80, 120]])
+def test_guard_refusal_is_visible(cuda, sizes):
+    """Hinted plans skip the host-side validation; when the hints do not hold the fused kernels refuse to run,
+    and they must leave NaN (never uninitialised memory) in every output, forward and backward."""
+    from feta_tmlr_b200 import ops
+    ei, batch, R = random_batch_graph(7, sizes)
+    G, F, K = len(sizes), 16, 4
+    plan = ops.build_cheb_plan(ei.to(cuda), batch.to(cuda), R, G, 2.0,
+                               hints={'max_nodes': min(sizes) - 1, 'block_diagonal': True})   # wrong on purpose
+    x = torch.randn(R, F, device=cuda, requires_grad=True)
+    theta = torch.randn(K, G, F, F, device=cuda, requires_grad=True)
+    bias = torch.zeros(F, device=cuda)
+    out = ops.cheb_filter(x, theta, bias, plan)
+    assert bool(torch.isnan(out).all())
+    out.backward(torch.ones_like(out))
+    assert bool(torch.isnan(x.grad).all()) and bool(torch.isnan(theta.grad).all())
+    with pytest.raises(RuntimeError):
+        plan.validate()

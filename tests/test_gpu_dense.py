@@ -144,3 +144,55 @@ def test_flat_adam_matches_torch(cuda, weight_decay):
         for a, b in zip(mine, ref):
             assert rel_err(a, b) < 2e-6, step
     assert float(fa.step_count) == 6.0
+
+
+def test_gradient_accumulation_over_two_backward_passes(cuda):
+    """Default mode (no opt-in side stream): a second backward pass accumulates into existing ``.grad`` tensors --
+    the case the side-stream variant must never be used for (autograd adds on the main stream)."""
+    from feta_tmlr_b200 import ops
+    from feta_tmlr_b200.layers import DiffTransformerEncoderLayer
+    assert ops.WGRAD_SIDE_STREAM is False
+    torch.manual_seed(3)
+    d, H, B, nmax = 64, 4, 48, 40
+    layer = DiffTransformerEncoderLayer(d, H, 2 * d, 0.0).to(cuda)
+    src = torch.randn(nmax, B, d, device=cuda)
+    lens = torch.randint(5, nmax + 1, (B,), device=cuda)
+    mask = torch.arange(nmax, device=cuda)[None, :] >= lens[:, None]
+    pe = torch.rand(B, nmax, nmax, device=cuda)
+    deg = torch.rand(B, nmax, device=cuda)
+
+    def run():
+        out, _ = layer(src, pe=pe, degree=deg, src_key_padding_mask=mask)
+        out.square().mean().backward()
+
+    run()
+    torch.cuda.synchronize()
+    once = {k: p.grad.clone() for k, p in layer.named_parameters()}
+    for _ in range(3):
+        run()                                   # accumulates: grad = 4 x once
+    torch.cuda.synchronize()
+    for k, p in layer.named_parameters():
+        assert rel_err(p.grad, 4 * once[k]) < 1e-5, k
+
+
+def test_side_stream_opt_in_matches_main_stream(cuda):
+    from feta_tmlr_b200 import ops
+    from feta_tmlr_b200.layers import DiffTransformerEncoderLayer
+    torch.manual_seed(4)
+    d, H, B, nmax = 64, 8, 32, 30
+    layer = DiffTransformerEncoderLayer(d, H, 2 * d, 0.0).to(cuda)
+    src = torch.randn(nmax, B, d, device=cuda)
+    pe = torch.rand(B, nmax, nmax, device=cuda)
+    deg = torch.rand(B, nmax, device=cuda)
+    grads = []
+    for on in (False, True):
+        for p in layer.parameters():
+            p.grad = None
+        out, _ = layer(src, pe=pe, degree=deg)
+        with ops.wgrad_side_stream(on):
+            out.square().mean().backward()
+        torch.cuda.synchronize()
+        grads.append({k: p.grad.clone() for k, p in layer.named_parameters()})
+    assert ops.WGRAD_SIDE_STREAM is False
+    for k in grads[0]:
+        assert torch.equal(grads[0][k], grads[1][k]), k

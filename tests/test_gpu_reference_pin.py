@@ -1,0 +1,185 @@
+"""GPU parity against vectors produced by RUNNING THE REFERENCE (tests/golden/ref_*.pt.gz, see
+tests/golden/make_golden_from_reference.py): the CUDA path through the C ABI, default switches, vs the outputs of
+the unmodified ``/root/reference/transformer/{ChebNetDynamic,models,data}.py`` -- no oracle code in the loop.
+
+Tolerances (north_star): integer work bit-exact; fp32 vs the fp64 reference run 1e-4 relative to the largest
+entry, forward AND gradients.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import check_grad, det_init, graphs_from_fixture, load_fixture, rel_err, to_dev
+from feta_tmlr_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+OPS = load_fixture("ref_ops.pt.gz")
+COLLATE = load_fixture("ref_collate.pt.gz")
+MODEL_FIXTURES = ["MUTAG", "ZINC", "PATTERN", "CLUSTER", "MOLHIV", "ZINC_bn", "MUTAG_all_layers",
+                  "MUTAG_learn_only", "ZINC_arma"]
+
+
+@pytest.mark.parametrize("i", range(len(OPS['cheb'])))
+def test_cheb_matches_reference_run(cuda, i):
+    """A1/A3 (ChebNetDynamic.py:132-193): out, dx, dTheta, dbias (and dW in learn_only mode)."""
+    from feta_tmlr_b200 import ChebConvDynamic
+    c = OPS['cheb'][i]
+    Fc, K = c['F'], c['K']
+    m = ChebConvDynamic(Fc, Fc, K, learn_only_filter_order_coeff=c['learn_only']).to(cuda)
+    m.bias.data.copy_(c['bias'])
+    x = c['x'].to(cuda).requires_grad_()
+    cd = c['coeff'].to(cuda).requires_grad_()
+    if c['learn_only']:
+        m.weight.data.copy_(c['weight'])
+        fc = cd.reshape((-1, K)).permute([1, 0])
+    else:
+        fc = cd.reshape((-1, K, Fc, Fc)).permute([1, 0, 2, 3])
+    b = (c['batch'].float() if c['float_batch'] else c['batch']).to(cuda)
+    y = m(x, c['edge_index'].to(cuda), fc, batch=b)
+    (y * c['w'].to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    assert y.shape == c['out'].shape
+    assert rel_err(y, c['out']) < TOL
+    check_grad(x.grad, c['dx'], TOL, "dx")
+    check_grad(cd.grad, c['dcoeff'], TOL, "dcoeff")
+    check_grad(m.bias.grad, c['dbias'], TOL, "dbias")
+    if c['learn_only']:
+        check_grad(m.weight.grad, c['dweight'], TOL, "dweight")
+
+
+@pytest.mark.parametrize("i", range(len(OPS['cheb'])))
+def test_plan_matches_reference_norm(cuda, i):
+    """A2 (ChebNetDynamic.py:108-130): the CSR plan holds exactly the reference's off-diagonal entries, grouped by
+    target in input order (bit-exact structure, values to fp32 rounding); the reference's diagonal cancels."""
+    from feta_tmlr_b200 import ops
+    c = OPS['cheb'][i]
+    R = c['x'].shape[0]
+    G = c['H'] * c['B']
+    p = ops.build_cheb_plan(c['edge_index'].to(cuda), c['batch'].to(cuda), R, G, 2.0)
+    rei, rw = c['norm_edge_index'], c['norm_weight']
+    off = rei[0] != rei[1]
+    src, dst, w = rei[0][off].numpy(), rei[1][off].numpy(), rw[off].numpy()
+    for tr, (rp, ci, va) in ((False, (p.rowptr, p.colidx, p.vals)), (True, (p.rowptr_t, p.colidx_t, p.vals_t))):
+        key, other = (src, dst) if tr else (dst, src)
+        order = np.argsort(key, kind='stable')
+        rowptr = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=R))]).astype(np.int32)
+        nnz = int(rowptr[-1])
+        assert np.array_equal(rp.cpu().numpy(), rowptr)
+        assert np.array_equal(ci.cpu().numpy()[:nnz], other[order].astype(np.int32))
+        np.testing.assert_allclose(va.cpu().numpy()[:nnz].astype(np.float64), w[order], rtol=3e-7, atol=0)
+
+
+@pytest.mark.parametrize("i", range(len(OPS['arma'])))
+def test_arma_matches_reference_run(cuda, i):
+    from feta_tmlr_b200 import ARMAConvDynamic
+    c = OPS['arma'][i]
+    m = ARMAConvDynamic(c['F'], c['F'], num_stacks=c['K'], num_layers=1)
+    det_init(m, c['seed'])
+    m = m.to(cuda)
+    x, cd = c['x'].to(cuda).requires_grad_(), c['coeff'].to(cuda).requires_grad_()
+    y = m(x, c['edge_index'].to(cuda), cd, batch=c['batch'].float().to(cuda))
+    (y * c['w'].to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(y, c['out']) < TOL
+    check_grad(x.grad, c['dx'], TOL, "dx")
+    check_grad(cd.grad, c['dcoeff'], TOL, "dcoeff")
+    for k, p in m.named_parameters():
+        if k in c['grads']:
+            check_grad(p.grad, c['grads'][k], TOL, k)
+        else:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+
+
+@pytest.mark.parametrize("i", range(len(OPS['coeff'])))
+def test_filter_coefficients_match_reference_run(cuda, i):
+    """A4 (models.py:240-287 run literally by the reference) vs coeff.cu + the pooled Linear."""
+    import feta_tmlr_b200.models as fmodels
+    c = OPS['coeff'][i]
+    H, dh = c['H'], c['dh']
+    d = H * dh
+    layer = fmodels.DiffTransformerEncoderLayer(d, H, 2 * d, 0.0)
+    enc = fmodels.DiffTransformerEncoderGenGCN(d, H, layer, 1, num_coefficients=4)
+    det_init(enc, c['seed'])
+    enc = enc.to(cuda)
+    lens = torch.tensor(c['lens'])
+    N = int(lens.sum())
+    B = len(c['lens'])
+    fi = torch.tensor([[b, j] for b in range(B) for j in range(c['lens'][b])])
+    batch = fi[:, 0].clone()
+    ei = torch.zeros((2, 0), dtype=torch.int64)
+    out = enc.get_filter_coefficients(c['attn'].to(cuda), ei.to(cuda), fi.to(cuda), batch.to(cuda), c['mask'].to(cuda))
+    (out * c['w'].to(cuda)).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(out, c['coeff']) < TOL
+    for k, p in enc.named_parameters():
+        if k in c['grads']:
+            check_grad(p.grad, c['grads'][k], TOL, k)
+
+
+def test_global_avg_matches_reference_run(cuda):
+    import feta_tmlr_b200.models as fmodels
+    c = OPS['global_avg']
+    out = fmodels.GlobalAvg1D()(c['x'].to(cuda), c['mask'].to(cuda))
+    assert rel_err(out, c['out']) < 1e-6
+
+
+@pytest.mark.parametrize("name", sorted(COLLATE))
+def test_device_batch_builder_equals_reference_collate(cuda, name):
+    """A7/N2: csrc/collate.cu vs the reference's collate_fn output, bit for bit."""
+    from feta_tmlr_b200 import data as fdata
+    c = COLLATE[name]
+    cfg = synthetic.CONFIGS[name]
+    graphs = graphs_from_fixture(c['graphs'])
+    store = fdata.GraphStore(graphs, kind=cfg['kind'], n_tags=cfg['n_tags'])
+    got = fdata.DeviceBatchBuilder(store, cuda).build(np.asarray(c['ids']))
+    torch.cuda.synchronize()
+    for k, (a, b) in enumerate(zip(got, c['batch'][:9])):
+        if b is None:
+            assert a is None, k
+            continue
+        assert a.dtype == b.dtype and tuple(a.shape) == tuple(b.shape), (k, a.dtype, b.dtype, a.shape, b.shape)
+        assert torch.equal(a.cpu(), b), "field %d" % k
+
+
+def _loss(name, out, labels):
+    import torch.nn.functional as F
+    if name in ("PATTERN", "CLUSTER", "MUTAG"):
+        return F.cross_entropy(out, labels.long())
+    if name == "ZINC":
+        return F.l1_loss(out, labels.to(out.dtype))
+    return F.binary_cross_entropy_with_logits(out.reshape(-1), labels.reshape(-1).to(out.dtype))
+
+
+@pytest.mark.parametrize("tag", MODEL_FIXTURES)
+def test_model_matches_reference_run(cuda, tag):
+    """Whole models at the BASELINE shapes (full d=64, reference hyper-parameters): the reference ran its literal
+    op sequence (host loop, all-pairs GCNConv, per-node filter materialisation) in fp64; the CUDA path runs with
+    its default switches in fp32."""
+    import feta_tmlr_b200.models as fmodels
+    fx = load_fixture("ref_model_%s.pt.gz" % tag)
+    name = fx['name']
+    m = synthetic.build_model(name, fmodels, **fx['over'])
+    det_init(m, fx['seed'])
+    m = m.to(cuda).train()
+    g = to_dev(fx['batch'], cuda)
+    res = m(g[0], g[6], g[7], g[8], g[1], g[2], g[3], g[4], return_filter_coeff=True)
+    out, coeff = res[0], res[-1]
+    loss = _loss(name, out, g[5])
+    loss.backward()
+    torch.cuda.synchronize()
+    assert out.shape == fx['out'].shape
+    assert rel_err(out, fx['out']) < TOL, rel_err(out, fx['out'])
+    assert rel_err(coeff, fx['coeff']) < TOL
+    assert abs(float(loss) - float(fx['loss'])) < TOL * max(1.0, abs(float(fx['loss'])))
+    got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    worst = ("", 0.0)
+    for k, want in fx['grads'].items():
+        assert k in got, k
+        try:
+            check_grad(got[k], want, TOL, k)
+        except AssertionError as e:
+            worst = max(worst, (k, e.args[0][-1]), key=lambda t: t[1])
+    assert worst[1] == 0.0, worst
+    for k in fx['no_grad']:
+        assert k not in got or float(got[k].abs().max()) == 0.0, k
