@@ -61,6 +61,7 @@ SIGNATURES = {
     "feta_scatter_rows": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int, _P]),
     "feta_collate_indices": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P,
                                      c_int, c_int, c_int64, c_int64, _P]),
+    "feta_collate_edges_static": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int, c_int64, c_int64, _P]),
     "feta_collate_pad_rows": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "feta_collate_pad_pe": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
 }

@@ -18,6 +18,17 @@
 namespace feta {
 
 // csrc/cheb_warp.cu: warp-per-graph TMA-staged forward (graphs of <= 64 rows); 1 = not eligible
+int cheb_fwd_tile_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                      const int32_t* graph_ptr, const int32_t* row_graph, const float* theta, int64_t sk, int64_t sg,
+                      const float* bias, float* out, int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta,
+                      cudaStream_t st);
+int cheb_fwd_dense_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                       const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias,
+                       float* out, int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
+int cheb_bwd_dense_try(const float* dout, const float* x, const int32_t* rowptr, const int32_t* colidx,
+                       const float* vals, const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t,
+                       const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, float* dx, float* dtheta,
+                       int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
 int cheb_fwd_warp_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                       const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias,
                       float* out, int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
@@ -414,6 +425,16 @@ extern "C" int feta_cheb_fwd(const float* x, const int32_t* rowptr, const int32_
   const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)theta % 16 == 0) &&
                        (sk % 4 == 0) && (sg % 4 == 0);
   FusedCfg cfg = fused_config(fin, max_nodes, 2, false);
+  if (fin == fout && block_diagonal && aligned) {   // large graphs: one CTA per graph, edge-parallel
+    rc = cheb_fwd_dense_try(x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, fin, max_nodes,
+                            plan_meta, st);
+    if (rc <= 0) return rc;
+  }
+  if (fin == fout && block_diagonal && aligned) {   // tcgen05 tile kernel (F = 8, 16; graphs <= 256 rows)
+    rc = cheb_fwd_tile_try(x, rowptr, colidx, vals, graph_ptr, row_graph, theta, sk, sg, bias, out, R, G, K, fin,
+                           max_nodes, plan_meta, st);
+    if (rc <= 0) return rc;
+  }
   if (fin == fout && block_diagonal && aligned && getenv("FETA_CHEB_NO_WARP_KERNEL") == nullptr) {
     rc = cheb_fwd_warp_try(x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, fin, max_nodes,
                            plan_meta, st);
@@ -487,6 +508,12 @@ extern "C" int feta_cheb_bwd(const float* dout, const float* x, const int32_t* r
                        (sk % 4 == 0) && (sg % 4 == 0) && (!dx || (uintptr_t)dx % 16 == 0) &&
                        (!dtheta || (uintptr_t)dtheta % 16 == 0);
   const bool fusable = fin == fout && block_diagonal && aligned;
+  if (fusable && (dx != nullptr || dtheta != nullptr)) {   // large graphs: dx and dTheta in ONE launch
+    rc = cheb_bwd_dense_try(dout, x, rowptr, colidx, vals, rowptr_t, colidx_t, vals_t, graph_ptr, theta, sk, sg, dx,
+                            dtheta, R, G, K, fin, max_nodes, plan_meta, st);
+    if (rc < 0) return rc;
+    if (rc == 0) return FETA_OK;
+  }
   if (dx != nullptr) {
     FusedCfg cfg = fused_config(fin, max_nodes, 2, false);
     bool done = false;

@@ -62,6 +62,25 @@ __global__ void __launch_bounds__(kColThreads) collate_edges_kernel(
   }
 }
 
+// static-shape variant: edge_indices is [2, e_cap]; columns >= E hold the (-1, -1) padding the plan builder ignores
+__global__ void __launch_bounds__(kColThreads) collate_edges_static_kernel(
+    const int64_t* __restrict__ graph_ids, const int64_t* __restrict__ ds_edge_ptr,
+    const int64_t* __restrict__ ds_edge_index, int64_t ds_E, const int64_t* __restrict__ out_node_ptr,
+    const int64_t* __restrict__ out_edge_ptr, int64_t* __restrict__ edge_indices, int B, int64_t E, int64_t e_cap) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e_cap; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = -1, t = -1;
+    if (e < E) {
+      const int b = owner_of(out_edge_ptr, B, e);
+      const int64_t src = ds_edge_ptr[graph_ids[b]] + (e - out_edge_ptr[b]);
+      const int64_t off = out_node_ptr[b];
+      s = ds_edge_index[src] + off;
+      t = ds_edge_index[ds_E + src] + off;
+    }
+    edge_indices[e] = s;
+    edge_indices[e_cap + e] = t;
+  }
+}
+
 __global__ void __launch_bounds__(kColThreads) collate_pad_rows_kernel(const int64_t* __restrict__ graph_ids,
                                                                       const int64_t* __restrict__ ds_node_ptr,
                                                                       const float* __restrict__ src,
@@ -121,6 +140,19 @@ extern "C" int feta_collate_indices(const int64_t* graph_ids, const int64_t* ds_
                                                               out_node_ptr, out_edge_ptr, edge_indices, B, E);
     FETA_LAUNCH_CHECK();
   }
+  return FETA_OK;
+}
+
+extern "C" int feta_collate_edges_static(const int64_t* graph_ids, const int64_t* ds_edge_ptr,
+                                         const int64_t* ds_edge_index, int64_t ds_E, const int64_t* out_node_ptr,
+                                         const int64_t* out_edge_ptr, int64_t* edge_indices, int B, int64_t E,
+                                         int64_t e_cap, void* stream_) {
+  FETA_REQUIRE(B >= 1 && E >= 0 && e_cap >= E && e_cap >= 1, "collate_edges_static: bad sizes (E must fit e_cap)");
+  FETA_REQUIRE(graph_ids && ds_edge_ptr && ds_edge_index && out_node_ptr && out_edge_ptr && edge_indices,
+               "collate_edges_static: NULL pointer");
+  collate_edges_static_kernel<<<col_grid(e_cap), kColThreads, 0, (cudaStream_t)stream_>>>(
+      graph_ids, ds_edge_ptr, ds_edge_index, ds_E, out_node_ptr, out_edge_ptr, edge_indices, B, E, e_cap);
+  FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
 

@@ -164,13 +164,22 @@ class DeviceBatchBuilder(object):
         self.degree = torch.from_numpy(store.degree).to(d) if store.has_degree else None
         self.y = torch.from_numpy(store.y).to(d)
 
-    def build(self, ids):
+    def build(self, ids, static=None):
+        """``static=(nmax_cap, e_cap)``: the static-shape tuple of ``collate_host(..., static=...)`` (node axis
+        padded to ``nmax_cap``, ``edge_indices [2, e_cap]`` padded with (-1, -1), node-level labels
+        ``[B, nmax_cap]`` with -100 in padded slots) so the batch can feed ``engine.GraphedTrainStep``."""
         lib = _lib.load()
         st = self.store
         ids = np.asarray(ids, dtype=np.int64)
         B = len(ids)
         lens, elens = st.sizes(ids)
         nmax, N, E = int(lens.max()), int(lens.sum()), int(elens.sum())
+        e_cols = E
+        if static is not None:
+            if nmax > static[0] or E > static[1]:
+                raise ValueError("batch exceeds the static capacity: nmax %d > %d or E %d > %d"
+                                 % (nmax, static[0], E, static[1]))
+            nmax, e_cols = int(static[0]), int(static[1])
         host = np.concatenate([ids, np.concatenate([[0], np.cumsum(lens)]),
                                np.concatenate([[0], np.cumsum(elens)])]).astype(np.int64)
         dev = torch.from_numpy(host).pin_memory().to(self.device, non_blocking=True)
@@ -178,14 +187,20 @@ class DeviceBatchBuilder(object):
         d = self.device
         stream = torch.cuda.current_stream().cuda_stream
         mask = torch.empty((B, nmax), dtype=torch.bool, device=d)
-        edge_indices = torch.empty((2, E), dtype=torch.int64, device=d)
+        edge_indices = torch.empty((2, e_cols), dtype=torch.int64, device=d)
         batch_indices = torch.empty((N,), dtype=torch.int64, device=d)
         feature_indices = torch.empty((N, 2), dtype=torch.int64, device=d)
         check(lib.feta_collate_indices(gid.data_ptr(), self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(),
                                        self.edge_index.data_ptr(), self.edge_index.shape[1], onp.data_ptr(),
-                                       oep.data_ptr(), mask.data_ptr(), edge_indices.data_ptr(),
-                                       batch_indices.data_ptr(), feature_indices.data_ptr(), B, nmax, N, E,
-                                       stream), "feta_collate_indices")
+                                       oep.data_ptr(), mask.data_ptr(),
+                                       edge_indices.data_ptr() if static is None else 0,
+                                       batch_indices.data_ptr(), feature_indices.data_ptr(), B, nmax, N,
+                                       E if static is None else 0, stream), "feta_collate_indices")
+        if static is not None:
+            check(lib.feta_collate_edges_static(gid.data_ptr(), self.edge_ptr.data_ptr(), self.edge_index.data_ptr(),
+                                                self.edge_index.shape[1], onp.data_ptr(), oep.data_ptr(),
+                                                edge_indices.data_ptr(), B, E, e_cols, stream),
+                  "feta_collate_edges_static")
 
         def pad_rows(src, C):
             dst = torch.empty((B, nmax, C), dtype=torch.float32, device=d)
@@ -205,6 +220,10 @@ class DeviceBatchBuilder(object):
         if st.kind == 'sbm':
             rows, _ = _ranges(st.node_ptr[ids], lens)
             labels = self.y[torch.from_numpy(rows).to(d)]
+            if static is not None:
+                lab = torch.full((B, nmax), -100, dtype=torch.int64, device=d)
+                lab[feature_indices[:, 0], feature_indices[:, 1]] = labels
+                labels = lab
         else:
             labels = self.y[gid]
         return (padded_x, mask, pos_enc, lap, degree, labels, edge_indices, batch_indices, feature_indices)

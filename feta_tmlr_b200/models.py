@@ -230,6 +230,12 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         return ctx
 
     def forward_static(self, src, pe, edge_index, degree, masks):
+        if any(getattr(mod, 'batch_norm', False) for mod in self.layers):
+            # the reference's BatchNorm1d runs over rows padded to the BATCH maximum (layers' flatten of
+            # [Nmax, B, d]); the static layout pads to a dataset-wide cap, which would change the statistics
+            raise NotImplementedError("forward_static / GraphedTrainStep: batch_norm=True is not supported in the "
+                                      "static-shape layout (statistics over padded rows would differ from the "
+                                      "reference); use forward() or LayerNorm")
         output = src
         nmax, B, d = src.shape
         H = self.num_heads

@@ -4,8 +4,8 @@ Same class names, constructor arguments, ``apply_to`` behaviour and pickle cache
 (``<savepath>.<split>`` holding a list of dense per-graph tensors, :35-49) as the reference, so a
 cache written by either side is readable by the other.  What changes is how the kernels are
 computed: the reference calls ``scipy.sparse.linalg.expm`` / ``np.linalg.eig`` once per graph on
-the host (minutes on full ZINC / molhiv); here all graphs of a dataset are padded into one
-``[G, n, n]`` batch and decomposed with ONE batched symmetric eigendecomposition
+the host (minutes on full ZINC / molhiv); here graphs are grouped into size-sorted chunks, each padded into
+a ``[G, n, n]`` batch (<= 256 MB) and decomposed with one batched symmetric eigendecomposition
 (``torch.linalg.eigh``, on the GPU when one is present):
 
     L_sym = U diag(w) U^T   ->   expm(-beta L) = U diag(exp(-beta w)) U^T        (DiffusionEncoding)
@@ -62,13 +62,41 @@ def dense_laplacians(graphs, normalization, device='cpu', dtype=torch.float64):
     return L, ns
 
 
-def _spectral_map(graphs, normalization, fn, device):
-    """U f(w) U^T for every graph with one batched eigh (symmetric normalisations)."""
-    L, ns = dense_laplacians(graphs, normalization, device=device)
-    # padded rows/cols are zero: they add zero eigenvalues whose eigenvectors live in the padding
-    w, U = torch.linalg.eigh(L)
-    M = (U * fn(w).unsqueeze(1)) @ U.transpose(1, 2)
-    return [M[i, :n, :n].to(torch.float32).cpu() for i, n in enumerate(ns)]
+CHUNK_BYTES = 256 << 20      # padded fp64 batch per eigh call (L, U and the product are each this big)
+
+
+def _size_sorted_chunks(graphs):
+    """Index chunks of similar-size graphs, each padded batch <= CHUNK_BYTES (the whole dataset in one padded
+    batch would be ~16 GB per copy for molhiv: 41k graphs padded to 222 nodes)."""
+    ns = np.array([_num_nodes(g) for g in graphs], dtype=np.int64)
+    order = np.argsort(ns, kind='stable')
+    i = 0
+    while i < len(order):
+        j = i + 1
+        while j < len(order) and (j + 1 - i) * int(ns[order[j]]) ** 2 * 8 <= CHUNK_BYTES:
+            j += 1
+        yield order[i:j]
+        i = j
+
+
+def _is_symmetric(L):
+    return (L == L.transpose(1, 2)).flatten(1).all(dim=1)
+
+
+def _spectral_map(graphs, normalization, fn, device, fallback):
+    """U f(w) U^T per graph, one batched eigh per size-sorted chunk (symmetric normalisations).  A graph whose
+    Laplacian is NOT symmetric (directed edge list) takes ``fallback(L)`` -- the general dense formula the
+    reference's scipy ``expm`` / matrix power computes -- instead of a silently wrong ``eigh``."""
+    out = [None] * len(graphs)
+    for idx in _size_sorted_chunks(graphs):
+        L, ns = dense_laplacians([graphs[i] for i in idx], normalization, device=device)
+        sym = _is_symmetric(L).cpu().numpy()
+        # padded rows/cols are zero: they add zero eigenvalues whose eigenvectors live in the padding
+        w, U = torch.linalg.eigh(L)
+        M = (U * fn(w).unsqueeze(1)) @ U.transpose(1, 2)
+        for j, (i, n) in enumerate(zip(idx, ns)):
+            out[i] = (M[j, :n, :n] if sym[j] else fallback(L[j, :n, :n])).to(torch.float32).cpu()
+    return out
 
 
 class PositionEncoding(object):
@@ -131,7 +159,8 @@ class DiffusionEncoding(PositionEncoding):
                 L, ns = dense_laplacians([g], 'rw')
                 out.append(torch.matrix_exp(-self.beta * L[0]).to(torch.float32))
             return out
-        return _spectral_map(graphs, self.normalization, lambda w: torch.exp(-self.beta * w), self.device)
+        return _spectral_map(graphs, self.normalization, lambda w: torch.exp(-self.beta * w), self.device,
+                             fallback=lambda L: torch.matrix_exp(-self.beta * L))
 
 
 class PStepRWEncoding(PositionEncoding):
@@ -152,7 +181,9 @@ class PStepRWEncoding(PositionEncoding):
                 M = torch.eye(L.shape[1], dtype=L.dtype) - self.beta * L[0]
                 out.append(torch.linalg.matrix_power(M, self.p).to(torch.float32))
             return out
-        return _spectral_map(graphs, self.normalization, lambda w: (1.0 - self.beta * w) ** self.p, self.device)
+        return _spectral_map(graphs, self.normalization, lambda w: (1.0 - self.beta * w) ** self.p, self.device,
+                             fallback=lambda L: torch.linalg.matrix_power(
+                                 torch.eye(L.shape[0], dtype=L.dtype, device=L.device) - self.beta * L, self.p))
 
 
 class AdjEncoding(PositionEncoding):
@@ -198,19 +229,23 @@ class LapEncoding(PositionEncoding):
     def compute_all(self, graphs):
         if self.normalization == 'rw':
             raise NotImplementedError("LapEncoding with 'rw' normalisation (non-symmetric) is not implemented")
-        L, ns = dense_laplacians(graphs, self.normalization, device=self.device)
-        nmax = L.shape[1]
-        # push the padding's zero eigenvalues to the top so real eigenpairs come first, ascending
-        pad = (torch.arange(nmax, device=L.device).unsqueeze(0) >= torch.from_numpy(ns).to(L.device).unsqueeze(1))
-        L = L + torch.diag_embed(pad.to(L.dtype) * 1e6)
-        w, U = torch.linalg.eigh(L)
-        out = []
-        for i, n in enumerate(ns):
-            pe = U[i, :n, 1:self.pos_enc_dim + 1]
-            pe = pe[:, :max(0, min(self.pos_enc_dim, n - 1))]
-            full = torch.zeros((n, self.pos_enc_dim), dtype=torch.float32)
-            full[:, :pe.shape[1]] = pe.to(torch.float32).cpu()
-            out.append(full)
+        out = [None] * len(graphs)
+        for idx in _size_sorted_chunks(graphs):
+            L, ns = dense_laplacians([graphs[i] for i in idx], self.normalization, device=self.device)
+            if not bool(_is_symmetric(L).all()):
+                raise NotImplementedError("LapEncoding: a graph's Laplacian is not symmetric (directed edge list); "
+                                          "the batched symmetric eigendecomposition does not apply")
+            nmax = L.shape[1]
+            # push the padding's zero eigenvalues to the top so real eigenpairs come first, ascending
+            pad = (torch.arange(nmax, device=L.device).unsqueeze(0)
+                   >= torch.from_numpy(ns).to(L.device).unsqueeze(1))
+            w, U = torch.linalg.eigh(L + torch.diag_embed(pad.to(L.dtype) * 1e6))
+            for j, (i, n) in enumerate(zip(idx, ns)):
+                pe = U[j, :n, 1:self.pos_enc_dim + 1]
+                pe = pe[:, :max(0, min(self.pos_enc_dim, n - 1))]
+                full = torch.zeros((n, self.pos_enc_dim), dtype=torch.float32)
+                full[:, :pe.shape[1]] = pe.to(torch.float32).cpu()
+                out[i] = full
         return out
 
     def apply_to(self, dataset):

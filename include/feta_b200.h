@@ -325,6 +325,14 @@ int feta_collate_indices(const int64_t* graph_ids /* [B] */, const int64_t* ds_n
                          const int64_t* out_edge_ptr /* [B+1] */, uint8_t* mask, int64_t* edge_indices,
                          int64_t* batch_indices, int64_t* feature_indices, int B, int nmax,
                          int64_t N, int64_t E, void* stream);
+/* static-shape variant of the edge list (engine.GraphedTrainStep): edge_indices is [2, e_cap], columns >= E
+ * are written as (-1, -1), which feta_graph_plan_build ignores; everything else as feta_collate_indices with
+ * nmax = the static node capacity. */
+int feta_collate_edges_static(const int64_t* graph_ids, const int64_t* ds_edge_ptr,
+                              const int64_t* ds_edge_index /* [2, E_ds] */, int64_t ds_num_edges,
+                              const int64_t* out_node_ptr, const int64_t* out_edge_ptr,
+                              int64_t* edge_indices /* [2, e_cap] */, int B, int64_t E, int64_t e_cap,
+                              void* stream);
 /* padded feature / PE / degree fill for the same batch:
  *   dst[b, n, :] = src[ds_node_ptr[graph_ids[b]] + n, :]  (n < len_b), 0 elsewhere;
  *   pe_dst[b, i, j] = pe_src[ds_pe_ptr[gid] + i*len + j]   (i, j < len_b), 0 elsewhere. */

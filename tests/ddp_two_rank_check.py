@@ -1,0 +1,96 @@
+"""Two NCCL ranks of ``engine.GraphedTrainStep`` (flat-bucket all-reduce inside the captured step, FlatAdam with
+grad_scale = 1/world) must land on the same parameters as ONE process stepping on the concatenated mini-batch.
+
+Launched by tests/test_gpu_ddp.py:  python -m torch.distributed.run --nproc-per-node 2 tests/ddp_two_rank_check.py
+Prints ``DDP2 OK max_rel=<x>`` on rank 0.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import feta_tmlr_b200.models as fmodels
+    from feta_tmlr_b200 import data as fdata, ddp, engine, synthetic
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", device_id=dev)
+    name, B, steps = os.environ.get("DDP2_CONFIG", "ZINC"), 8, 3
+    cfg = synthetic.CONFIGS[name]
+    graphs = synthetic.make_dataset(name, steps * world * B, seed=31)
+    store = fdata.GraphStore(graphs, kind=cfg['kind'], n_tags=cfg['n_tags'])
+    caps = engine.static_caps(store, B)
+    node = cfg['head'] == 'node'
+
+    def lf_static(out, y):
+        if node:
+            return torch.nn.functional.cross_entropy(out.reshape(-1, out.shape[-1]), y.reshape(-1), ignore_index=-100)
+        return torch.nn.functional.l1_loss(out, y)
+
+    torch.manual_seed(0)
+    model = synthetic.build_model(name, fmodels, layers=2).to(dev)
+    ddp.broadcast_parameters(model)
+    ref = None
+    if rank == 0:
+        import copy
+        ref = copy.deepcopy(model)
+    # every rank: its shard of each global batch;  engine warm-up runs on step 0's shard (3 un-captured steps),
+    # so the single-process reference below takes the same 3 extra steps on global batch 0
+    def ids(step, r):
+        base = step * world * B
+        return np.arange(base + r * B, base + (r + 1) * B)
+    shard = [fdata.collate_host(store, ids(s, rank), static=caps) for s in range(steps)]
+    eng = engine.GraphedTrainStep(model, lf_static, tuple(None if t is None else t.to(dev) for t in shard[0][:7]),
+                                  lr=1e-3, device=dev, warmup=3)
+    for s in range(steps):
+        eng.step(shard[s])
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+        seq = [0, 0, 0] + list(range(steps))
+        for s in seq:
+            gids = np.concatenate([ids(s, r) for r in range(world)])
+            if node:
+                # per-rank mean over its own real nodes, then the mean over ranks (what DDP computes)
+                opt.zero_grad()
+                for r in range(world):
+                    b = tuple(None if t is None else t.to(dev) for t in fdata.collate_host(store, ids(s, r))[:9])
+                    out = ref(b[0], b[6], b[7], b[8], b[1], b[2], b[3], b[4])[0]
+                    (torch.nn.functional.cross_entropy(out, b[5].long()) / world).backward()
+                opt.step()
+            else:
+                b = tuple(None if t is None else t.to(dev) for t in fdata.collate_host(store, gids)[:9])
+                opt.zero_grad()
+                out = ref(b[0], b[6], b[7], b[8], b[1], b[2], b[3], b[4])[0]
+                torch.nn.functional.l1_loss(out, b[5]).backward()
+                opt.step()
+        worst = 0.0
+        for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            err = float((p - q).abs().max() / q.abs().max().clamp_min(1e-12))
+            worst = max(worst, err)
+        ok = worst < 2e-4
+        print("DDP2 %s max_rel=%.3e" % ("OK" if ok else "FAIL", worst), flush=True)
+    # replicas identical across ranks
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    other = flat.clone()
+    dist.broadcast(other, src=0)
+    same = bool(torch.equal(flat, other))
+    if not same:
+        print("DDP2 FAIL rank %d parameters differ from rank 0" % rank, flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    del eng
+    sys.stdout.flush()
+    os._exit(0 if (ok and same) else 1)
+
+
+if __name__ == "__main__":
+    main()

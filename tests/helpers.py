@@ -119,19 +119,26 @@ def grad_summary(g):
                 absmax=g.abs().max())
 
 
-def check_grad(got, want, tol, name=""):
-    """``want``: a tensor or a ``grad_summary`` dict (fixture side).  Relative to the largest entry."""
+def grad_scale(wants):
+    """Largest gradient entry over a fixture's whole gradient dict (tensors or summaries)."""
+    return max([float(w['absmax'] if isinstance(w, dict) else w.abs().max()) for w in wants.values()] + [0.0])
+
+
+def check_grad(got, want, tol, name="", floor=0.0):
+    """``want``: a tensor or a ``grad_summary`` dict (fixture side).  Error relative to the largest entry of
+    THIS gradient, or to ``floor`` when the whole gradient is smaller than that (a gradient that is analytically
+    zero -- e.g. a bias followed by BatchNorm -- is rounding noise on both sides)."""
     got = got.detach().double().cpu()
     if isinstance(want, dict):
         s = grad_summary(got)
         for k in ("rowsum", "colsum", "rows", "cols"):
             ref = want[k].double()
-            scale = max(float(ref.abs().max()), float(want['absmax']), 1e-30)     # a summary can be all ~0
+            scale = max(float(ref.abs().max()), float(want['absmax']), floor, 1e-30)     # a summary can be all ~0
             err = float((s[k].double() - ref).abs().max()) / scale
             assert err < tol, (name, k, err)
         return
     want = want.double()
-    err = float((got - want).abs().max() / want.abs().max().clamp_min(1e-30))
+    err = float((got - want).abs().max()) / max(float(want.abs().max()), floor, 1e-30)
     assert err < tol, (name, err)
 
 

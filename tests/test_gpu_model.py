@@ -172,3 +172,49 @@ def test_graphed_train_step_matches_eager(cuda, double_buffer):
     assert np.allclose(losses, losses_ref[4:] if False else losses_ref[-len(losses):], rtol=2e-4), (losses, losses_ref)
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         assert rel_err(p2, p1) < 1e-3, k
+
+
+@pytest.mark.parametrize("name,B", [("ZINC", 6), ("PATTERN", 2)])
+def test_tile_edges_per_head_matches_oracle_on_tiled_edges(cuda, name, B):
+    """``tile_edges_per_head=True`` (opt-in fix of SURVEY F4: every head is filtered over the real graph) ==
+    the reference op sequence fed an edge_index tiled over the H stacked copies; packed and static contexts."""
+    from feta_tmlr_b200 import data as fdata, engine
+    cfg, graphs, store, batch = make_batch(name, B, seed=21)
+    o, m = _models(cuda, name, layers=2)
+    m.encoder.tile_edges_per_head = True
+    px, mask, pe, lap, deg, labels, ei, bi, fi = batch[:9]
+    H, N = cfg['heads'], fi.shape[0]
+    ei_tiled = torch.cat([ei + h * N for h in range(H)], dim=1)
+    oo = o(px, ei_tiled, bi, fi, mask, pe, lap, deg)[0]
+    g = to_dev(batch[:9], cuda)
+    go = m(g[0], g[6], g[7], g[8], g[1], g[2], g[3], g[4])[0]
+    assert rel_err(go, oo) < TOL
+    _loss(name, oo, labels).backward()
+    _loss(name, go, g[5]).backward()
+    torch.cuda.synchronize()
+    po, pg = dict(o.named_parameters()), dict(m.named_parameters())
+    gmax = max(float(p.grad.abs().max()) for p in po.values() if p.grad is not None)
+    for k in po:
+        if po[k].grad is not None and float(po[k].grad.abs().max()) > 1e-3 * gmax:
+            assert rel_err(pg[k].grad, po[k].grad) < TOL, k
+    # the un-tiled default must differ (otherwise this test shows nothing)
+    m.encoder.tile_edges_per_head = False
+    assert rel_err(m(g[0], g[6], g[7], g[8], g[1], g[2], g[3], g[4])[0], oo) > 10 * TOL
+    # static context with the flag
+    m.encoder.tile_edges_per_head = True
+    nmax_cap, e_cap = engine.static_caps(store, B)
+    sb = to_dev(fdata.collate_host(store, np.arange(B), static=(nmax_cap + 2, e_cap))[:9], cuda)
+    so = m.forward_static(sb[0], sb[6], sb[1], sb[2], sb[3], sb[4])
+    if cfg['head'] == 'node':
+        so = so[~sb[1]]
+    assert rel_err(so.reshape(oo.shape), oo) < TOL
+
+
+def test_forward_static_rejects_batch_norm(cuda):
+    import feta_tmlr_b200.models as fmodels
+    from feta_tmlr_b200 import data as fdata, engine
+    cfg, graphs, store, batch = make_batch("ZINC", 4, seed=22)
+    m = synthetic.build_model("ZINC", fmodels, layers=2, batch_norm=True).to(cuda)
+    sb = to_dev(fdata.collate_host(store, np.arange(4), static=engine.static_caps(store, 4))[:9], cuda)
+    with pytest.raises(NotImplementedError):
+        m.forward_static(sb[0], sb[6], sb[1], sb[2], sb[3], sb[4])

@@ -142,3 +142,48 @@ def test_device_batch_builder_bit_exact(cuda, name):
         assert (a is None) == (b is None)
         if a is not None:
             assert a.dtype == b.dtype and torch.equal(a.cpu(), b), name
+
+
+@pytest.mark.parametrize("name", ["ZINC", "PATTERN", "CLUSTER", "MOLHIV"])
+def test_device_batch_builder_static_mode(cuda, name):
+    """N2 for the CUDA-graph engine: ``build(ids, static=caps)`` == ``collate_host(..., static=caps)`` bit for bit,
+    and a batch that does not fit the capacities raises."""
+    from feta_tmlr_b200 import data as fdata, engine
+    ids = np.array([7, 2, 11, 0, 5, 9])
+    cfg, graphs, store, _ = make_batch(name, 12, seed=3, ids=ids)
+    caps = engine.static_caps(store, len(ids))
+    caps = (caps[0] + 2, caps[1])
+    host = fdata.collate_host(store, ids, static=caps)
+    dev = fdata.DeviceBatchBuilder(store, cuda).build(ids, static=caps)
+    torch.cuda.synchronize()
+    for k, (a, b) in enumerate(zip(dev, host)):
+        assert (a is None) == (b is None), k
+        if a is not None:
+            assert a.dtype == b.dtype and tuple(a.shape) == tuple(b.shape) and torch.equal(a.cpu(), b), (name, k)
+    with pytest.raises(ValueError):
+        fdata.DeviceBatchBuilder(store, cuda).build(ids, static=(caps[0], 8))
+
+
+def test_graphed_step_fed_by_device_batch_builder(cuda):
+    """The GPU batch builder feeds the whole-step CUDA graph: same losses as host-collated static batches."""
+    import copy
+    import feta_tmlr_b200.models as fmodels
+    from feta_tmlr_b200 import data as fdata, engine, synthetic
+    name, B = "ZINC", 8
+    cfg = synthetic.CONFIGS[name]
+    graphs = synthetic.make_dataset(name, 3 * B, seed=9)
+    store = fdata.GraphStore(graphs, kind=cfg['kind'], n_tags=cfg['n_tags'])
+    caps = engine.static_caps(store, B)
+    idsets = [np.arange(i * B, (i + 1) * B) for i in range(3)]
+    host = [fdata.collate_host(store, ids, static=caps) for ids in idsets]
+    torch.manual_seed(0)
+    m1 = synthetic.build_model(name, fmodels, layers=2).to(cuda)
+    m2 = copy.deepcopy(m1)
+    lf = torch.nn.functional.l1_loss
+    e1 = engine.GraphedTrainStep(m1, lf, host[0], lr=1e-3, device=cuda)
+    builder = fdata.DeviceBatchBuilder(store, cuda)
+    e2 = engine.GraphedTrainStep(m2, lf, builder.build(idsets[0], static=caps), lr=1e-3, device=cuda)
+    for i in range(3):
+        l1 = float(e1.step(host[i]))
+        l2 = float(e2.step(builder.build(idsets[i], static=caps)))
+        assert abs(l1 - l2) <= 1e-6 * max(1.0, abs(l1)), (i, l1, l2)

@@ -3,13 +3,15 @@ tests/golden/make_golden_from_reference.py): the CUDA path through the C ABI, de
 the unmodified ``/root/reference/transformer/{ChebNetDynamic,models,data}.py`` -- no oracle code in the loop.
 
 Tolerances (north_star): integer work bit-exact; fp32 vs the fp64 reference run 1e-4 relative to the largest
-entry, forward AND gradients.
+entry, forward AND gradients -- per parameter; a parameter whose whole gradient is more than 1000x smaller than the
+model's largest gradient (analytically-zero gradients such as a bias in front of BatchNorm) is judged against that
+floor instead of against its own rounding noise.
 """
 import numpy as np
 import pytest
 import torch
 
-from helpers import check_grad, det_init, graphs_from_fixture, load_fixture, rel_err, to_dev
+from helpers import check_grad, grad_scale, det_init, graphs_from_fixture, load_fixture, rel_err, to_dev
 from feta_tmlr_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
@@ -174,10 +176,11 @@ def test_model_matches_reference_run(cuda, tag):
     assert abs(float(loss) - float(fx['loss'])) < TOL * max(1.0, abs(float(fx['loss'])))
     got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
     worst = ("", 0.0)
+    floor = 1e-3 * grad_scale(fx['grads'])      # gradients 1000x below the largest one: absolute, not relative
     for k, want in fx['grads'].items():
         assert k in got, k
         try:
-            check_grad(got[k], want, TOL, k)
+            check_grad(got[k], want, TOL, k, floor=floor)
         except AssertionError as e:
             worst = max(worst, (k, e.args[0][-1]), key=lambda t: t[1])
     assert worst[1] == 0.0, worst

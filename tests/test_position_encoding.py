@@ -75,3 +75,48 @@ def test_synthetic_diffusion_pe_is_the_same_kernel():
     a = synthetic.diffusion_pe(g['edge_index'], g['x'].shape[0], 1.0)
     b = pe.DiffusionEncoding(None, 1.0, normalization='sym', device='cpu').compute_all([g])[0]
     assert np.allclose(a, b.numpy(), atol=2e-6)
+
+
+def test_directed_graph_takes_the_general_formula():
+    """A non-symmetric Laplacian must not go through eigh (which reads one triangle)."""
+    g = _graphs(1)[0]
+    g = dict(g)
+    g['edge_index'] = np.concatenate([g['edge_index'], np.array([[0], [g['x'].shape[0] - 1]])], axis=1)   # one-way edge
+    out = pe.DiffusionEncoding(None, beta=1.0, normalization='sym', device='cpu').compute_all([g])[0]
+    ref = od.diffusion_pe(torch.from_numpy(g['edge_index']), g['x'].shape[0], 1.0, 'sym')
+    assert torch.allclose(out, ref.float(), atol=2e-6)
+    with pytest.raises(NotImplementedError):
+        pe.LapEncoding(4, normalization='sym', device='cpu').compute_all([g])
+
+
+def test_chunked_batches_keep_dataset_order(monkeypatch):
+    gs = _graphs(9, shape='PATTERN')
+    whole = pe.DiffusionEncoding(None, beta=1.0, normalization='sym', device='cpu').compute_all(gs)
+    monkeypatch.setattr(pe, 'CHUNK_BYTES', 3 * 190 * 190 * 8)           # forces several chunks
+    parts = pe.DiffusionEncoding(None, beta=1.0, normalization='sym', device='cpu').compute_all(gs)
+    for a, b, g in zip(whole, parts, gs):
+        assert a.shape == (g['x'].shape[0],) * 2 and torch.allclose(a, b, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_position_encodings_on_cuda(cuda):
+    """N3 on the device: batched eigh on the GPU vs the reference formulas (scipy expm / matrix power / eigvalsh)."""
+    gs = _graphs(10)
+    for norm in (None, 'sym'):
+        out = pe.DiffusionEncoding(None, beta=1.0, normalization=norm, device='cuda').compute_all(gs)
+        for g, m in zip(gs, out):
+            ref = od.diffusion_pe(torch.from_numpy(g['edge_index']), g['x'].shape[0], 1.0, norm)
+            assert m.device.type == 'cpu' and torch.allclose(m, ref.float(), atol=2e-6)
+    out = pe.PStepRWEncoding(None, p=3, beta=0.5, normalization='sym', device='cuda').compute_all(gs)
+    for g, m in zip(gs, out):
+        ref = od.pstep_pe(torch.from_numpy(g['edge_index']), g['x'].shape[0], 3, 0.5, 'sym')
+        assert torch.allclose(m, ref.float(), atol=1e-5)
+    gp = _graphs(4, shape='CLUSTER')
+    out = pe.LapEncoding(8, normalization='sym', device='cuda').compute_all(gp)
+    for g, m in zip(gp, out):
+        n = g['x'].shape[0]
+        L = od._dense_laplacian(torch.from_numpy(g['edge_index']), n, 'sym').astype(np.float64)
+        w = np.sort(np.linalg.eigvalsh(L))
+        for c in range(8):
+            v = m[:, c].double().numpy()
+            assert abs(np.linalg.norm(v) - 1.0) < 1e-5 and np.allclose(L @ v, w[c + 1] * v, atol=1e-4)
