@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--sweep-only", action="store_true", help="run only the HBM-sized Chebyshev sweep")
     ap.add_argument("--sweep-f", type=int, default=0, help="feature width for --sweep-only (default: config's dh)")
     ap.add_argument("--sweep-rows", type=int, default=3_000_000)
+    ap.add_argument("--repeats", type=int, default=5, help="timed legs of --steps steps each; the median is reported")
+    ap.add_argument("--no-extra", action="store_true", help="skip the PATTERN-shape leg (extra.pattern)")
+    ap.add_argument("--no-builder", action="store_true", help="skip the GPU-batch-builder end-to-end leg")
     return ap.parse_args()
 
 
@@ -199,14 +202,27 @@ def cheb_algorithmic_bytes(R, F, nnz, G, K):
     return 4 * R * F + 4 * R * F + 8 * nnz + 4 * (R + 1) + 4 * G * K * F * F + 4 * (G + 1) + 4 * F
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed ncu --set full captures
-# (profiles/r1_cheb_fwd_ncu.md capture v6: F=16, 3.0M rows; profiles/r1_attention_ncu.md: ZINC attention fwd)
-NCU_TRAFFIC = {("cheb_sweep", 16, 3_000_000): 747_573_504 + 175_733_248,
-               ("attn_fwd", "ZINC"): 2_729_984}
+def cheb_bwd_bytes(R, F, nnz, G, K):
+    """DESIGN.md section 4, per backward kernel: dOut (or x + dOut) in, dx (or dTheta) out, CSR, Theta."""
+    return 8 * R * F + 8 * nnz + 4 * (R + 1) + 4 * G * K * F * F
 
 
-def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=3_000_000):
-    """The fused Chebyshev kernel on an HBM-sized (>> 126 MB L2) batch of molecule-shape graphs."""
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from a committed `ncu --set full` capture
+    (profiles/ncu_traffic.json: {key: {"bytes": ..., "capture": "<file>", "git": "<build the capture profiled>"}}).
+    A capture describes the build it was taken on, so the entry is returned with its provenance, never silently."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, "no profiles/ncu_traffic.json"
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(key)
+    if e is None:
+        return None, "no ncu capture for %s" % key
+    return int(e["bytes"]), "ncu --set full, %s (build %s)" % (e.get("capture"), e.get("git"))
+
+
+def make_sweep_inputs(dev, F, K, target_rows):
     from feta_tmlr_b200 import ops
     g = torch.Generator(device=dev).manual_seed(0)
     G = target_rows // 25
@@ -229,87 +245,120 @@ def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=3_000_000):
     x = torch.randn(R, F, device=dev, generator=g)
     theta = (torch.randn(G, K * F * F, device=dev, generator=g) * 0.1).reshape(G, K, F, F).permute(1, 0, 2, 3)
     bias = torch.zeros(F, device=dev)
-    for _ in range(3):
-        ops.cheb_filter(x, theta, bias, plan)
+    go = torch.randn(R, F, device=dev, generator=g)
+    return plan, x, theta, bias, go, R, G, nnz
+
+
+def _time_loop(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    iters = 10
     torch.cuda.synchronize()
     ev[0].record()
     for _ in range(iters):
-        ops.cheb_filter(x, theta, bias, plan)
+        fn()
     ev[1].record()
     torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1]) / iters
-    nbytes = cheb_algorithmic_bytes(R, F, nnz, G, K)
-    ach = nbytes / (ms * 1e-3) / 1e9
-    return {"kernel": "cheb_fwd_warp_kernel<%d,2>" % F, "workload": "molecule-shape, %d graphs, %d rows, %d nnz, "
-            "K=%d, F=%d (working set %.2f GB >> L2)" % (G, R, nnz, K, F, nbytes / 1e9), "bound": "hbm",
-            "achieved": round(ach, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(ach / hbm_gbs, 4),
-            "traffic": NCU_TRAFFIC.get(("cheb_sweep", F, target_rows)),
-            "ms_per_launch": round(ms, 4), "algorithmic_bytes": nbytes}
+    return ev[0].elapsed_time(ev[1]) / iters
 
 
-def main():
-    args = parse_args()
-    from feta_tmlr_b200 import synthetic
-    cfg = dict(synthetic.CONFIGS[args.config])
-    B = args.batch or cfg['batch']
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = ("%s-shape synthetic, batch %d/GPU, ChebConvDynamic K=4, H=%d, L=%d, d=%d, pos_enc=%s, "
-                "lap_dim=%d, LayerNorm, Adam" % (args.config, B, cfg['heads'], cfg['layers'], cfg['d_model'],
-                                                 cfg['pos_enc'], cfg['lap_dim']))
+def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=3_000_000, backward=True):
+    """The Chebyshev kernels on an HBM-sized (>> 126 MB L2) batch of molecule-shape graphs: forward, and the two
+    backward kernels timed separately (autograd asked for dx only / dTheta only)."""
+    from feta_tmlr_b200 import ops
+    plan, x, theta, bias, go, R, G, nnz = make_sweep_inputs(dev, F, K, target_rows)
+    wl = "molecule-shape, %d graphs (10..40 nodes), %d rows, %d nnz, K=%d, F=%d" % (G, R, nnz, K, F)
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        val, dt, cores = run_reference(args, cfg, B)
-        line = {"impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": workload, "where": "host CPU, %d threads" % cores},
-                "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "%d steps of one %d-graph batch each (oracle/, literal reference op "
-                                           "sequence incl. all-pairs GCN)" % (args.steps, B)},
-                "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
+    def entry(kernel, ms, nbytes, key):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        tr, why = ncu_traffic(key)
+        return {"kernel": kernel, "workload": wl + " (working set %.2f GB >> L2)" % (nbytes / 1e9), "bound": "hbm",
+                "achieved": round(ach, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(ach / hbm_gbs, 4),
+                "traffic": tr, "traffic_source": why, "ms_per_launch": round(ms, 4), "algorithmic_bytes": int(nbytes)}
+    out = {}
+    ms = _time_loop(lambda: ops.cheb_filter(x, theta, bias, plan))
+    out["fwd"] = entry("cheb_fwd_warp_kernel<%d,2>" % F, ms, cheb_algorithmic_bytes(R, F, nnz, G, K),
+                       "cheb_sweep_fwd_f%d_%d" % (F, target_rows))
+    if backward:
+        xr = x.detach().requires_grad_()
+        y = ops.cheb_filter(xr, theta, bias, plan)
+        ms = _time_loop(lambda: torch.autograd.grad(y, xr, go, retain_graph=True))
+        out["bwd_dx"] = entry("cheb_bwd_dx_fused_kernel<%d>" % F, ms, cheb_bwd_bytes(R, F, nnz, G, K),
+                              "cheb_sweep_dx_f%d_%d" % (F, target_rows))
+        del y, xr
+        tr_ = theta.detach().requires_grad_()
+        y = ops.cheb_filter(x, tr_, bias, plan)
+        ms = _time_loop(lambda: torch.autograd.grad(y, tr_, go, retain_graph=True))
+        out["bwd_dtheta"] = entry("cheb_bwd_dtheta_fused_kernel<%d>" % F, ms, cheb_bwd_bytes(R, F, nnz, G, K),
+                                  "cheb_sweep_dtheta_f%d_%d" % (F, target_rows))
+    return out
 
-    # ------------------------------------------------------------------ this repo's CUDA path
+
+def kernel_times(cfg, B, model, bq, dev, use_graph):
+    """This repo's hot kernels alone on one of the step's own batches, as CUDA-graph replays between two events
+    (events cannot bracket a kernel inside a replay of the step graph; an eager pass would time the CPU launch
+    gaps of such small kernels instead)."""
+    from feta_tmlr_b200 import ops
+    mask_b, pe_b = bq[1], bq[2]
+    nm, H_, d_ = mask_b.shape[1], cfg['heads'], cfg['d_model']
+    gq = torch.Generator(device=dev).manual_seed(1)
+    qkv_t = torch.randn(nm, B, 3 * d_, device=dev, generator=gq)
+    go_t = torch.randn(nm, B, H_, d_ // H_, device=dev, generator=gq)
+    sc = float(d_ // H_) ** -0.5
+    us = {}
+
+    def attn_f():
+        ops.diff_attention(qkv_t, pe_b, mask_b, H_, sc)
+
+    def attn_fb():
+        xq = qkv_t.detach().requires_grad_()
+        _, o_ = ops.diff_attention(xq, pe_b, mask_b, H_, sc)
+        torch.autograd.grad(o_, xq, go_t)
+    us["attn_fwd"] = time_graphed(attn_f, dev)
+    us["attn_bwd"] = time_graphed(attn_fb, dev) - us["attn_fwd"]
+    if use_graph:
+        ctx_t = model.encoder.static_context(bq[6], mask_b, nm)
+        Rt, Gt, dh_ = H_ * B * nm, H_ * B, d_ // H_
+    else:
+        ctx_t = model.encoder.batch_context(bq[6], bq[8], bq[7], mask_b, nm)
+        Rt, Gt, dh_ = H_ * bq[8].shape[0], H_ * B, d_ // H_
+    x_t = torch.randn(Rt, dh_, device=dev, generator=gq)
+    th_t = (torch.randn(Gt, 4 * dh_ * dh_, device=dev, generator=gq) * 0.1).reshape(Gt, 4, dh_, dh_).permute(1, 0, 2, 3)
+    bias_t = torch.zeros(dh_, device=dev)
+    go_c = torch.randn(Rt, dh_, device=dev, generator=gq)
+    us["cheb_fwd"] = time_graphed(lambda: ops.cheb_filter(x_t, th_t, bias_t, ctx_t.plan), dev)
+
+    def cheb_fb():
+        xr, tr = x_t.detach().requires_grad_(), th_t.detach().requires_grad_()
+        torch.autograd.grad(ops.cheb_filter(xr, tr, bias_t, ctx_t.plan), (xr, tr), go_c)
+    us["cheb_bwd"] = time_graphed(cheb_fb, dev) - us["cheb_fwd"]
+    return us, ctx_t.plan.meta_host()[0], Rt, nm
+
+
+def run_config(name, args, dev, rank, world, steps, warmup, repeats, with_e2e=True, with_kernels=True,
+               with_builder=False):
+    """One BASELINE config end to end: value (inputs resident in HBM), e2e (host buffers), kernel micro-times."""
     import torch.distributed as dist
     import feta_tmlr_b200.models as fmodels
-    from feta_tmlr_b200 import _lib, ddp, ops
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
-    hbm_gbs, peak_src = peaks()
-    if args.sweep_only:
-        dh = cfg['d_model'] // cfg['heads']
-        print(json.dumps(cheb_sweep(dev, hbm_gbs, F=args.sweep_f or dh, target_rows=args.sweep_rows)))
-        return 0
-
-    # rotating pool of distinct batches whose device-resident total exceeds the 126 MB L2
+    from feta_tmlr_b200 import _lib, ddp, synthetic
+    cfg = dict(synthetic.CONFIGS[name])
+    B = (args.batch if (args.batch and name == args.config) else cfg['batch'])
     use_graph = not args.eager
-    probe = make_pool(args.config, cfg, B, 1, seed=1000 + rank, static=use_graph)
+    probe = make_pool(name, cfg, B, 1, seed=1000 + rank, static=use_graph)
     per_batch = batch_nbytes(probe[0][:7])
     n_pool = args.pool or int(min(256, max(8, np.ceil(160e6 / per_batch))))
-    pool_host = make_pool(args.config, cfg, B, n_pool, seed=rank, static=use_graph)
+    pool_host = make_pool(name, cfg, B, n_pool, seed=rank, static=use_graph)
     pool_pinned = [tuple(None if t is None else t.pin_memory() for t in b) for b in pool_host]
     pool_dev = [tuple(None if t is None else t.to(dev) for t in b) for b in pool_host]
 
     torch.manual_seed(0)
-    model = synthetic.build_model(args.config, fmodels).to(dev)
+    model = synthetic.build_model(name, fmodels).to(dev)
     ddp.broadcast_parameters(model)
-    lf = loss_fn_for(args.config)
+    lf = loss_fn_for(name)
     if cfg['head'] == 'node':
-        lf = lambda out, y: torch.nn.functional.cross_entropy(out.reshape(-1, out.shape[-1]), y.reshape(-1),
-                                                              ignore_index=-100) if use_graph else \
-            torch.nn.functional.cross_entropy(out, y.long())
+        lf = (lambda out, y: torch.nn.functional.cross_entropy(out.reshape(-1, out.shape[-1]), y.reshape(-1),
+                                                               ignore_index=-100)) if use_graph else \
+            (lambda out, y: torch.nn.functional.cross_entropy(out, y.long()))
 
     def barrier():
         torch.cuda.synchronize()
@@ -317,6 +366,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    eng = None
     if use_graph:
         from feta_tmlr_b200 import engine
         eng = engine.GraphedTrainStep(model, lf, pool_dev[0], lr=1e-3, device=dev, double_buffer=True)
@@ -352,118 +402,227 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), _lib.launch_count() - n0
 
+    def repeated(fn, offset=0):
+        """`repeats` timed legs of exactly `steps` steps each (max over ranks per leg); the MEDIAN leg is reported."""
+        legs = []
+        for r in range(repeats):
+            ms, launches = timed(fn, steps, warmup if r == 0 else 1, offset=offset + r * (steps + 1))
+            legs.append((ms, launches))
+        legs.sort()
+        ms, launches = legs[len(legs) // 2]
+        per = [world * B * steps / (m * 1e-3) for m, _ in legs]
+        return ms, launches, {"repeats": repeats, "median": round(world * B * steps / (ms * 1e-3), 1),
+                              "min": round(min(per), 1), "max": round(max(per), 1)}
+
+    res = {"name": name, "B": B, "cfg": cfg, "n_pool": n_pool, "per_batch": per_batch, "bucket_bytes": bucket.nbytes(),
+           "use_graph": use_graph}
     # ---- leg 1: inputs resident in HBM
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
-    ms, launches = timed(lambda i: step(pool_dev[i % n_pool]), args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    ms, launches, spread = repeated(lambda i: step(pool_dev[i % n_pool]))
+    res["clocks"] = sampler.stop() if rank == 0 else None
     if use_graph:
-        launches = launches_per_step * args.steps        # kernels replayed from the captured graph
-    value = world * B * args.steps / (ms * 1e-3)
-
+        launches = launches_per_step * steps              # kernels replayed from the captured graph
+    res.update(ms=ms, launches=int(launches), value=world * B * steps / (ms * 1e-3), spread=spread)
     if args.quick:
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": round(value, 1), "ms_per_step": round(ms / args.steps, 4),
-                              "quick": True}), flush=True)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-            os._exit(0)
-        return 0
+        return res, eng
     # ---- leg 2: end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
-    d2h = [0]
+    d2h = [0.0]
+    if with_e2e:
+        def e2e_step(i):
+            hb = pool_pinned[i % n_pool]
+            if use_graph:                                     # H2D straight into the graph's static buffers; the copy
+                loss = eng.step(hb, prefetch=pool_pinned[(i + 1) % n_pool])   # of the NEXT batch overlaps this step
+            else:
+                loss = step(tuple(None if t is None else t.to(dev, non_blocking=True) for t in hb))
+            d2h[0] = float(loss.detach().cpu())              # device -> host read of the step's result
+        ms_e2e, _, spread_e2e = repeated(e2e_step, offset=7)
+        res["e2e"] = {"value": round(world * B * steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
+                      "h2d_bytes_per_step": int(np.mean([batch_nbytes(b[:7]) for b in pool_pinned])),
+                      "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / steps, 4), "spread": spread_e2e}
+        res["last_loss"] = d2h[0]
+    if with_builder and use_graph:
+        # N2 end to end: the dataset lives in HBM, only the graph ids of the step cross PCIe, the GPU batch builder
+        # (csrc/collate.cu) writes the static batch and the graph replays on it
+        from feta_tmlr_b200 import data as fdata, engine
+        graphs = synthetic.make_dataset(name, B * min(n_pool, 16), seed=rank)
+        store = fdata.GraphStore(graphs, kind=cfg['kind'], n_tags=cfg['n_tags'])
+        caps = tuple(int(v) for v in (pool_host[0][0].shape[1], pool_host[0][6].shape[1]))
+        try:
+            builder = fdata.DeviceBatchBuilder(store, dev)
+            nb = min(n_pool, 16)
 
-    def e2e_step(i):
-        hb = pool_pinned[i % n_pool]
-        if use_graph:                                     # H2D straight into the graph's static buffers; the copy of
-            loss = eng.step(hb, prefetch=pool_pinned[(i + 1) % n_pool])   # the NEXT batch overlaps this step
-        else:
-            loss = step(tuple(None if t is None else t.to(dev, non_blocking=True) for t in hb))
-        d2h[0] = float(loss.detach().cpu())              # device -> host read of the step's result
-
-    ms_e2e, _ = timed(e2e_step, args.steps, args.warmup, offset=7)
-    e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
-    h2d_bytes = int(np.mean([batch_nbytes(b[:7]) for b in pool_pinned]))
+            def built_step(i):
+                ids = np.arange((i % nb) * B, (i % nb + 1) * B)
+                loss = eng.step(builder.build(ids, static=caps))
+                d2h[0] = float(loss.detach().cpu())
+            ms_b, _, spread_b = repeated(built_step, offset=3)
+            res["e2e_device_builder"] = {"value": round(world * B * steps / (ms_b * 1e-3), 1), "unit": UNIT,
+                                         "h2d_bytes_per_step": 8 * (3 * B + 2), "d2h_bytes_per_step": 4,
+                                         "ms_per_step": round(ms_b / steps, 4), "spread": spread_b}
+        except ValueError as e:                     # a batch beyond the static capacities of the host pool
+            res["e2e_device_builder"] = {"error": str(e)[:120]}
     if use_graph and eng.plan_guard_tripped():
         raise RuntimeError("device-side plan guard tripped: static capacities do not cover a batch")
-
-    # ---- leg 3 (rank 0, not part of value/e2e): this repo's hot kernels alone, on one of the step's own
-    # batches, as CUDA-graph replays between two events (events cannot bracket a kernel inside a replay of
-    # the step graph; an eager pass would time the CPU launch gaps of such small kernels instead)
-    kern_us = {}
-    if rank == 0:
-        bq = pool_dev[3 % n_pool]
-        mask_b, pe_b = bq[1], bq[2]
-        nm, H_, d_ = mask_b.shape[1], cfg['heads'], cfg['d_model']
-        gq = torch.Generator(device=dev).manual_seed(1)
-        qkv_t = torch.randn(nm, B, 3 * d_, device=dev, generator=gq)
-        go_t = torch.randn(nm, B, H_, d_ // H_, device=dev, generator=gq)
-        sc = float(d_ // H_) ** -0.5
-
-        def attn_f():
-            ops.diff_attention(qkv_t, pe_b, mask_b, H_, sc)
-
-        def attn_fb():
-            xq = qkv_t.detach().requires_grad_()
-            _, o_ = ops.diff_attention(xq, pe_b, mask_b, H_, sc)
-            torch.autograd.grad(o_, xq, go_t)
-        kern_us["attn_fwd"] = time_graphed(attn_f, dev)
-        kern_us["attn_bwd"] = time_graphed(attn_fb, dev) - kern_us["attn_fwd"]
-        if use_graph:
-            ctx_t = model.encoder.static_context(bq[6], mask_b, nm)
-            Rt, Gt, dh_ = H_ * B * nm, H_ * B, d_ // H_
-        else:
-            ctx_t = model.encoder.batch_context(bq[6], bq[8], bq[7], mask_b, nm)
-            Rt, Gt, dh_ = H_ * bq[8].shape[0], H_ * B, d_ // H_
-        x_t = torch.randn(Rt, dh_, device=dev, generator=gq)
-        th_t = (torch.randn(Gt, 4 * dh_ * dh_, device=dev, generator=gq) * 0.1).reshape(Gt, 4, dh_, dh_).permute(1, 0, 2, 3)
-        bias_t = torch.zeros(dh_, device=dev)
-        kern_us["cheb_fwd"] = time_graphed(lambda: ops.cheb_filter(x_t, th_t, bias_t, ctx_t.plan), dev)
-        cheb_nnz = ctx_t.plan.meta_host()[0]
-        cheb_rows = Rt
-
-    # ---- roofline of this repo's dominant kernel inside the step (+ the HBM-sized Chebyshev sweep)
-    line = None
-    if rank == 0:
-        H, L = cfg['heads'], cfg['layers']
-        dh = cfg['d_model'] // H
-        d = cfg['d_model']
+    if with_kernels and rank == 0:
+        us, nnz, rows, nm = kernel_times(cfg, B, model, pool_dev[3 % n_pool], dev, use_graph)
+        res.update(kern_us=us, cheb_nnz=nnz, cheb_rows=rows, nm=nm)
+        H, d = cfg['heads'], cfg['d_model']
         attn_rows = []
         for b in pool_dev[:min(n_pool, 8)]:
             lens = (~b[1]).sum(1).double()
             N, sumsq = int(lens.sum()), float((lens * lens).sum())
             # SURVEY.md section 8(d): q,k,v + pe + attn write + O
             attn_rows.append(3 * 4 * N * d + (4 * sumsq if b[2] is not None else 0) + 4 * H * sumsq + 4 * N * d)
-        attn_bytes = float(np.mean(attn_rows))
-        cheb_bytes = float(cheb_algorithmic_bytes(cheb_rows, dh, cheb_nnz, H * B, 4))
+        res["attn_bytes"] = float(np.mean(attn_rows))
+    return res, eng
 
-        def roof(kernel, nbytes, us_, launches_per_step_, note):
+
+def teardown(world, engines):
+    """Orderly exit under torchrun: drop the captured graphs (they hold the NCCL communicator's kernels), sync,
+    destroy the process group.  NCCL's teardown after a graph-captured collective has been seen to block on this
+    pool, so the destroy runs under a watchdog; if it does not return the process still exits 0 -- every rank has
+    already passed the final barrier and printed."""
+    import torch.distributed as dist
+    import threading
+    for e in engines:
+        if e is not None:
+            e.graphs = []
+            e.graph = None
+    del engines
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        done = threading.Event()
+
+        def _destroy():
+            try:
+                dist.destroy_process_group()
+            finally:
+                done.set()
+        th = threading.Thread(target=_destroy, daemon=True)
+        th.start()
+        if not done.wait(20.0):
+            sys.stderr.write("bench.py: destroy_process_group() did not return within 20 s; exiting\n")
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+
+def main():
+    args = parse_args()
+    from feta_tmlr_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS[args.config])
+    B = args.batch or cfg['batch']
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def workload_of(name, c, b):
+        return ("%s-shape synthetic, batch %d/GPU, ChebConvDynamic K=4, H=%d, L=%d, d=%d, pos_enc=%s, "
+                "lap_dim=%d, LayerNorm, Adam" % (name, b, c['heads'], c['layers'], c['d_model'], c['pos_enc'],
+                                                 c['lap_dim']))
+    workload = workload_of(args.config, cfg, B)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        val, dt, cores = run_reference(args, cfg, B)
+        line = {"impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": workload, "where": "host CPU, %d threads" % cores},
+                "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "%d steps of one %d-graph batch each (oracle/, literal reference op "
+                                           "sequence incl. all-pairs GCN; pinned against the reference run, "
+                                           "tests/test_reference_pin.py)" % (args.steps, B)},
+                "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this repo's CUDA path
+    import torch.distributed as dist
+    from feta_tmlr_b200 import _lib
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    hbm_gbs, peak_src = peaks()
+    if args.sweep_only:
+        dh = cfg['d_model'] // cfg['heads']
+        print(json.dumps(cheb_sweep(dev, hbm_gbs, F=args.sweep_f or dh, target_rows=args.sweep_rows)))
+        return 0
+
+    engines = []
+    res, eng = run_config(args.config, args, dev, rank, world, args.steps, args.warmup, args.repeats,
+                          with_builder=not args.no_builder)
+    engines.append(eng)
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": round(res["value"], 1),
+                              "ms_per_step": round(res["ms"] / args.steps, 4), "quick": True,
+                              "spread": res["spread"]}), flush=True)
+        teardown(world, engines)
+        return 0
+
+    # ---- the north-star scaling shape rides along: PATTERN, batch 64 per GPU (BASELINE configs[2])
+    extra = {}
+    if not args.no_extra and args.config != "PATTERN":
+        pres, peng = run_config("PATTERN", args, dev, rank, world, args.steps, args.warmup, max(3, args.repeats // 2 + 1),
+                                with_kernels=True)
+        engines.append(peng)
+        pc = pres["cfg"]
+        extra["pattern"] = {"workload": workload_of("PATTERN", pc, pres["B"]), "value": round(pres["value"], 1),
+                            "unit": UNIT, "ms_per_step": round(pres["ms"] / args.steps, 4), "spread": pres["spread"],
+                            "e2e": pres.get("e2e"), "gpu_launches": pres["launches"],
+                            "allreduce_bytes_per_step": pres["bucket_bytes"] if world > 1 else 0,
+                            "kernels_us": {k: round(v, 2) for k, v in pres.get("kern_us", {}).items()}}
+
+    line = None
+    if rank == 0:
+        H, L = cfg['heads'], cfg['layers']
+        dh = cfg['d_model'] // H
+        kern_us, nm = res["kern_us"], res["nm"]
+        attn_bytes = res["attn_bytes"]
+        cheb_bytes = float(cheb_algorithmic_bytes(res["cheb_rows"], dh, res["cheb_nnz"], H * B, 4))
+
+        def roof(kernel, nbytes, us_, launches_per_step_, note, key):
             ms_ = us_ * 1e-3
             ach = nbytes / (ms_ * 1e-3) / 1e9
+            tr, why = ncu_traffic(key)
             return {"kernel": kernel, "bound": "hbm", "achieved": round(ach, 2), "peak": hbm_gbs, "unit": "GB/s",
-                    "frac": round(ach / hbm_gbs, 5), "traffic": None, "peak_source": peak_src,
+                    "frac": round(ach / hbm_gbs, 5), "traffic": tr, "traffic_source": why, "peak_source": peak_src,
                     "algorithmic_bytes": int(nbytes), "us_per_launch": round(ms_ * 1e3, 2),
                     "launches_per_step": launches_per_step_, "note": note}
         small = ("%.2f MB per launch: L2-resident, instruction/latency bound at the BASELINE shape (SURVEY.md F5); "
-                 "timed as CUDA-graph replays of the kernel alone on one of the step's batches")
+                 "timed as CUDA-graph replays of the kernel ALONE on one of the step's batches (random q/k/v), not "
+                 "inside the step graph")
         attn_name = "attn_fwd_tiled_kernel<%d>" if (nm > 64 and dh in (8, 16)) else "attn_fwd_kernel<%d>"
-        roofline = roof(attn_name % dh, attn_bytes, kern_us.get("attn_fwd", float("nan")), L,
-                        "largest share of the step among this repo's kernels (profiles/); " + small % (attn_bytes / 1e6))
-        roofline["attn_bwd_us_per_launch"] = round(kern_us.get("attn_bwd", float("nan")), 2)
-        if args.config == "ZINC" and not args.batch:
-            roofline["traffic"] = NCU_TRAFFIC[("attn_fwd", "ZINC")]     # L2-resident: DRAM sees less than the algorithmic bytes
-        roofline_cheb = roof("cheb_fwd_%s_kernel<%d>" % ("warp" if nm <= 64 else "fused", dh), cheb_bytes,
-                             kern_us.get("cheb_fwd", float("nan")), 1,
+        roofline = roof(attn_name % dh, attn_bytes, kern_us["attn_fwd"], L,
+                        "largest share of the step among this repo's kernels (profiles/); " + small % (attn_bytes / 1e6),
+                        "attn_fwd_%s" % args.config)
+        roofline["attn_bwd_us_per_launch"] = round(kern_us["attn_bwd"], 2)
+        roofline_cheb = roof("cheb_fwd_%s_kernel<%d>" % ("warp" if nm <= 64 else "graph", dh), cheb_bytes,
+                             kern_us["cheb_fwd"], 1,
                              small % (cheb_bytes / 1e6) + "; roofline_sweep is the same kernel family on an HBM-sized "
-                             "batch; rows = %d (padded-domain static layout)" % cheb_rows)
+                             "batch; rows = %d (padded-domain static layout)" % res["cheb_rows"],
+                             "cheb_fwd_%s" % args.config)
+        roofline_cheb["cheb_bwd_us_per_launch"] = round(kern_us["cheb_bwd"], 2)
         sweep = None
         if not args.no_sweep:
-            try:
-                # always F = 16 (head dim of MUTAG / PATTERN / CLUSTER / molhiv; the ncu capture's shape)
-                sweep = cheb_sweep(dev, hbm_gbs, F=16, target_rows=args.sweep_rows)
-            except torch.OutOfMemoryError as e:       # bounded sweep; never take the box down
-                sweep = {"error": "OOM: %s" % str(e)[:80]}
+            sweep = {}
+            for F_ in (16, 8):                 # head dims of MUTAG/PATTERN/CLUSTER/molhiv (16) and ZINC (8)
+                try:
+                    sweep["F%d" % F_] = cheb_sweep(dev, hbm_gbs, F=F_, target_rows=args.sweep_rows)
+                except torch.OutOfMemoryError as e:       # bounded sweep; never take the box down
+                    sweep["F%d" % F_] = {"error": "OOM: %s" % str(e)[:80]}
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
             a2 = argparse.Namespace(**vars(args))
@@ -472,36 +631,32 @@ def main():
             cpu_baseline = {"value": round(cval, 2), "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": "4 timed steps (1 warm-up) of one %d-graph batch each, oracle/ on host cores"
                                       % B}
-        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        use_graph = res["use_graph"]
+        line = {"metric": METRIC, "value": round(res["value"], 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(res["ms"] / args.steps, 4), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "graphs_per_step": world * B,
                            "parallelism": "dp%d (graphs sharded, one flat-bucket NCCL all-reduce of %d B/step)"
-                                          % (world, bucket.nbytes()) if world > 1 else "single GPU",
+                                          % (world, res["bucket_bytes"]) if world > 1 else "single GPU",
                            "l2": "inputs rotate through a pool of %d distinct device-resident batches "
-                                 "(%.0f MB > 126 MB L2)" % (n_pool, n_pool * per_batch / 1e6),
+                                 "(%.0f MB > 126 MB L2)" % (res["n_pool"], res["n_pool"] * res["per_batch"] / 1e6),
                            "edges": "reference-faithful un-tiled edge_index (SURVEY.md F4)",
+                           "timing": "value = median of %d legs of exactly %d steps each (spread: min/max)"
+                                     % (args.repeats, args.steps),
                            "execution": ("whole training step (forward, loss, backward, gradient all-reduce, flat Adam) "
                                          "captured as ONE CUDA graph over static shapes (engine.GraphedTrainStep; two "
                                          "graphs over two input-buffer sets so the next batch's H2D copy overlaps), "
                                          "replayed per mini-batch") if use_graph else
                            "eager PyTorch autograd over C-ABI kernels, current stream"},
-                "clocks": clocks,
-                "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 4)},
-                "gpu_launches": int(launches), "roofline": roofline, "roofline_cheb_in_step": roofline_cheb,
-                "roofline_sweep": sweep,
-                "cpu_baseline": cpu_baseline, "last_loss": d2h[0]}
+                "clocks": res["clocks"], "spread": res["spread"],
+                "e2e": res.get("e2e"),
+                "gpu_launches": res["launches"], "roofline": roofline, "roofline_cheb_in_step": roofline_cheb,
+                "roofline_sweep": sweep, "cpu_baseline": cpu_baseline, "last_loss": res.get("last_loss"),
+                "extra": dict(extra, e2e_device_builder=res.get("e2e_device_builder"),
+                              kernels_us={k: round(v, 2) for k, v in kern_us.items()})}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-        # destroy_process_group() blocks forever once an NCCL collective has been captured into a CUDA
-        # graph (observed on this pool: scripts/ddp_graph_probe.py) -- leave without tearing NCCL down
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    teardown(world, engines)
     return 0
 
 

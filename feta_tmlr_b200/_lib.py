@@ -45,6 +45,10 @@ SIGNATURES = {
     "feta_add_layernorm_bwd_blocks": (c_int, [c_int64]),
     "feta_add_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "feta_add_layernorm_bwd_fold": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
+    "feta_add_batchnorm_blocks": (c_int, [c_int64]),
+    "feta_add_batchnorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float,
+                                       c_int64, c_int, _P]),
+    "feta_add_batchnorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "feta_adam_step": (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, c_float, _P, _P]),
     "feta_coeff_scalar": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, _P]),
     "feta_coeff_pool_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),

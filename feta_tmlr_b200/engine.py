@@ -70,7 +70,7 @@ class GraphedTrainStep(object):
     path of an end-to-end step (it is still paid for every step)."""
 
     def __init__(self, model, loss_fn, example_batch, lr=1e-3, device=None, warmup=3, double_buffer=False,
-                 flat_adam=True, weight_decay=0.0):
+                 flat_adam=True, weight_decay=0.0, comm_slices=3):
         self.model = model
         self.loss_fn = loss_fn
         dev = device or next(model.parameters()).device
@@ -93,10 +93,20 @@ class GraphedTrainStep(object):
                                          capturable=True)
         else:
             self.opt = torch.optim.Adam(model.parameters(), lr=lr, fused=True, capturable=True)
+        # Gradient exchange overlapped with the backward pass (world > 1, flat Adam): the flat bucket is cut into
+        # `comm_slices` contiguous slices in parameter order; gradients arrive last-layer-first, so the LAST slice
+        # completes early in the backward pass.  When every gradient of a slice has been produced (per-parameter
+        # post-accumulate hooks) the slice is copied into the flat buffer and all-reduced on a communication stream
+        # (forked from the main stream and from the weight-gradient side stream) while the rest of the backward
+        # pass runs; only the first slice's all-reduce (embedding + first layers) is exposed before Adam.
+        self.comm_slices = int(comm_slices) if (self.world > 1 and self.flat_adam) else 0
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.comm_slices else None
+        self._slices, self._hooks, self._works = [], [], []
         self.losses = [None] * self.nsets
         self.loss = None
         self.launches_per_step = 0
         self.cur = 0
+        self._in_body = False
         self.copy_stream = torch.cuda.Stream(device=dev) if double_buffer else None
         self._staged = None                       # (batch object, its H2D-complete event)
         self._done = [None] * self.nsets          # event after the last replay that read set s
@@ -109,6 +119,13 @@ class GraphedTrainStep(object):
                 self._body(0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if self.comm_slices:
+            self._setup_comm_slices()
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                            # one sliced step outside capture (NCCL warm-up)
+                self._body(0)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
         self.graphs = []
         for s in range(self.nsets):
             g = torch.cuda.CUDAGraph()
@@ -120,15 +137,69 @@ class GraphedTrainStep(object):
             self.graphs.append(g)
         self.graph = self.graphs[0]
 
+    # -- overlapped gradient exchange ---------------------------------------------------------------
+    def _setup_comm_slices(self):
+        """Cut the live parameters (those that received a gradient in the warm-up steps) into contiguous slices of
+        roughly equal bytes and hook them."""
+        live = [i for i, p in enumerate(self.params) if p.grad is not None]
+        total = sum(self.params[i].numel() for i in live)
+        bounds, acc, target = [], 0, total / self.comm_slices
+        for i in live:
+            acc += self.params[i].numel()
+            if acc >= target * (len(bounds) + 1) and len(bounds) < self.comm_slices - 1:
+                bounds.append(i + 1)
+        edges = [0] + bounds + [len(self.params)]
+        offs = [0]
+        for p in self.params:
+            offs.append(offs[-1] + p.numel())
+        self._slices = []
+        for a, b in zip(edges[:-1], edges[1:]):
+            idx = [i for i in live if a <= i < b]
+            if idx:
+                self._slices.append({"idx": idx, "lo": offs[a], "hi": offs[b], "left": 0})
+        for sl in self._slices:
+            for i in sl["idx"]:
+                self._hooks.append(self.params[i].register_post_accumulate_grad_hook(self._make_hook(sl)))
+
+    def _make_hook(self, sl):
+        def hook(_p):
+            sl["left"] -= 1
+            if sl["left"] == 0 and self._in_body:
+                self._reduce_slice(sl)
+        return hook
+
+    def _reduce_slice(self, sl):
+        dev = self.device
+        main, cs = torch.cuda.current_stream(dev), self.comm_stream
+        cs.wait_stream(main)
+        cs.wait_stream(ops._side_stream(dev))                      # weight gradients are produced there
+        with torch.cuda.stream(cs):
+            torch._foreach_copy_([self.bucket.views[i] for i in sl["idx"]], [self.params[i].grad for i in sl["idx"]])
+            self._works.append(torch.distributed.all_reduce(self.bucket.flat[sl["lo"]:sl["hi"]],
+                                                            op=torch.distributed.ReduceOp.SUM, async_op=True))
+
     def _body(self, s=0):
         px, mask, pe, lap, deg, labels, ei = self.sets[s]
         for p in self.params:
             p.grad = None                       # autograd then WRITES each gradient (no += kernels)
         out = self.model.forward_static(px, ei, mask, pe, lap, deg)
         loss = self.loss_fn(out, labels)
+        sliced = bool(self._slices)
+        if sliced:
+            for sl in self._slices:
+                sl["left"] = len(sl["idx"])
+            self._works = []
+        self._in_body = True
         with ops.wgrad_side_stream(True):       # safe here: every p.grad is None and is read only after the pass
             loss.backward()
-        if self.flat_adam:                      # gradients -> flat buffer (one multi-tensor copy), one SUM all-reduce,
+        self._in_body = False
+        if sliced:
+            main = torch.cuda.current_stream(self.device)
+            for w in self._works:
+                w.wait()
+            main.wait_stream(self.comm_stream)
+            self.opt.step(grad_scale=1.0 / self.world)
+        elif self.flat_adam:                    # gradients -> flat buffer (one multi-tensor copy), one SUM all-reduce,
             live = [(p, v) for p, v in zip(self.params, self.bucket.views) if p.grad is not None]   # one Adam kernel
             torch._foreach_copy_([v for _, v in live], [p.grad for p, _ in live])
             if self.world > 1:

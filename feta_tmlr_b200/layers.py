@@ -95,9 +95,10 @@ class DiffTransformerEncoderLayer(nn.Module):
         self.scaling = None
 
     def forward(self, src, pe=None, degree=None, src_mask=None, src_key_padding_mask=None,
-                need_heads=False, rowscale=None):
+                need_heads=False, rowscale=None, bn_rows=None):
         """``rowscale`` (extension): the seq-first ``degree.t().contiguous()`` precomputed once per forward by
-        the encoder instead of once per layer."""
+        the encoder instead of once per layer.  ``bn_rows`` (extension, BatchNorm variant): 0/1 weight per
+        flattened row ``[Nmax * B]``; rows with 0 stay out of the batch statistics (static-shape batches)."""
         if src_mask is not None:
             raise NotImplementedError("src_mask (attn_mask) is never passed by the reference "
                                       "(models.py:166) and is not implemented")
@@ -117,7 +118,19 @@ class DiffTransformerEncoderLayer(nn.Module):
             if self.scaling is None:
                 self.scaling = 1. / pe.diagonal(dim1=1, dim2=2).max().item()
             rowscale = (self.scaling * pe.diagonal(dim1=1, dim2=2)).transpose(0, 1).contiguous()
-        if self.batch_norm:
+        if self.batch_norm and self.training and ops.batchnorm_supported(src.shape[-1]) and src.is_cuda \
+                and self.dropout1.p == 0.0:
+            # fused residual + BatchNorm1d over the flattened rows (padding rows included, like the reference)
+            bsz, dm = src.shape[1], src.shape[-1]
+            src = ops.add_batch_norm(src.reshape(-1, dm), src2.reshape(-1, dm), self.norm1,
+                                     bscale=rowscale.reshape(-1), roww=bn_rows)
+            h = ops.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
+            src2 = ops.linear(self.dropout(h), self.linear2.weight, self.linear2.bias)
+            src = ops.add_batch_norm(src, src2, self.norm2, roww=bn_rows)
+            src = src.view(-1, bsz, dm)
+        elif self.batch_norm:
+            if bn_rows is not None:
+                raise NotImplementedError("bn_rows needs the fused BatchNorm path (training mode, d_model dividing 256)")
             src = src + self.dropout1(rowscale.unsqueeze(-1) * src2)
             bsz = src.shape[1]
             src = src.reshape(-1, src.shape[-1])

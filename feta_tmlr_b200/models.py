@@ -230,12 +230,18 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         return ctx
 
     def forward_static(self, src, pe, edge_index, degree, masks):
+        bn_rows = None
         if any(getattr(mod, 'batch_norm', False) for mod in self.layers):
-            # the reference's BatchNorm1d runs over rows padded to the BATCH maximum (layers' flatten of
-            # [Nmax, B, d]); the static layout pads to a dataset-wide cap, which would change the statistics
-            raise NotImplementedError("forward_static / GraphedTrainStep: batch_norm=True is not supported in the "
-                                      "static-shape layout (statistics over padded rows would differ from the "
-                                      "reference); use forward() or LayerNorm")
+            # the reference's BatchNorm1d runs over rows padded to the BATCH maximum (the layer flattens
+            # [Nmax, B, d]); the static layout pads to a dataset-wide cap.  Rows i >= batch maximum are excluded
+            # from the statistics by a 0/1 row weight (computed on the device: no synchronisation), which
+            # reproduces the reference's statistics exactly; eval mode / other widths are not supported here.
+            if not self.training or not ops.batchnorm_supported(src.shape[-1]):
+                raise NotImplementedError("forward_static with batch_norm=True needs training mode and a d_model "
+                                          "that divides 256 (fused BatchNorm with row weights)")
+            batch_max = (~masks).sum(dim=1).max()
+            bn_rows = (torch.arange(src.shape[0], device=src.device).view(-1, 1) < batch_max).to(torch.float32) \
+                .expand(src.shape[0], src.shape[1]).reshape(-1).contiguous()
         output = src
         nmax, B, d = src.shape
         H = self.num_heads
@@ -247,7 +253,7 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         rowscale = None if degree is None else degree.transpose(0, 1).contiguous()
         for layer_num, mod in enumerate(self.layers):
             output, attn, out_each_head = mod(output, pe=pe, degree=degree, src_key_padding_mask=masks,
-                                              need_heads=True, rowscale=rowscale)
+                                              need_heads=True, rowscale=rowscale, bn_rows=bn_rows)
             if self.last_layer_filter and layer_num + 1 != num_layers:
                 continue
             if ctx is None:

@@ -920,3 +920,68 @@ class AddLayerNormFn(torch.autograd.Function):
 
 def add_layer_norm(a, b, gamma, beta, eps=1e-5, bscale=None):
     return AddLayerNormFn.apply(a, b, bscale, gamma, beta, eps)
+
+
+class AddBatchNormFn(torch.autograd.Function):
+    """y = BatchNorm1d(a + bscale * b) in TRAINING mode over rows (the layer's flattened [Nmax*B, d], padding rows
+    included like the reference); ``roww`` (0/1 per row, optional) excludes rows from the statistics -- the
+    static-shape layout pads beyond the batch maximum the reference pads to.  Running statistics are updated in
+    place like ``nn.BatchNorm1d``.  Two launches each way (csrc/batchnorm.cu)."""
+
+    @staticmethod
+    def forward(ctx, a, b, bscale, roww, gamma, beta, running_mean, running_var, num_batches, momentum, eps):
+        _need_cuda(a, b, gamma, beta)
+        lib = _lib.load()
+        a = _f32c(a)
+        b = None if b is None else _f32c(b)
+        bscale = None if bscale is None else _f32c(bscale)
+        roww = None if roww is None else _f32c(roww)
+        D = a.shape[-1]
+        T = a.numel() // D
+        y, z = torch.empty_like(a), torch.empty_like(a)
+        mean = torch.empty(D, dtype=torch.float32, device=a.device)
+        rstd = torch.empty(D, dtype=torch.float32, device=a.device)
+        nblk = lib.feta_add_batchnorm_blocks(T)
+        partial = torch.empty(nblk * 3 * D, dtype=torch.float32, device=a.device)
+        gamma, beta = _f32c(gamma), _f32c(beta)
+        check(lib.feta_add_batchnorm_fwd(_ptr(a), _ptr(b), _ptr(bscale), _ptr(roww), _ptr(gamma), _ptr(beta), _ptr(y),
+                                         _ptr(z), _ptr(mean), _ptr(rstd), _ptr(running_mean), _ptr(running_var),
+                                         _ptr(num_batches), _ptr(partial), float(momentum), float(eps), T, D, _stream()),
+              "feta_add_batchnorm_fwd")
+        ctx.save_for_backward(z, mean, rstd, gamma, bscale, roww)
+        ctx.has_b = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        z, mean, rstd, gamma, bscale, roww = ctx.saved_tensors
+        D = z.shape[-1]
+        T = z.numel() // D
+        dy = _f32c(dy)
+        dz = torch.empty_like(z)
+        dbs = torch.empty_like(z) if (ctx.has_b and bscale is not None) else None
+        dg = torch.empty(D, dtype=torch.float32, device=z.device)
+        db = torch.empty(D, dtype=torch.float32, device=z.device)
+        nblk = lib.feta_add_batchnorm_blocks(T)
+        partial = torch.empty(nblk * 3 * D, dtype=torch.float32, device=z.device)
+        check(lib.feta_add_batchnorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale), _ptr(roww),
+                                         _ptr(dz), _ptr(dbs), _ptr(dg), _ptr(db), _ptr(partial), T, D, _stream()),
+              "feta_add_batchnorm_bwd")
+        grad_b = None
+        if ctx.has_b:
+            grad_b = dbs if dbs is not None else dz
+        return dz, grad_b, None, None, dg, db, None, None, None, None, None
+
+
+def batchnorm_supported(D):
+    return D % 4 == 0 and D <= 256 and 256 % D == 0
+
+
+def add_batch_norm(a, b, bn, bscale=None, roww=None):
+    """``bn``: an ``nn.BatchNorm1d`` in training mode (parameters, running buffers, momentum, eps are its own)."""
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    track = bn.track_running_stats and bn.running_mean is not None
+    return AddBatchNormFn.apply(a, b, bscale, roww, bn.weight, bn.bias, bn.running_mean if track else None,
+                                bn.running_var if track else None, bn.num_batches_tracked if track else None,
+                                momentum, bn.eps)

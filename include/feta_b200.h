@@ -313,6 +313,24 @@ int feta_scatter_rows(const float* packed, const int64_t* feature_indices, float
                       int64_t stride_b, int64_t stride_n, int64_t N, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * A6 layer glue, BatchNorm variant (the reference's ZINC default: experiments/run_transformer_gengcn.py:57,64;
+ * the layer flattens [Nmax, B, d] to rows -- padding included -- before nn.BatchNorm1d).
+ *   z = a + bscale[row] * b;  y = (z - mean_c) * rstd_c * gamma_c + beta_c,  batch statistics (biased variance)
+ *   over the rows with roww[row] != 0 (NULL: all rows);  running_mean / running_var (unbiased) / num_batches
+ *   updated like torch.nn.BatchNorm1d in training mode (NULL: skipped).  D must divide 256.
+ *   partial: feta_add_batchnorm_blocks(T) * 3 * D floats of scratch.  Backward returns dz (= d a), dbs (= d b,
+ *   NULL when b was absent), dgamma, dbeta.
+ * --------------------------------------------------------------------------------------- */
+int feta_add_batchnorm_blocks(int64_t T);
+int feta_add_batchnorm_fwd(const float* a, const float* b, const float* bscale, const float* roww,
+                           const float* gamma, const float* beta, float* y, float* z, float* mean, float* rstd,
+                           float* running_mean, float* running_var, int64_t* num_batches, float* partial,
+                           float momentum, float eps, int64_t T, int D, void* stream);
+int feta_add_batchnorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
+                           const float* gamma, const float* bscale, const float* roww, float* dz, float* dbs,
+                           float* dgamma, float* dbeta, float* partial, int64_t T, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * A7  collate index builders (transformer/data.py:161-225, :394-460): GPU batch builder over a
  * dataset pre-packed on the device.  Given the ids of the B graphs of a mini-batch and the
  * packed dataset (node_ptr/edge_ptr prefix sums, edge_index local to each graph), writes the

@@ -196,3 +196,36 @@ def test_side_stream_opt_in_matches_main_stream(cuda):
     assert ops.WGRAD_SIDE_STREAM is False
     for k in grads[0]:
         assert torch.equal(grads[0][k], grads[1][k]), k
+
+
+@pytest.mark.parametrize("T,D", [(37, 64), (4736, 64), (1000, 16), (777, 128)])
+@pytest.mark.parametrize("scaled,weighted", [(False, False), (True, False), (True, True)])
+def test_add_batch_norm_parity(cuda, T, D, scaled, weighted):
+    """Fused residual + BatchNorm1d (training) vs torch.nn.BatchNorm1d in fp64: output, every gradient, running
+    statistics (unbiased variance, num_batches_tracked); with row weights the statistics come from the kept rows."""
+    from feta_tmlr_b200 import ops
+    g = torch.Generator().manual_seed(T + D)
+    a, b = torch.randn(T, D, generator=g) + 0.5, torch.randn(T, D, generator=g)
+    bs = torch.rand(T, generator=g) + 0.5 if scaled else None
+    w = (torch.rand(T, generator=g) < 0.7).float() if weighted else None
+    go = torch.randn(T, D, generator=g)
+    bn_ref = torch.nn.BatchNorm1d(D).double()
+    bn_ref.weight.data.uniform_(0.5, 1.5, generator=g)
+    bn_ref.bias.data.uniform_(-0.5, 0.5, generator=g)
+    bn = torch.nn.BatchNorm1d(D)
+    bn.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in bn_ref.state_dict().items()})
+    bn = bn.to(cuda).train()
+    ar, br = a.double().requires_grad_(), b.double().requires_grad_()
+    z = ar + (br if bs is None else bs.double().unsqueeze(1) * br)
+    keep = torch.ones(T, dtype=torch.bool) if w is None else w.bool()
+    yk = bn_ref(z[keep])
+    (yk * go.double()[keep]).sum().backward()
+    ad, bd = a.to(cuda).requires_grad_(), b.to(cuda).requires_grad_()
+    y = ops.add_batch_norm(ad, bd, bn, bscale=None if bs is None else bs.to(cuda), roww=None if w is None else w.to(cuda))
+    (y * go.to(cuda))[keep.to(cuda)].sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(y[keep.to(cuda)], yk) < TOL
+    assert rel_err(ad.grad, ar.grad) < TOL and rel_err(bd.grad, br.grad) < TOL
+    assert rel_err(bn.weight.grad, bn_ref.weight.grad) < TOL and rel_err(bn.bias.grad, bn_ref.bias.grad) < TOL
+    assert rel_err(bn.running_mean, bn_ref.running_mean) < 1e-5 and rel_err(bn.running_var, bn_ref.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == 1

@@ -210,11 +210,30 @@ def test_tile_edges_per_head_matches_oracle_on_tiled_edges(cuda, name, B):
     assert rel_err(so.reshape(oo.shape), oo) < TOL
 
 
-def test_forward_static_rejects_batch_norm(cuda):
+def test_forward_static_batch_norm_matches_packed_forward(cuda):
+    """BatchNorm variant (the reference's ZINC default) in the static-shape layout: rows beyond the batch maximum are
+    weighted out of the statistics, so forward_static == forward (whose statistics are the reference's, pinned by
+    the ZINC_bn reference-run fixture) -- outputs, parameter gradients and running statistics."""
+    import copy
     import feta_tmlr_b200.models as fmodels
     from feta_tmlr_b200 import data as fdata, engine
-    cfg, graphs, store, batch = make_batch("ZINC", 4, seed=22)
-    m = synthetic.build_model("ZINC", fmodels, layers=2, batch_norm=True).to(cuda)
-    sb = to_dev(fdata.collate_host(store, np.arange(4), static=engine.static_caps(store, 4))[:9], cuda)
+    cfg, graphs, store, batch = make_batch("ZINC", 6, seed=22)
+    torch.manual_seed(0)
+    m1 = synthetic.build_model("ZINC", fmodels, layers=2, batch_norm=True).to(cuda).train()
+    m2 = copy.deepcopy(m1)
+    g = to_dev(batch[:9], cuda)
+    caps = engine.static_caps(store, 6)
+    sb = to_dev(fdata.collate_host(store, np.arange(6), static=(caps[0] + 5, caps[1]))[:9], cuda)
+    ref = m1(g[0], g[6], g[7], g[8], g[1], g[2], g[3], g[4])[0]
+    out = m2.forward_static(sb[0], sb[6], sb[1], sb[2], sb[3], sb[4])
+    assert rel_err(out, ref) < 1e-5
+    ref.square().sum().backward()
+    out.square().sum().backward()
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if p1.grad is not None and float(p1.grad.abs().max()) > 1e-6:
+            assert rel_err(p2.grad, p1.grad) < 1e-4, k
+    for (k, b1), (_, b2) in zip(m1.named_buffers(), m2.named_buffers()):
+        assert rel_err(b2.float(), b1.float()) < 1e-5, k
+    m2.eval()
     with pytest.raises(NotImplementedError):
-        m.forward_static(sb[0], sb[6], sb[1], sb[2], sb[3], sb[4])
+        m2.forward_static(sb[0], sb[6], sb[1], sb[2], sb[3], sb[4])
