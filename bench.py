@@ -442,6 +442,8 @@ def run_config(name, args, dev, rank, world, steps, warmup, repeats, with_e2e=Tr
                       "h2d_bytes_per_step": int(np.mean([batch_nbytes(b[:7]) for b in pool_pinned])),
                       "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / steps, 4), "spread": spread_e2e}
         res["last_loss"] = d2h[0]
+    if use_graph and eng.plan_guard_tripped():
+        raise RuntimeError("device-side plan guard tripped: static capacities do not cover a batch")
     if with_builder and use_graph:
         # N2 end to end: the dataset lives in HBM, only the graph ids of the step cross PCIe, the GPU batch builder
         # (csrc/collate.cu) writes the static batch and the graph replays on it
@@ -461,10 +463,10 @@ def run_config(name, args, dev, rank, world, steps, warmup, repeats, with_e2e=Tr
             res["e2e_device_builder"] = {"value": round(world * B * steps / (ms_b * 1e-3), 1), "unit": UNIT,
                                          "h2d_bytes_per_step": 8 * (3 * B + 2), "d2h_bytes_per_step": 4,
                                          "ms_per_step": round(ms_b / steps, 4), "spread": spread_b}
+            if eng.plan_guard_tripped():
+                res["e2e_device_builder"] = {"error": "device-side plan guard tripped on a builder batch"}
         except ValueError as e:                     # a batch beyond the static capacities of the host pool
             res["e2e_device_builder"] = {"error": str(e)[:120]}
-    if use_graph and eng.plan_guard_tripped():
-        raise RuntimeError("device-side plan guard tripped: static capacities do not cover a batch")
     if with_kernels and rank == 0:
         us, nnz, rows, nm = kernel_times(cfg, B, model, pool_dev[3 % n_pool], dev, use_graph)
         res.update(kern_us=us, cheb_nnz=nnz, cheb_rows=rows, nm=nm)

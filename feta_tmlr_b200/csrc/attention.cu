@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
     const float* __restrict__ pe, const uint8_t* __restrict__ mask, float* __restrict__ attn,
     float* __restrict__ o_heads, int64_t osn, int64_t osb, float* __restrict__ rowflag, int H, int nmax,
-    float scale, int rows_per_cta) {
+    float scale, int rows_per_cta, const float* __restrict__ drop, float* __restrict__ attn_post) {
   extern __shared__ float smem[];
   __shared__ int s_neff;
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
     float* orow = o_heads + (int64_t)i * osn + (int64_t)b * osb + h * DH;
     if (mk[i]) {  // padded query: defined as zero (never consumed by the model)
       for (int j = lane; j < nmax; j += 32) arow[j] = 0.0f;
+      if (attn_post)
+        for (int j = lane; j < nmax; j += 32) attn_post[(((size_t)b * H + h) * nmax + i) * nmax + j] = 0.0f;
       if (lane < DH) orow[lane] = 0.0f;
       if (DH > 32 && lane + 32 < DH) orow[lane + 32] = 0.0f;
       if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = 0.0f;
@@ -123,8 +125,14 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
     for (int ch = 0; ch < NCH; ++ch) {
       const int j = lane + 32 * ch;
       const float p = s[ch] / denom;
+      float pd = p;        // attention-weight dropout: P V uses P * drop (0 or 1/(1-p)); `attn` keeps P for backward
+      if (drop != nullptr && j < nmax) {
+        const size_t at = (((size_t)b * H + h) * nmax + i) * nmax + j;
+        pd = p * __ldg(drop + at);
+        attn_post[at] = pd;
+      }
       if (j < nmax) arow[j] = p;
-      if (j < n) pr[j] = p;
+      if (j < n) pr[j] = pd;
     }
     if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = sum > 1e-6f ? 1.0f : 0.0f;
     __syncwarp();
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_tiled_kernel(
     const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int64_t sn, int64_t sb,
     const float* __restrict__ pe, const uint8_t* __restrict__ mask, float* __restrict__ attn,
     float* __restrict__ o_heads, int64_t osn, int64_t osb, float* __restrict__ rowflag, int H, int nmax,
-    float scale, int rows_per_cta) {
+    float scale, int rows_per_cta, const float* __restrict__ drop, float* __restrict__ attn_post) {
   extern __shared__ float smem[];
   __shared__ int s_neff;
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
@@ -190,6 +198,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_tiled_kernel(
     float* orow = o_heads + (int64_t)i * osn + (int64_t)b * osb + h * DH;
     if (mk[i]) {  // padded query: defined as zero (never consumed by the model)
       for (int j = lane; j < nmax; j += 32) arow[j] = 0.0f;
+      if (attn_post)
+        for (int j = lane; j < nmax; j += 32) attn_post[(((size_t)b * H + h) * nmax + i) * nmax + j] = 0.0f;
       if (lane < DH) orow[lane] = 0.0f;
       if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = 0.0f;
       continue;
@@ -237,8 +247,14 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_tiled_kernel(
     for (int ch = 0; ch < NCH; ++ch) {
       const int j = lane + 32 * ch;
       const float p = s[ch] / denom;
+      float pd = p;        // attention-weight dropout: P V uses P * drop (0 or 1/(1-p)); `attn` keeps P for backward
+      if (drop != nullptr && j < nmax) {
+        const size_t at = (((size_t)b * H + h) * nmax + i) * nmax + j;
+        pd = p * __ldg(drop + at);
+        attn_post[at] = pd;
+      }
       if (j < nmax) arow[j] = p;
-      if (j < n) pr[j] = p;
+      if (j < n) pr[j] = pd;
     }
     if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = sum > 1e-6f ? 1.0f : 0.0f;
     __syncwarp();
@@ -272,7 +288,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(
     const uint8_t* __restrict__ mask, const float* __restrict__ attn, const float* __restrict__ rowflag,
     const float* __restrict__ d_o, int64_t osn, int64_t osb, const float* __restrict__ d_attn,
     float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int64_t dsn, int64_t dsb, int H, int nmax,
-    float scale) {
+    float scale, const float* __restrict__ drop) {
   extern __shared__ float smem[];
   __shared__ int s_neff;
   __shared__ int s_valid[kAttnWarps];
@@ -322,20 +338,28 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(
       for (int c = 0; c < DH; ++c) dor[c] = dOs[i * DH + c];
       const float* arow = attn + (((size_t)b * H + h) * nmax + i) * nmax;
       const float* garow = d_attn ? d_attn + (((size_t)b * H + h) * nmax + i) * nmax : nullptr;
-      float p[NCH], dp[NCH];
+      const float* drow = drop ? drop + (((size_t)b * H + h) * nmax + i) * nmax : nullptr;
+      float p[NCH], dp[NCH], pp[NCH];      // P (pre-dropout), dP (pre-dropout), P * drop
       float delta = 0.0f;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int j = lane + 32 * ch;
-        float pv = 0.0f, dpv = 0.0f;
+        float pv = 0.0f, dpv = 0.0f, ppv = 0.0f;
         if (j < n) {
           pv = __ldg(arow + j);
 #pragma unroll
           for (int c = 0; c < DH; ++c) dpv = fmaf(dor[c], Vt[c * npad + j], dpv);
           if (garow) dpv += __ldg(garow + j);
+          ppv = pv;
+          if (drow) {
+            const float dm = __ldg(drow + j);
+            dpv *= dm;
+            ppv = pv * dm;
+          }
         }
         p[ch] = pv;
         dp[ch] = dpv;
+        pp[ch] = ppv;
         delta = fmaf(pv, dpv, delta);
       }
       delta = warp_sum(delta) * __ldg(rowflag + ((size_t)b * H + h) * nmax + i);
@@ -343,7 +367,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(
       for (int ch = 0; ch < NCH; ++ch) {
         const int j = lane + 32 * ch;
         if (j < n) {
-          pr[j] = p[ch];
+          pr[j] = pp[ch];
           ds[j] = p[ch] * (dp[ch] - delta);
         }
       }
@@ -407,7 +431,7 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_tiled_kernel(
     const uint8_t* __restrict__ mask, const float* __restrict__ attn, const float* __restrict__ rowflag,
     const float* __restrict__ d_o, int64_t osn, int64_t osb, const float* __restrict__ d_attn,
     float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int64_t dsn, int64_t dsb, int H, int nmax,
-    float scale) {
+    float scale, const float* __restrict__ drop) {
   constexpr int LD = DH + 4, C4 = DH / 4, JT = THREADS / C4, EMAX = (32 * NCH + JT - 1) / JT;
   constexpr int RND = THREADS / 32;   // rows per round (one per warp)
   extern __shared__ float smem[];
@@ -464,10 +488,11 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_tiled_kernel(
       }
       const float* arow = attn + (((size_t)b * H + h) * nmax + i) * nmax;
       const float* garow = d_attn ? d_attn + (((size_t)b * H + h) * nmax + i) * nmax : nullptr;
-      float p[NCH], dp[NCH];
+      float p[NCH], dp[NCH], pp[NCH];
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int j = lane + 32 * ch;
+        pp[ch] = 0.0f;
         p[ch] = j < n ? __ldg(arow + j) : 0.0f;
         dp[ch] = (garow && j < n) ? __ldg(garow + j) : 0.0f;
       }
@@ -483,7 +508,14 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_tiled_kernel(
             a = fmaf(dor[4 * c], t.x, a), a = fmaf(dor[4 * c + 1], t.y, a);
             a = fmaf(dor[4 * c + 2], t.z, a), a = fmaf(dor[4 * c + 3], t.w, a);
           }
+          float ppv = p[ch];
+          if (drop != nullptr) {     // attention-weight dropout: dP_pre = dP_post * drop, dV uses P * drop
+            const float dm = __ldg(drop + (((size_t)b * H + h) * nmax + i) * nmax + j);
+            a *= dm;
+            ppv *= dm;
+          }
           dp[ch] = a;
+          pp[ch] = ppv;
           delta = fmaf(p[ch], a, delta);
         }
       }
@@ -492,7 +524,7 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_tiled_kernel(
       for (int ch = 0; ch < NCH; ++ch) {
         const int j = lane + 32 * ch;
         if (j < n) {
-          pr[j] = p[ch];
+          pr[j] = pp[ch];
           ds[j] = p[ch] * (dp[ch] - delta);
         }
       }
@@ -573,7 +605,7 @@ static size_t attn_fwd_tiled_smem(int dh, int nmax) {
 template <int DH, int NCH>
 static int launch_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
                            const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag,
-                           int B, int H, int nmax, float scale, cudaStream_t st) {
+                           int B, int H, int nmax, float scale, const float* drop, float* attn_post, cudaStream_t st) {
   if constexpr ((DH == 8 || DH == 16) && NCH >= 4 && NCH <= 8) {
     const uintptr_t ptrs = (uintptr_t)k | (uintptr_t)v | (uintptr_t)o_heads;
     if ((ptrs % 16) == 0 && ((sn | sb | osn | osb) % 4) == 0 && getenv("FETA_ATTN_FWD_LEGACY") == nullptr) {
@@ -582,7 +614,8 @@ static int launch_attn_fwd(const float* q, const float* k, const float* v, int64
                                      (int)smem_t));
       dim3 grid_t((unsigned)ceil_div(nmax, kRowsPerCta), (unsigned)(B * H));
       attn_fwd_tiled_kernel<DH, NCH><<<grid_t, kAttnThreads, smem_t, st>>>(q, k, v, sn, sb, pe, mask, attn, o_heads, osn,
-                                                                           osb, rowflag, H, nmax, scale, kRowsPerCta);
+                                                                           osb, rowflag, H, nmax, scale, kRowsPerCta,
+                                                                           drop, attn_post);
       FETA_LAUNCH_CHECK();
       return FETA_OK;
     }
@@ -593,7 +626,7 @@ static int launch_attn_fwd(const float* q, const float* k, const float* v, int64
   const int rows_per_cta = nmax <= 64 ? ((nmax + kAttnWarps - 1) / kAttnWarps) * kAttnWarps : kRowsPerCta;
   dim3 grid((unsigned)ceil_div(nmax, rows_per_cta), (unsigned)(B * H));
   attn_fwd_kernel<DH, NCH><<<grid, kAttnThreads, smem, st>>>(q, k, v, sn, sb, pe, mask, attn, o_heads, osn, osb,
-                                                             rowflag, H, nmax, scale, rows_per_cta);
+                                                             rowflag, H, nmax, scale, rows_per_cta, drop, attn_post);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
@@ -618,14 +651,14 @@ template <int DH, int NCH>
 static int launch_attn_bwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
                            const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o,
                            int64_t osn, int64_t osb, const float* d_attn, float* dq, float* dk, float* dv, int64_t dsn,
-                           int64_t dsb, int B, int H, int nmax, float scale, cudaStream_t st) {
+                           int64_t dsb, int B, int H, int nmax, float scale, const float* drop, cudaStream_t st) {
   if constexpr ((DH == 8 || DH == 16) && NCH >= 4 && NCH <= 8) {
     if (attn_bwd_tiled_ok(DH, nmax, q, k, v, d_o, dq, dk, dv, sn, sb, osn, osb, dsn, dsb)) {
       const size_t smem_t = attn_bwd_tiled_smem(DH, nmax);
       FETA_CUDA(cudaFuncSetAttribute(attn_bwd_tiled_kernel<DH, NCH, kAttnBwdTiledThreads>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
       attn_bwd_tiled_kernel<DH, NCH, kAttnBwdTiledThreads><<<(unsigned)(B * H), kAttnBwdTiledThreads, smem_t, st>>>(
-          q, k, v, sn, sb, mask, attn, rowflag, d_o, osn, osb, d_attn, dq, dk, dv, dsn, dsb, H, nmax, scale);
+          q, k, v, sn, sb, mask, attn, rowflag, d_o, osn, osb, d_attn, dq, dk, dv, dsn, dsb, H, nmax, scale, drop);
       FETA_LAUNCH_CHECK();
       return FETA_OK;
     }
@@ -634,7 +667,7 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, int64
   FETA_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<DH, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attn_bwd_kernel<DH, NCH><<<(unsigned)(B * H), kAttnThreads, smem, st>>>(q, k, v, sn, sb, mask, attn, rowflag, d_o,
                                                                           osn, osb, d_attn, dq, dk, dv, dsn, dsb, H,
-                                                                          nmax, scale);
+                                                                          nmax, scale, drop);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
@@ -661,10 +694,13 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, int64
 
 using namespace feta;
 
-extern "C" int feta_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
-                             const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag,
-                             int B, int H, int nmax, int dh, float scale, int use_tensor_cores, void* stream_) {
+static int attn_fwd_impl(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
+                         const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag,
+                         int B, int H, int nmax, int dh, float scale, int use_tensor_cores, const float* drop,
+                         float* attn_post, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  FETA_REQUIRE((drop == nullptr) == (attn_post == nullptr), "attn_fwd: drop and attn_post go together");
+  if (drop != nullptr) use_tensor_cores = 0;     // the tcgen05 path has no dropout variant
   FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && dh >= 1, "attn_fwd: bad sizes");
   if (B == 0 || nmax == 0) return FETA_OK;
   FETA_REQUIRE(q && k && v && mask && attn && o_heads && rowflag, "attn_fwd: NULL pointer argument");
@@ -679,15 +715,32 @@ extern "C" int feta_attn_fwd(const float* q, const float* k, const float* v, int
     return FETA_EUNSUPPORTED;
   }
   FETA_ATTN_DISPATCH(launch_attn_fwd, q, k, v, sn, sb, pe, mask, attn, o_heads, osn, osb, rowflag, B, H, nmax, scale,
-                     st);
+                     drop, attn_post, st);
   set_last_error("attn_fwd: head dim %d not in {4,8,16,32,64}", dh);
   return FETA_EUNSUPPORTED;
 }
 
-extern "C" int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
-                             const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o_heads,
-                             int64_t osn, int64_t osb, const float* d_attn, float* dq, float* dk, float* dv,
-                             int64_t dsn, int64_t dsb, int B, int H, int nmax, int dh, float scale, void* stream_) {
+extern "C" int feta_attn_fwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb, const float* pe,
+                             const uint8_t* mask, float* attn, float* o_heads, int64_t osn, int64_t osb, float* rowflag,
+                             int B, int H, int nmax, int dh, float scale, int use_tensor_cores, void* stream_) {
+  return attn_fwd_impl(q, k, v, sn, sb, pe, mask, attn, o_heads, osn, osb, rowflag, B, H, nmax, dh, scale,
+                       use_tensor_cores, nullptr, nullptr, stream_);
+}
+
+extern "C" int feta_attn_fwd_dropout(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
+                                     const float* pe, const uint8_t* mask, const float* drop, float* attn,
+                                     float* attn_post, float* o_heads, int64_t osn, int64_t osb, float* rowflag, int B,
+                                     int H, int nmax, int dh, float scale, void* stream_) {
+  FETA_REQUIRE(drop && attn_post, "attn_fwd_dropout: NULL drop / attn_post");
+  return attn_fwd_impl(q, k, v, sn, sb, pe, mask, attn, o_heads, osn, osb, rowflag, B, H, nmax, dh, scale, 0, drop,
+                       attn_post, stream_);
+}
+
+static int attn_bwd_impl(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
+                         const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o_heads,
+                         int64_t osn, int64_t osb, const float* d_attn, float* dq, float* dk, float* dv,
+                         int64_t dsn, int64_t dsb, int B, int H, int nmax, int dh, float scale, const float* drop,
+                         void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && dh >= 1, "attn_bwd: bad sizes");
   if (B == 0 || nmax == 0) return FETA_OK;
@@ -699,7 +752,25 @@ extern "C" int feta_attn_bwd(const float* q, const float* k, const float* v, int
     return FETA_EUNSUPPORTED;
   }
   FETA_ATTN_DISPATCH(launch_attn_bwd, q, k, v, sn, sb, mask, attn, rowflag, d_o_heads, osn, osb, d_attn, dq, dk, dv,
-                     dsn, dsb, B, H, nmax, scale, st);
+                     dsn, dsb, B, H, nmax, scale, drop, st);
   set_last_error("attn_bwd: head dim %d not in {4,8,16,32,64}", dh);
   return FETA_EUNSUPPORTED;
+}
+
+extern "C" int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
+                             const uint8_t* mask, const float* attn, const float* rowflag, const float* d_o_heads,
+                             int64_t osn, int64_t osb, const float* d_attn, float* dq, float* dk, float* dv,
+                             int64_t dsn, int64_t dsb, int B, int H, int nmax, int dh, float scale, void* stream_) {
+  return attn_bwd_impl(q, k, v, sn, sb, mask, attn, rowflag, d_o_heads, osn, osb, d_attn, dq, dk, dv, dsn, dsb, B, H,
+                       nmax, dh, scale, nullptr, stream_);
+}
+
+extern "C" int feta_attn_bwd_dropout(const float* q, const float* k, const float* v, int64_t sn, int64_t sb,
+                                     const uint8_t* mask, const float* attn, const float* rowflag, const float* drop,
+                                     const float* d_o_heads, int64_t osn, int64_t osb, const float* d_attn_post,
+                                     float* dq, float* dk, float* dv, int64_t dsn, int64_t dsb, int B, int H, int nmax,
+                                     int dh, float scale, void* stream_) {
+  FETA_REQUIRE(drop != nullptr, "attn_bwd_dropout: NULL drop");
+  return attn_bwd_impl(q, k, v, sn, sb, mask, attn, rowflag, d_o_heads, osn, osb, d_attn_post, dq, dk, dv, dsn, dsb, B,
+                       H, nmax, dh, scale, drop, stream_);
 }

@@ -12,6 +12,8 @@
 //
 //   feta_linear_fwd:  Y[T,N]  = act(X[T,K] . W[N,K]^T + b)            (nn.Linear forward, W as PyTorch stores it)
 //   feta_linear_dx:   dX[T,K] = (dY[T,N] . W[N,K]) * [mask > 0] + dres  (its input gradient)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace feta {
@@ -186,6 +188,18 @@ static inline bool pick_bm64(int64_t T, int cols) {   // 64-row CTAs only when t
 
 using namespace feta;
 
+namespace feta {
+int linear5_fwd_try(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out, int relu,
+                    cudaStream_t st);
+int linear5_dx_try(const float* dY, const float* W, const float* dres, const float* mask_src, float* dX, int64_t T,
+                   int in, int out, cudaStream_t st);
+}
+
+extern "C" int feta_linear_tc5_supported(int in, int out) {
+  return in >= 64 && out >= 64 && in % 64 == 0 && out % 64 == 0 && in <= 1024 && out <= 1024 &&
+         getenv("FETA_LINEAR_NO_TC5") == nullptr;
+}
+
 extern "C" int feta_linear_tc_supported(int in, int out) {
   return in >= 8 && out >= 8 && in % 8 == 0 && out % 8 == 0 && in <= 256 && out <= 256;
 }
@@ -199,6 +213,10 @@ extern "C" int feta_linear_fwd(const float* X, const float* W, const float* bias
   FETA_REQUIRE(X && W && Y, "linear_fwd: NULL pointer argument");
   FETA_REQUIRE(((uintptr_t)X % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)Y % 8) == 0,
                "linear_fwd: X/W must be 16-byte aligned");
+  {   // tcgen05 path (linear_tc5.cu) when the shape is a multiple of its 128 x 64 x 64 tiles
+    const int rc = linear5_fwd_try(X, W, bias, Y, T, in, out, relu, st);
+    if (rc <= 0) return rc;
+  }
   const int ld = in + 4;
   if (pick_bm64(T, out)) {
     const size_t smem = (size_t)(64 + kBN) * ld * sizeof(float);
@@ -225,6 +243,10 @@ extern "C" int feta_linear_dx(const float* dY, const float* W, const float* dres
   FETA_REQUIRE(((uintptr_t)dY % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)dX % 8) == 0 &&
                    ((uintptr_t)dres % 8) == 0 && ((uintptr_t)mask_src % 8) == 0,
                "linear_dx: pointers must be 16-byte (dY, W) / 8-byte aligned");
+  {
+    const int rc = linear5_dx_try(dY, W, dres, mask_src, dX, T, in, out, st);
+    if (rc <= 0) return rc;
+  }
   const size_t wbytes = (size_t)out * (kBN + 8) * sizeof(float);
   if (pick_bm64(T, in)) {
     const size_t smem = (size_t)64 * (out + 4) * sizeof(float) + wbytes;

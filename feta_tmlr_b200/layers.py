@@ -45,22 +45,22 @@ class DiffMultiheadAttention(nn.Module):
         if bias:
             nn.init.constant_(self.out_proj.bias, 0.0)
 
-    def forward(self, src, pe=None, key_padding_mask=None, with_residual=False):
+    def forward(self, src, pe=None, key_padding_mask=None, with_residual=False, drop=None):
         """src [Nmax, B, d] -> (out [Nmax, B, d], attn [B, H, Nmax, Nmax], heads [B, Nmax, H, dh]).
         ``with_residual``: a 4th output, ``src`` routed through the in-projection's autograd node (its
         gradient is then folded into the in-projection's dX GEMM, ops.LinearFn)."""
-        if self.dropout > 0.0 and self.training:
-            raise NotImplementedError("DiffTransformerEncoderLayer(b200): attention-weight dropout > 0 is "
-                                      "not implemented in the fused kernel (all reference drivers "
-                                      "default to --dropout 0.0)")
         N, B, E = src.shape
+        if drop is None and self.dropout > 0.0 and self.training:
+            # attention-weight dropout (F.dropout on P before P V): the multipliers come from torch's Philox stream
+            # (CUDA-graph safe), the kernels apply them in the forward pass and again in the backward pass
+            drop = ops.dropout_multiplier((B, self.num_heads, N, N), self.dropout, src.device)
         res = None
         if with_residual:
             qkv, res = ops.linear_res(src, self.in_proj_weight, self.in_proj_bias)
         else:
             qkv = ops.linear(src, self.in_proj_weight, self.in_proj_bias)    # library GEMM (+ own wgrad)
         attn, o_sf = ops.diff_attention(qkv, pe, key_padding_mask, self.num_heads,
-                                        float(self.head_dim) ** -0.5, self.share_qk)
+                                        float(self.head_dim) ** -0.5, self.share_qk, drop=drop)
         # the kernel writes O seq-first, so concat-heads -> out_proj needs no copy; `heads` is the
         # [B, Nmax, H, dh] view the FeTA encoder consumes (models.py:179)
         out = self.out_proj(o_sf.view(N, B, E))

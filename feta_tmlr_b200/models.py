@@ -18,7 +18,12 @@ from torch import nn
 
 from . import ops
 from .ChebNetDynamic import ARMAConvDynamic, ChebConvDynamic
-from .layers import DiffTransformerEncoderLayer
+from .layers import DiffTransformerEncoderLayer, Linear
+
+
+# Every Linear of the heads / encoder glue is ``layers.Linear``: an ``nn.Linear`` (same parameters and state_dict keys)
+# whose weight / bias gradients are reduced over the token axis by csrc/dense.cu -- the library's SIMT sgemm needs
+# ~40 us for the [1024 x 256]^T [1024 x 256] weight gradient of ``encoder.linear`` alone (profiles/r2_launches_zinc.md).
 
 
 class GCNConv(nn.Module):
@@ -73,8 +78,8 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
             self.spectral_gnns = ChebConvDynamic(dh, dh, self.order, normalization=laplacian_norm,
                                                  learn_only_filter_order_coeff=False)
         self.gcn = GCNConv(self.num_coefficients, self.num_coefficients)            # :144
-        self.linear = nn.Linear(self.num_coefficients, self.num_coefficients)       # :145
-        self.linear_cat = nn.Linear(2 * d_model, d_model)                           # :146
+        self.linear = Linear(self.num_coefficients, self.num_coefficients)       # :145
+        self.linear_cat = Linear(2 * d_model, d_model)                           # :146
         self.gnn_type = gnn_type
         self.num_heads = num_heads
         self.last_layer_filter = last_layer_filter
@@ -317,8 +322,8 @@ class DiffGraphTransformerGenGCN(nn.Module):
         self.lap_pos_enc = lap_pos_enc
         self.lap_pos_enc_dim = lap_pos_enc_dim
         if lap_pos_enc and lap_pos_enc_dim > 0:
-            self.embedding_lap_pos_enc = nn.Linear(lap_pos_enc_dim, d_model)
-        self.embedding = nn.Linear(in_features=in_size, out_features=d_model, bias=False)
+            self.embedding_lap_pos_enc = Linear(lap_pos_enc_dim, d_model)
+        self.embedding = Linear(in_features=in_size, out_features=d_model, bias=False)
         encoder_layer = DiffTransformerEncoderLayer(d_model, nb_heads, dim_feedforward, dropout,
                                                     batch_norm=batch_norm, **layer_kw)
         self.encoder = DiffTransformerEncoderGenGCN(
@@ -327,8 +332,8 @@ class DiffGraphTransformerGenGCN(nn.Module):
             learn_only_filter_order_coeff=learn_only_filter_order_coeff)
         self.gcn = GCNConv(d_model, d_model)                                        # :508 (unused)
         self.pooling = GlobalAvg1D()
-        self.classifier = nn.Sequential(nn.Linear(d_model, d_model), nn.ReLU(True),
-                                        nn.Linear(d_model, nb_class))
+        self.classifier = nn.Sequential(Linear(d_model, d_model), nn.ReLU(True),
+                                        Linear(d_model, nb_class))
 
     def _embed(self, x, x_lap_pos_enc):
         output = self.embedding(x.permute(1, 0, 2))
@@ -374,16 +379,16 @@ class DiffGraphTransformerGenGCNSBM(nn.Module):
         self.lap_pos_enc = lap_pos_enc
         self.lap_pos_enc_dim = lap_pos_enc_dim
         if lap_pos_enc and lap_pos_enc_dim > 0:
-            self.embedding_lap_pos_enc = nn.Linear(lap_pos_enc_dim, d_model)
-        self.embedding = nn.Linear(in_features=in_size, out_features=d_model, bias=False)
+            self.embedding_lap_pos_enc = Linear(lap_pos_enc_dim, d_model)
+        self.embedding = Linear(in_features=in_size, out_features=d_model, bias=False)
         encoder_layer = DiffTransformerEncoderLayer(d_model, nb_heads, dim_feedforward, dropout,
                                                     batch_norm=batch_norm, **layer_kw)
         self.encoder = DiffTransformerEncoderGenGCN(
             d_model, nb_heads, encoder_layer, nb_layers, num_coefficients=filter_order,
             gnn_type=gnn_type, last_layer_filter=last_layer_filter,
             learn_only_filter_order_coeff=learn_only_filter_order_coeff)
-        self.classifier = nn.Sequential(nn.Linear(d_model, d_model), nn.ReLU(True),
-                                        nn.Linear(d_model, nb_class))
+        self.classifier = nn.Sequential(Linear(d_model, d_model), nn.ReLU(True),
+                                        Linear(d_model, nb_class))
 
     _embed = DiffGraphTransformerGenGCN._embed
 
@@ -472,7 +477,7 @@ class DiffGraphTransformerGenGCNMolHiv(nn.Module):
         self.lap_pos_enc = lap_pos_enc
         self.lap_pos_enc_dim = lap_pos_enc_dim
         if lap_pos_enc and lap_pos_enc_dim > 0:
-            self.embedding_lap_pos_enc = nn.Linear(lap_pos_enc_dim, d_model)
+            self.embedding_lap_pos_enc = Linear(lap_pos_enc_dim, d_model)
         self.d_model = d_model
         self.embedding = AtomEncoder(emb_dim=d_model)
         self.edge_embeddings = BondEncoder(emb_dim=d_model)
@@ -484,8 +489,8 @@ class DiffGraphTransformerGenGCNMolHiv(nn.Module):
             learn_only_filter_order_coeff=learn_only_filter_order_coeff, use_skip_conn=use_skip_conn)
         self.gcn = GCNConv(d_model, d_model)
         self.pooling = GlobalAvg1D()
-        self.classifier = nn.Sequential(nn.Linear(d_model, d_model), nn.LeakyReLU(True),
-                                        nn.Linear(d_model, nb_class))
+        self.classifier = nn.Sequential(Linear(d_model, d_model), nn.LeakyReLU(True),
+                                        Linear(d_model, nb_class))
         self.sigmoid = nn.Sigmoid()
 
     def regularisation(self, coeff):

@@ -364,8 +364,8 @@ class DiffAttentionFn(torch.autograd.Function):
     The attention core of the layer models.py:166-167 calls."""
 
     @staticmethod
-    def forward(ctx, qkv, pe, mask_u8, num_heads, scale, share_qk):
-        _need_cuda(qkv, pe, mask_u8)
+    def forward(ctx, qkv, pe, mask_u8, num_heads, scale, share_qk, drop=None):
+        _need_cuda(qkv, pe, mask_u8, drop)
         lib = _lib.load()
         qkv = _f32c(qkv)
         N, B, d3 = qkv.shape
@@ -380,22 +380,33 @@ class DiffAttentionFn(torch.autograd.Function):
         rowflag = torch.empty((B, H, N), dtype=torch.float32, device=qkv.device)
         base = qkv.data_ptr()
         qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
-        with _timed("attn_fwd"):
-            check(lib.feta_attn_fwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(attn), _ptr(o_heads),
-                                    B * d, d, _ptr(rowflag), B, H, N, dh, float(scale), int(ATTN_TENSOR_CORES),
-                                    _stream()), "feta_attn_fwd")
-        ctx.save_for_backward(qkv, mask_u8, attn, rowflag)
+        attn_out = attn
+        if drop is not None:           # attention-weight dropout: `drop` holds 0 or 1/(1-p) per weight
+            drop = _f32c(drop)
+            if tuple(drop.shape) != (B, H, N, N):
+                raise ValueError("drop must be [B, H, Nmax, Nmax]")
+            attn_out = torch.empty_like(attn)
+            with _timed("attn_fwd"):
+                check(lib.feta_attn_fwd_dropout(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(drop), _ptr(attn),
+                                                _ptr(attn_out), _ptr(o_heads), B * d, d, _ptr(rowflag), B, H, N, dh,
+                                                float(scale), _stream()), "feta_attn_fwd_dropout")
+        else:
+            with _timed("attn_fwd"):
+                check(lib.feta_attn_fwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(attn), _ptr(o_heads),
+                                        B * d, d, _ptr(rowflag), B, H, N, dh, float(scale), int(ATTN_TENSOR_CORES),
+                                        _stream()), "feta_attn_fwd")
+        ctx.save_for_backward(qkv, mask_u8, attn, rowflag, drop)
         ctx.cfg = (H, float(scale), bool(share_qk))
         ctx.mark_non_differentiable(rowflag)
         # the coefficient path detaches `attn` (models.py:282): without this autograd would hand backward an
         # attn-sized tensor of zeros per layer (a fill kernel + 4*H*N^2 bytes read by attn_bwd)
         ctx.set_materialize_grads(False)
-        return attn, o_heads, rowflag
+        return attn_out, o_heads, rowflag
 
     @staticmethod
     def backward(ctx, d_attn, d_o_heads, _unused):
         lib = _lib.load()
-        qkv, mask_u8, attn, rowflag = ctx.saved_tensors
+        qkv, mask_u8, attn, rowflag, drop = ctx.saved_tensors
         H, scale, share_qk = ctx.cfg
         N, B, d3 = qkv.shape
         d = d3 // 3
@@ -409,19 +420,33 @@ class DiffAttentionFn(torch.autograd.Function):
         qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
         db = dqkv.data_ptr()
         with _timed("attn_bwd"):
-            check(lib.feta_attn_bwd(qp, kp, vp, B * d3, d3, _ptr(mask_u8), _ptr(attn), _ptr(rowflag),
-                                    _ptr(d_o_heads), B * d, d, _ptr(d_attn_c), db, db + d * 4, db + 2 * d * 4,
-                                    B * d3, d3, B, H, N, dh, scale, _stream()), "feta_attn_bwd")
+            if drop is not None:
+                check(lib.feta_attn_bwd_dropout(qp, kp, vp, B * d3, d3, _ptr(mask_u8), _ptr(attn), _ptr(rowflag),
+                                                _ptr(drop), _ptr(d_o_heads), B * d, d, _ptr(d_attn_c), db, db + d * 4,
+                                                db + 2 * d * 4, B * d3, d3, B, H, N, dh, scale, _stream()),
+                      "feta_attn_bwd_dropout")
+            else:
+                check(lib.feta_attn_bwd(qp, kp, vp, B * d3, d3, _ptr(mask_u8), _ptr(attn), _ptr(rowflag),
+                                        _ptr(d_o_heads), B * d, d, _ptr(d_attn_c), db, db + d * 4, db + 2 * d * 4,
+                                        B * d3, d3, B, H, N, dh, scale, _stream()), "feta_attn_bwd")
         if share_qk:
             dqkv[..., :d] += dqkv[..., d:2 * d]
             dqkv[..., d:2 * d] = 0
-        return dqkv, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None
 
 
-def diff_attention(qkv, pe, key_padding_mask, num_heads, scale, share_qk=False):
+def dropout_multiplier(shape, p, device, generator=None):
+    """0 or 1/(1-p) per attention weight (what ``F.dropout`` multiplies by); capture-safe (torch's Philox state)."""
+    keep = torch.rand(shape, device=device, generator=generator) >= p
+    return keep.to(torch.float32) * (1.0 / (1.0 - p))
+
+
+def diff_attention(qkv, pe, key_padding_mask, num_heads, scale, share_qk=False, drop=None):
+    """``drop`` (optional, [B, H, Nmax, Nmax]): attention-weight dropout multipliers; the returned attention is the
+    dropped one (``F.dropout(P)``), the saved one the un-dropped P."""
     N, B, _ = qkv.shape
     mask_u8 = _mask_u8(key_padding_mask, B, N, qkv.device)
-    attn, o_sf, _ = DiffAttentionFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk)
+    attn, o_sf, _ = DiffAttentionFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk, drop)
     return attn, o_sf            # o_sf [Nmax, B, H, dh]; out_each_head = o_sf.permute(1, 0, 2, 3)
 
 
@@ -721,10 +746,16 @@ class wgrad_side_stream(object):
 # 7.0-13.4 us vs 4.3-7.9 us per GEMM -- three legacy TF32 MMAs per product run at about the SIMT fp32 rate),
 # so the default stays the library GEMM; kept, with parity tests, as the base of a tcgen05 version.
 LINEAR_TENSOR_CORES = _os.environ.get("FETA_LINEAR_TC", "0") == "1"
+# The tcgen05 successor (csrc/linear_tc5.cu: 3xTF32 tcgen05.mma, accumulators in TMEM, bias / ReLU / ReLU-mask /
+# residual-gradient epilogues).  FETA_LINEAR_TC5=1 routes every Linear of the layer whose (in, out) are multiples of
+# 64 through it (forward and dX); other shapes keep the library GEMM.
+LINEAR_TC5 = _os.environ.get("FETA_LINEAR_TC5", "0") == "1"
 
 
 def linear_tc_enabled(in_f, out_f):
-    return bool(LINEAR_TENSOR_CORES and _lib.load().feta_linear_tc_supported(int(in_f), int(out_f)))
+    lib = _lib.load()
+    return bool((LINEAR_TENSOR_CORES and lib.feta_linear_tc_supported(int(in_f), int(out_f))) or
+                (LINEAR_TC5 and lib.feta_linear_tc5_supported(int(in_f), int(out_f))))
 _SIDE = {}
 _JOIN_TASK = {}          # device -> id of the autograd graph task that already queued its join
 
@@ -770,8 +801,8 @@ class LinearFn(torch.autograd.Function):
         ctx.premasked = bool(grad_premasked)
         ctx.set_materialize_grads(False)
         out_f, in_f = weight.shape
-        ctx.tc = bool(LINEAR_TENSOR_CORES and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
-                      and lib.feta_linear_tc_supported(in_f, out_f))
+        ctx.tc = bool(x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+                      and linear_tc_enabled(in_f, out_f))
         if ctx.tc:
             x2 = _f32c(x.reshape(-1, in_f))
             w = _f32c(weight)

@@ -192,6 +192,21 @@ int feta_attn_bwd(const float* q, const float* k, const float* v, int64_t stride
                   int64_t dstride_n,
                   int64_t dstride_b, int B, int H, int nmax, int dh, float scale, void* stream);
 
+/* Attention-weight dropout (--dropout > 0; the layer applies it to P before P V, and the returned attention matrix
+ * is the dropped one -- GraphiT semantics restated in oracle/layers.py): `drop` [B, H, Nmax, Nmax] holds the
+ * multiplier of every weight (0 or 1/(1-p)), generated by the caller.  Forward writes BOTH attn (P, kept for
+ * the backward pass) and attn_post (P * drop, what the caller returns); O = (P * drop) V.  Backward takes the
+ * gradient of attn_post (or NULL) and applies dP = dP_post * drop, dV = (P * drop)^T dO. */
+int feta_attn_fwd_dropout(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
+                          const float* pe, const uint8_t* mask, const float* drop, float* attn, float* attn_post,
+                          float* o_heads, int64_t o_stride_n, int64_t o_stride_b, float* rowflag, int B, int H,
+                          int nmax, int dh, float scale, void* stream);
+int feta_attn_bwd_dropout(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
+                          const uint8_t* mask, const float* attn, const float* rowflag, const float* drop,
+                          const float* d_o_heads, int64_t o_stride_n, int64_t o_stride_b, const float* d_attn_post,
+                          float* dq, float* dk, float* dv, int64_t dstride_n, int64_t dstride_b, int B, int H,
+                          int nmax, int dh, float scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * A6 (layer glue)  token-axis reductions of the layer's backward (the residual + norm1 / FFN +
  * norm2 part of the layer transformer/models.py:4 imports; torch F.linear / nn.LayerNorm in the
@@ -233,6 +248,9 @@ int feta_add_layernorm_bwd_fold(const float* partial, int64_t T, int D, float* d
  *                     dres [T,in] (may be NULL): gradient of the residual connection that branches off X.
  * Shapes: in, out multiples of 8, <= 256 (feta_linear_tc_supported); other shapes: use a library GEMM.
  * --------------------------------------------------------------------------------------- */
+/* 1 when feta_linear_fwd / feta_linear_dx run this (in, out) pair on the tcgen05 path (csrc/linear_tc5.cu:
+ * 128 x 64 x 64 tiles, 3xTF32 in TMEM): both multiples of 64. */
+int feta_linear_tc5_supported(int in, int out);
 int feta_linear_tc_supported(int in, int out);
 int feta_linear_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out, int relu,
                     void* stream);

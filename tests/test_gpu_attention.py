@@ -132,7 +132,62 @@ def test_attention_rejects_unsupported(cuda):
     src, pe, degree, mask = _inputs(6, 2, 5, 36)
     with pytest.raises(RuntimeError):
         m(src.to(cuda), pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda))
-    m = DiffTransformerEncoderLayer(32, 4, 64, 0.5).to(cuda).train()       # attention dropout
+    m = DiffTransformerEncoderLayer(32, 4, 64, 0.0).to(cuda)
     src, pe, degree, mask = _inputs(6, 2, 5, 32)
-    with pytest.raises(NotImplementedError):
-        m(src.to(cuda), pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda))
+    with pytest.raises(NotImplementedError):                               # attn_mask is never passed by the reference
+        m(src.to(cuda), pe=pe.to(cuda), degree=degree.to(cuda), src_mask=torch.zeros(5, 5, device=cuda),
+          src_key_padding_mask=mask.to(cuda))
+
+
+@pytest.mark.parametrize("d,H,nmax", [(64, 8, 37), (64, 4, 150), (32, 1, 20)])
+def test_attention_weight_dropout_with_injected_mask(cuda, monkeypatch, d, H, nmax):
+    """--dropout > 0 (attention-weight dropout, F.dropout on P before P V): the kernels take the multipliers
+    (0 or 1/(1-p)) as a tensor, so the oracle can be fed the SAME mask.  Forward, returned (dropped) attention and
+    every gradient, including the gradient flowing through the returned attention matrix."""
+    import oracle.layers as olayers
+    from feta_tmlr_b200.layers import DiffMultiheadAttention
+    p = 0.25
+    B = 4
+    torch.manual_seed(d + nmax)
+    o = olayers.OracleDiffMultiheadAttention(d, H, dropout=p)
+    m = DiffMultiheadAttention(d, H, dropout=p).to(cuda)
+    m.load_state_dict(o.state_dict())
+    o.train(), m.train()
+    src, pe, degree, mask = _inputs(nmax + 1, B, nmax, d)
+    g = torch.Generator().manual_seed(7)
+    dm = (torch.rand(B, H, nmax, nmax, generator=g) >= p).float() / (1.0 - p)
+    monkeypatch.setattr(olayers.F, "dropout", lambda w, p=0.5, training=True: w * dm if w.dim() == 4 else w)
+    so = src.clone().requires_grad_()
+    oo, oa, oh = o(so, pe=pe, key_padding_mask=mask, zero_padded_queries=True)
+    sg = src.to(cuda).requires_grad_()
+    go, ga, gh = m(sg, pe=pe.to(cuda), key_padding_mask=mask.to(cuda), drop=dm.to(cuda))
+    assert rel_err(go, oo) < TOL and rel_err(ga, oa) < TOL and rel_err(gh, oh) < TOL
+    w = torch.randn(oo.shape, generator=g)
+    wa = torch.randn(oa.shape, generator=g)
+    ((oo * w).sum() + (oa * wa).sum()).backward()
+    ((go * w.to(cuda)).sum() + (ga * wa.to(cuda)).sum()).backward()
+    assert rel_err(sg.grad, so.grad) < TOL
+    for (n1, p1), (n2, p2) in zip(o.named_parameters(), m.named_parameters()):
+        assert rel_err(p2.grad, p1.grad) < 2e-4, n1
+
+
+def test_attention_dropout_trains_and_is_off_in_eval(cuda):
+    """The layer draws its own multipliers in training mode (no NotImplementedError any more) and is deterministic
+    in eval mode."""
+    from feta_tmlr_b200 import DiffTransformerEncoderLayer
+    torch.manual_seed(0)
+    m = DiffTransformerEncoderLayer(64, 8, 128, 0.2).to(cuda)
+    src, pe, degree, mask = _inputs(3, 6, 30, 64)
+    args = dict(pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda))
+    m.train()
+    s = src.to(cuda).requires_grad_()
+    out, attn = m(s, **args)
+    out.square().mean().backward()
+    assert torch.isfinite(s.grad).all() and float(s.grad.abs().max()) > 0
+    frac_zero = float(((attn == 0) & (~mask.to(cuda))[:, None, :, None] & (~mask.to(cuda))[:, None, None, :]).float().mean())
+    assert frac_zero > 0.02                                   # some real weights were dropped
+    m.eval()
+    with torch.no_grad():
+        a, _ = m(src.to(cuda), **args)
+        b, _ = m(src.to(cuda), **args)
+    assert torch.equal(a, b)

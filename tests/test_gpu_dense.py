@@ -72,12 +72,18 @@ def test_linear_parity(cuda, side, tc, T, fin, fout, relu, with_res):
     assert rel_err(bd.grad, br.grad) <= TOL
 
 
-@pytest.fixture(params=[True, False], ids=["tensor_cores", "library_gemm"])
-def tc(request):
+@pytest.fixture(params=["tcgen05", "mma_sync", "library_gemm"])
+def tc(request, monkeypatch):
+    """tcgen05: csrc/linear_tc5.cu where the shape is a multiple of its tiles (else mma.sync);  mma_sync:
+    csrc/dense_tc.cu only;  library_gemm: torch / cuBLAS."""
     from feta_tmlr_b200 import ops
     old = ops.LINEAR_TENSOR_CORES
-    ops.LINEAR_TENSOR_CORES = request.param
-    yield request.param
+    ops.LINEAR_TENSOR_CORES = request.param != "library_gemm"
+    if request.param == "mma_sync":
+        monkeypatch.setenv("FETA_LINEAR_NO_TC5", "1")
+    else:
+        monkeypatch.delenv("FETA_LINEAR_NO_TC5", raising=False)
+    yield request.param != "library_gemm"
     ops.LINEAR_TENSOR_CORES = old
 
 
@@ -229,3 +235,26 @@ def test_add_batch_norm_parity(cuda, T, D, scaled, weighted):
     assert rel_err(bn.weight.grad, bn_ref.weight.grad) < TOL and rel_err(bn.bias.grad, bn_ref.bias.grad) < TOL
     assert rel_err(bn.running_mean, bn_ref.running_mean) < 1e-5 and rel_err(bn.running_var, bn_ref.running_var) < 1e-5
     assert int(bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("T", [1, 127, 128, 129, 4736, 12032])
+@pytest.mark.parametrize("fin,fout", [(64, 192), (64, 64), (64, 128), (128, 64), (192, 64), (256, 128)])
+def test_linear_tcgen05_only_switch(cuda, monkeypatch, T, fin, fout):
+    """FETA_LINEAR_TC5 alone (library GEMM elsewhere): forward with bias + ReLU, dX with ReLU mask and residual."""
+    from feta_tmlr_b200 import ops
+    monkeypatch.setattr(ops, "LINEAR_TC5", True)
+    monkeypatch.setattr(ops, "LINEAR_TENSOR_CORES", False)
+    assert ops.linear_tc_enabled(fin, fout)
+    g = torch.Generator().manual_seed(T + fin + fout)
+    x = torch.randn(T, fin, generator=g)
+    W, b = torch.randn(fout, fin, generator=g) * 0.2, torch.randn(fout, generator=g)
+    go, gr = torch.randn(T, fout, generator=g), torch.randn(T, fin, generator=g)
+    xr, Wr, br = (t.double().requires_grad_() for t in (x, W, b))
+    ref = torch.relu(torch.nn.functional.linear(xr, Wr, br))
+    ((ref * go.double()).sum() + (xr * gr.double()).sum()).backward()
+    xd, Wd, bd = (t.to(cuda).requires_grad_() for t in (x, W, b))
+    y, res = ops.linear_res(xd, Wd, bd, relu=True)
+    ((y * go.to(cuda)).sum() + (res * gr.to(cuda)).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_err(y, ref) < TOL
+    assert rel_err(xd.grad, xr.grad) < TOL and rel_err(Wd.grad, Wr.grad) < TOL and rel_err(bd.grad, br.grad) < TOL
