@@ -44,6 +44,10 @@ SIGNATURES = {
     "feta_linear_wgrad": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_int64, c_int, c_int, _P]),
     "feta_linear_tc_supported": (c_int, [c_int, c_int]),
     "feta_linear_tc5_supported": (c_int, [c_int, c_int]),
+    "feta_layer_tail_supported": (c_int, [c_int, c_int]),
+    "feta_layer_tail_fwd": (c_int, [_P] * 22 + [c_int64, c_int, c_int, c_float, c_float, _P]),
+    "feta_linear_layernorm_supported": (c_int, [c_int, c_int]),
+    "feta_linear_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P]),
     "feta_linear_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "feta_linear_dx": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "feta_add_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, _P]),

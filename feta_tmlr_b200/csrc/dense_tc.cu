@@ -207,7 +207,8 @@ extern "C" int feta_linear_tc_supported(int in, int out) {
 extern "C" int feta_linear_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out,
                                int relu, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  FETA_REQUIRE(T >= 0 && feta_linear_tc_supported(in, out), "linear_fwd: unsupported shape T=%lld in=%d out=%d",
+  FETA_REQUIRE(T >= 0 && (feta_linear_tc_supported(in, out) || feta_linear_tc5_supported(in, out)),
+               "linear_fwd: unsupported shape T=%lld in=%d out=%d",
                (long long)T, in, out);
   if (T == 0) return FETA_OK;
   FETA_REQUIRE(X && W && Y, "linear_fwd: NULL pointer argument");
@@ -236,7 +237,8 @@ extern "C" int feta_linear_fwd(const float* X, const float* W, const float* bias
 extern "C" int feta_linear_dx(const float* dY, const float* W, const float* dres, const float* mask_src, float* dX,
                               int64_t T, int in, int out, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  FETA_REQUIRE(T >= 0 && feta_linear_tc_supported(in, out), "linear_dx: unsupported shape T=%lld in=%d out=%d",
+  FETA_REQUIRE(T >= 0 && (feta_linear_tc_supported(in, out) || feta_linear_tc5_supported(in, out)),
+               "linear_dx: unsupported shape T=%lld in=%d out=%d",
                (long long)T, in, out);
   if (T == 0) return FETA_OK;
   FETA_REQUIRE(dY && W && dX, "linear_dx: NULL pointer argument");

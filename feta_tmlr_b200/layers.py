@@ -45,7 +45,7 @@ class DiffMultiheadAttention(nn.Module):
         if bias:
             nn.init.constant_(self.out_proj.bias, 0.0)
 
-    def forward(self, src, pe=None, key_padding_mask=None, with_residual=False, drop=None):
+    def forward(self, src, pe=None, key_padding_mask=None, with_residual=False, drop=None, defer_out_proj=False):
         """src [Nmax, B, d] -> (out [Nmax, B, d], attn [B, H, Nmax, Nmax], heads [B, Nmax, H, dh]).
         ``with_residual``: a 4th output, ``src`` routed through the in-projection's autograd node (its
         gradient is then folded into the in-projection's dX GEMM, ops.LinearFn)."""
@@ -63,7 +63,8 @@ class DiffMultiheadAttention(nn.Module):
                                         float(self.head_dim) ** -0.5, self.share_qk, drop=drop)
         # the kernel writes O seq-first, so concat-heads -> out_proj needs no copy; `heads` is the
         # [B, Nmax, H, dh] view the FeTA encoder consumes (models.py:179)
-        out = self.out_proj(o_sf.view(N, B, E))
+        # defer_out_proj: the caller fuses out_proj with the degree scale, the residual and norm1 (one launch)
+        out = o_sf.view(N, B, E) if defer_out_proj else self.out_proj(o_sf.view(N, B, E))
         if with_residual:
             return out, attn, o_sf.permute(1, 0, 2, 3), res
         return out, attn, o_sf.permute(1, 0, 2, 3)
@@ -103,9 +104,13 @@ class DiffTransformerEncoderLayer(nn.Module):
             raise NotImplementedError("src_mask (attn_mask) is never passed by the reference "
                                       "(models.py:166) and is not implemented")
         fused = not self.batch_norm
+        dm = src.shape[-1]
+        no_drop = (not self.training) or self.dropout1.p == 0.0
+        fuse_ln = fused and no_drop and src.is_cuda and ops.linear_layernorm_enabled(dm, dm) \
+            and ops.linear_layernorm_enabled(self.linear1.weight.shape[0], dm)
         if fused:
             src2, attn, heads, src = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask,
-                                                    with_residual=True)
+                                                    with_residual=True, defer_out_proj=fuse_ln)
         else:
             src2, attn, heads = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask)
         if rowscale is not None:
@@ -139,6 +144,15 @@ class DiffTransformerEncoderLayer(nn.Module):
             src = src + self.dropout2(src2)
             src = self.norm2(src)
             src = src.view(-1, bsz, src.shape[-1])
+        elif fuse_ln:
+            # tcgen05 path, 4 launches per layer forward: in-projection, attention, [out_proj + degree scale +
+            # residual + norm1], linear1(+ReLU), [linear2 + residual + norm2]
+            op = self.self_attn.out_proj
+            src = ops.linear_add_layer_norm(src2, op.weight, op.bias, src, self.norm1.weight, self.norm1.bias,
+                                            self.norm1.eps, bscale=rowscale.reshape(-1))
+            h, src = ops.linear_res(src, self.linear1.weight, self.linear1.bias, relu=True, grad_premasked=True)
+            src = ops.linear_add_layer_norm(h, self.linear2.weight, self.linear2.bias, src, self.norm2.weight,
+                                            self.norm2.bias, self.norm2.eps, mask_input_grad=True)
         else:                                    # residual add fused into the LayerNorm kernels
             src = ops.add_layer_norm(src, self.dropout1(src2), self.norm1.weight, self.norm1.bias, self.norm1.eps,
                                      bscale=rowscale.reshape(-1))       # degree * src2 fused in

@@ -782,6 +782,69 @@ def _queue_side_join(device):
     torch.autograd.Variable._execution_engine.queue_callback(_join)
 
 
+def _linear_wgrad(dy, x, out_f, in_f, has_bias):
+    """dW = dy^T x, db = colsum(dy) through feta_linear_wgrad -- on the weight-gradient side stream when a caller
+    opted in (wgrad_side_stream), else on the current stream."""
+    lib = _lib.load()
+    dy2 = _f32c(dy.reshape(-1, out_f))
+    x2 = _f32c(x.reshape(-1, in_f))
+    T = dy2.shape[0]
+    if out_f % 4 or in_f % 4:
+        return dy2.t().matmul(x2), (dy2.sum(0) if has_bias else None)
+    S = lib.feta_linear_wgrad_slices(T)
+    n_part = S * (out_f * in_f + out_f)
+    partial = torch.empty(n_part, dtype=torch.float32, device=dy.device)
+    dw = torch.empty((out_f, in_f), dtype=torch.float32, device=dy.device)
+    db = torch.empty(out_f, dtype=torch.float32, device=dy.device) if has_bias else None
+    cnt = _counters(dy.device)
+    if WGRAD_SIDE_STREAM:
+        main = torch.cuda.current_stream(dy.device)
+        side = _side_stream(dy.device)
+        side.wait_stream(main)                      # dy, x (and the buffers above) are ready
+        check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
+                                    _ptr(cnt), T, out_f, in_f, side.cuda_stream), "feta_linear_wgrad")
+        for t in (dy2, x2, partial, dw, db):        # allocator: not reusable until `side` passed here
+            if t is not None:
+                t.record_stream(side)
+        _queue_side_join(dy.device)
+    else:
+        check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
+                                    _ptr(cnt), T, out_f, in_f, _stream()), "feta_linear_wgrad")
+    return dw, db
+
+
+def _layernorm_backward(dy, z, mean, rstd, gamma, bscale, want_dbs):
+    """(dz, dbs, dgamma, dbeta) of y = LayerNorm(z) * gamma + beta with z = a + bscale * b."""
+    lib = _lib.load()
+    D = z.shape[-1]
+    T = z.numel() // D
+    dy = _f32c(dy)
+    dz = torch.empty_like(z)
+    dbs = torch.empty_like(z) if want_dbs else None
+    nblk = lib.feta_add_layernorm_bwd_blocks(T)
+    partial = torch.empty(nblk * 2 * D, dtype=torch.float32, device=z.device)
+    dg = torch.empty(D, dtype=torch.float32, device=z.device)
+    db = torch.empty(D, dtype=torch.float32, device=z.device)
+    cnt = _counters(z.device)
+    if WGRAD_SIDE_STREAM:       # dz on the critical path; the dgamma / dbeta fold on the side stream
+        check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale),
+                                         _ptr(dz), _ptr(dbs), None, None, _ptr(partial), None, T, D, _stream()),
+              "feta_add_layernorm_bwd")
+        main = torch.cuda.current_stream(z.device)
+        side = _side_stream(z.device)
+        side.wait_stream(main)
+        check(lib.feta_add_layernorm_bwd_fold(_ptr(partial), T, D, _ptr(dg), _ptr(db), side.cuda_stream),
+              "feta_add_layernorm_bwd_fold")
+        for t in (partial, dg, db):
+            t.record_stream(side)
+        _queue_side_join(z.device)
+    else:
+        check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale),
+                                         _ptr(dz), _ptr(dbs), _ptr(dg), _ptr(db), _ptr(partial),
+                                         cnt.data_ptr() + 256 * 4, T, D, _stream()), "feta_add_layernorm_bwd")
+    return dz, dbs, dg, db
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b.  Forward and dX are library GEMMs; dW / db (reductions over the ~5k-token axis
     the libraries under-parallelise here) go through feta_linear_wgrad."""
@@ -846,32 +909,7 @@ class LinearFn(torch.autograd.Function):
                 if dres is not None:
                     dx = dx + dres
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dy2 = _f32c(dy.reshape(-1, out_f))
-            x2 = _f32c(x.reshape(-1, in_f))
-            T = dy2.shape[0]
-            if out_f % 4 or in_f % 4:
-                dw = dy2.t().matmul(x2)
-                db = dy2.sum(0) if ctx.has_bias else None
-            else:
-                S = lib.feta_linear_wgrad_slices(T)
-                n_part = S * (out_f * in_f + out_f)
-                partial = torch.empty(n_part, dtype=torch.float32, device=dy.device)
-                dw = torch.empty((out_f, in_f), dtype=torch.float32, device=dy.device)
-                db = torch.empty(out_f, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-                cnt = _counters(dy.device)
-                if WGRAD_SIDE_STREAM:
-                    main = torch.cuda.current_stream(dy.device)
-                    side = _side_stream(dy.device)
-                    side.wait_stream(main)                      # dy, x (and the buffers above) are ready
-                    check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
-                                                _ptr(cnt), T, out_f, in_f, side.cuda_stream), "feta_linear_wgrad")
-                    for t in (dy2, x2, partial, dw, db):        # allocator: not reusable until `side` passed here
-                        if t is not None:
-                            t.record_stream(side)
-                    _queue_side_join(dy.device)
-                else:
-                    check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
-                                                _ptr(cnt), T, out_f, in_f, _stream()), "feta_linear_wgrad")
+            dw, db = _linear_wgrad(dy, x, out_f, in_f, ctx.has_bias)
         return dx, dw, db, None, None, None, None
 
 
@@ -915,34 +953,8 @@ class AddLayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        lib = _lib.load()
         z, mean, rstd, gamma, bscale = ctx.saved_tensors
-        D = z.shape[-1]
-        T = z.numel() // D
-        dy = _f32c(dy)
-        dz = torch.empty_like(z)
-        dbs = torch.empty_like(z) if (ctx.has_b and bscale is not None) else None
-        nblk = lib.feta_add_layernorm_bwd_blocks(T)
-        partial = torch.empty(nblk * 2 * D, dtype=torch.float32, device=z.device)
-        dg = torch.empty(D, dtype=torch.float32, device=z.device)
-        db = torch.empty(D, dtype=torch.float32, device=z.device)
-        cnt = _counters(z.device)
-        if WGRAD_SIDE_STREAM:       # dz on the critical path; the dgamma / dbeta fold on the side stream
-            check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale),
-                                             _ptr(dz), _ptr(dbs), None, None, _ptr(partial), None, T, D, _stream()),
-                  "feta_add_layernorm_bwd")
-            main = torch.cuda.current_stream(z.device)
-            side = _side_stream(z.device)
-            side.wait_stream(main)
-            check(lib.feta_add_layernorm_bwd_fold(_ptr(partial), T, D, _ptr(dg), _ptr(db), side.cuda_stream),
-                  "feta_add_layernorm_bwd_fold")
-            for t in (partial, dg, db):
-                t.record_stream(side)
-            _queue_side_join(z.device)
-        else:
-            check(lib.feta_add_layernorm_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale),
-                                             _ptr(dz), _ptr(dbs), _ptr(dg), _ptr(db), _ptr(partial),
-                                             cnt.data_ptr() + 256 * 4, T, D, _stream()), "feta_add_layernorm_bwd")
+        dz, dbs, dg, db = _layernorm_backward(dy, z, mean, rstd, gamma, bscale, ctx.has_b and bscale is not None)
         grad_b = None
         if ctx.has_b:
             grad_b = dbs if dbs is not None else dz
@@ -951,6 +963,62 @@ class AddLayerNormFn(torch.autograd.Function):
 
 def add_layer_norm(a, b, gamma, beta, eps=1e-5, bscale=None):
     return AddLayerNormFn.apply(a, b, bscale, gamma, beta, eps)
+
+
+class LinearAddLayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(res + bscale * (x W^T + b)) * gamma + beta in ONE launch (csrc/linear_tc5.cu: tcgen05 GEMM with
+    the degree scale, residual add and LayerNorm in its epilogue); backward = LayerNorm backward, then the Linear's
+    dX (tcgen05, optional ReLU mask of its input) and its weight gradients (side stream when opted in)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, res, bscale, gamma, beta, eps, mask_input_grad):
+        _need_cuda(x, weight, bias, res, gamma, beta)
+        lib = _lib.load()
+        out_f, in_f = weight.shape
+        x2 = _f32c(x.reshape(-1, in_f))
+        res2 = _f32c(res.reshape(-1, out_f))
+        w = _f32c(weight)
+        bc = None if bias is None else _f32c(bias)
+        bscale = None if bscale is None else _f32c(bscale)
+        gamma, beta = _f32c(gamma), _f32c(beta)
+        T = x2.shape[0]
+        y = torch.empty(res.shape, dtype=torch.float32, device=x.device)
+        z = torch.empty(res.shape, dtype=torch.float32, device=x.device)
+        mean = torch.empty(T, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(T, dtype=torch.float32, device=x.device)
+        check(lib.feta_linear_layernorm_fwd(_ptr(x2), _ptr(w), _ptr(bc), _ptr(res2), _ptr(bscale), _ptr(gamma),
+                                            _ptr(beta), _ptr(y), _ptr(z), _ptr(mean), _ptr(rstd), T, in_f, out_f,
+                                            float(eps), _stream()), "feta_linear_layernorm_fwd")
+        ctx.save_for_backward(x, w, z, mean, rstd, gamma, bscale)
+        ctx.has_bias = bias is not None
+        ctx.mask_in = bool(mask_input_grad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, w, z, mean, rstd, gamma, bscale = ctx.saved_tensors
+        out_f, in_f = w.shape
+        dz, dbs, dg, dbeta = _layernorm_backward(dy, z, mean, rstd, gamma, bscale, bscale is not None)
+        dlin = dbs if dbs is not None else dz                   # gradient of the Linear's output
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dl2 = _f32c(dlin.reshape(-1, out_f))
+            x2 = _f32c(x.reshape(-1, in_f)) if ctx.mask_in else None
+            dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+            check(lib.feta_linear_dx(_ptr(dl2), _ptr(w), None, _ptr(x2), _ptr(dx), dl2.shape[0], in_f, out_f,
+                                     _stream()), "feta_linear_dx")
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = _linear_wgrad(dlin, x, out_f, in_f, ctx.has_bias)
+        return dx, dw, db, dz.view(z.shape), None, dg, dbeta, None, None
+
+
+def linear_layernorm_enabled(in_f, out_f):
+    return bool(LINEAR_TC5 and _lib.load().feta_linear_layernorm_supported(int(in_f), int(out_f)))
+
+
+def linear_add_layer_norm(x, weight, bias, res, gamma, beta, eps=1e-5, bscale=None, mask_input_grad=False):
+    return LinearAddLayerNormFn.apply(x, weight, bias, res, bscale, gamma, beta, eps, mask_input_grad)
 
 
 class AddBatchNormFn(torch.autograd.Function):

@@ -248,6 +248,25 @@ int feta_add_layernorm_bwd_fold(const float* partial, int64_t T, int D, float* d
  *                     dres [T,in] (may be NULL): gradient of the residual connection that branches off X.
  * Shapes: in, out multiples of 8, <= 256 (feta_linear_tc_supported); other shapes: use a library GEMM.
  * --------------------------------------------------------------------------------------- */
+/* Linear + degree scale + residual + LayerNorm in ONE launch on the tcgen05 path (out = 64 = d_model, in a multiple
+ * of 64):  z = res + bscale[row] * (X . W^T + b)  (bscale, b may be NULL);  y = LayerNorm(z) * gamma + beta.
+ * z, mean, rstd are what feta_add_layernorm_bwd takes; the Linear's own backward is feta_linear_dx / feta_linear_wgrad. */
+int feta_linear_layernorm_supported(int in, int out);
+int feta_linear_layernorm_fwd(const float* X, const float* W, const float* bias, const float* res, const float* bscale,
+                              const float* gamma, const float* beta, float* y, float* z, float* mean, float* rstd,
+                              int64_t T, int in, int out, float eps, void* stream);
+/* The tail of an encoder layer in ONE launch (d_model 64, dim_feedforward 128): three chained tcgen05 GEMMs per
+ * 128-token tile, activations stay on the SM between them:
+ *   z1 = res + bscale*(o Wo^T + bo); y1 = LN1(z1); h = relu(y1 W1^T + b1); z2 = y1 + h W2^T + b2; y2 = LN2(z2).
+ * o, res [T, 64]; bscale [T] or NULL; Wo [64,64], W1 [128,64], W2 [64,128] as nn.Linear stores them; biases may be
+ * NULL.  Everything the backward pass needs is written: z1, mean1, rstd1, y1, h, z2, mean2, rstd2 (the backward is
+ * feta_add_layernorm_bwd / feta_linear_dx / feta_linear_wgrad per Linear). */
+int feta_layer_tail_supported(int d_model, int dff);
+int feta_layer_tail_fwd(const float* o, const float* res, const float* bscale, const float* Wo, const float* bo,
+                        const float* g1, const float* be1, const float* W1, const float* b1, const float* W2,
+                        const float* b2, const float* g2, const float* be2, float* z1, float* mean1, float* rstd1,
+                        float* y1, float* h, float* z2, float* mean2, float* rstd2, float* y2, int64_t T, int d_model,
+                        int dff, float eps1, float eps2, void* stream);
 /* 1 when feta_linear_fwd / feta_linear_dx run this (in, out) pair on the tcgen05 path (csrc/linear_tc5.cu:
  * 128 x 64 x 64 tiles, 3xTF32 in TMEM): both multiples of 64. */
 int feta_linear_tc5_supported(int in, int out);

@@ -39,11 +39,13 @@ def _pair(cuda, d, H, seed, **kw):
     return o, m
 
 
-@pytest.fixture(params=[False, True], ids=["cuda_core", "tcgen05"])
+@pytest.fixture(params=["cuda_core", "tcgen05", "tcgen05_linear"])
 def tensor_cores(request, monkeypatch):
-    """Run the test through both attention forward kernels (fp32 CUDA-core / tcgen05 3xTF32)."""
+    """Run the test through both attention forward kernels (fp32 CUDA-core / tcgen05 3xTF32), and with the layer's
+    Linear layers on the tcgen05 path (csrc/linear_tc5.cu, fused Linear + residual + LayerNorm)."""
     from feta_tmlr_b200 import ops
-    monkeypatch.setattr(ops, "ATTN_TENSOR_CORES", request.param)
+    monkeypatch.setattr(ops, "ATTN_TENSOR_CORES", request.param == "tcgen05")
+    monkeypatch.setattr(ops, "LINEAR_TC5", request.param == "tcgen05_linear")
     return request.param
 
 

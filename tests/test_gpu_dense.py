@@ -249,12 +249,49 @@ def test_linear_tcgen05_only_switch(cuda, monkeypatch, T, fin, fout):
     x = torch.randn(T, fin, generator=g)
     W, b = torch.randn(fout, fin, generator=g) * 0.2, torch.randn(fout, generator=g)
     go, gr = torch.randn(T, fout, generator=g), torch.randn(T, fin, generator=g)
-    xr, Wr, br = (t.double().requires_grad_() for t in (x, W, b))
-    ref = torch.relu(torch.nn.functional.linear(xr, Wr, br))
-    ((ref * go.double()).sum() + (xr * gr.double()).sum()).backward()
     xd, Wd, bd = (t.to(cuda).requires_grad_() for t in (x, W, b))
     y, res = ops.linear_res(xd, Wd, bd, relu=True)
+    xr, Wr, br = (t.double().requires_grad_() for t in (x, W, b))
+    # the ReLU mask of the fp64 reference is taken from the kernel's output: a pre-activation within fp32 rounding of
+    # zero may legitimately fall on either side (1.5 M outputs at the largest shape)
+    ref = torch.nn.functional.linear(xr, Wr, br) * (y.detach().cpu() > 0).double()
+    ((ref * go.double()).sum() + (xr * gr.double()).sum()).backward()
     ((y * go.to(cuda)).sum() + (res * gr.to(cuda)).sum()).backward()
     torch.cuda.synchronize()
     assert rel_err(y, ref) < TOL
     assert rel_err(xd.grad, xr.grad) < TOL and rel_err(Wd.grad, Wr.grad) < TOL and rel_err(bd.grad, br.grad) < TOL
+
+
+@pytest.mark.parametrize("T", [1, 130, 4736])
+@pytest.mark.parametrize("fin", [64, 128])
+@pytest.mark.parametrize("scaled,masked", [(True, False), (False, True)])
+def test_linear_add_layer_norm_fused(cuda, side, T, fin, scaled, masked):
+    """One-launch [Linear + degree scale + residual + LayerNorm] (tcgen05) vs fp64 PyTorch: y and every gradient;
+    `masked`: the Linear's input is a ReLU output whose mask is applied in the dX epilogue."""
+    from feta_tmlr_b200 import ops
+    D = 64
+    g = torch.Generator().manual_seed(T + fin)
+    x = torch.randn(T, fin, generator=g)
+    if masked:
+        x = torch.relu(x)
+    W, b = torch.randn(D, fin, generator=g) * 0.2, torch.randn(D, generator=g)
+    res = torch.randn(T, D, generator=g)
+    gamma, beta = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g)
+    bs = torch.rand(T, generator=g) + 0.5 if scaled else None
+    go = torch.randn(T, D, generator=g)
+    pre = torch.randn(T, fin, generator=g)                     # pre-activation whose ReLU is x (masked case)
+    xr, Wr, br, rr, gr, ber = (t.double().requires_grad_() for t in (x, W, b, res, gamma, beta))
+    lin = torch.nn.functional.linear(xr, Wr, br)
+    z = rr + (lin if bs is None else bs.double().unsqueeze(1) * lin)
+    ref = torch.nn.functional.layer_norm(z, (D,), gr, ber, 1e-5)
+    ref.backward(go.double())
+    xd, Wd, bd, rd, gd, bed = (t.to(cuda).requires_grad_() for t in (x, W, b, res, gamma, beta))
+    y = ops.linear_add_layer_norm(xd, Wd, bd, rd, gd, bed, 1e-5, bscale=None if bs is None else bs.to(cuda),
+                                  mask_input_grad=masked)
+    y.backward(go.to(cuda))
+    torch.cuda.synchronize()
+    assert rel_err(y, ref) < TOL
+    want_dx = xr.grad * (x > 0).double() if masked else xr.grad
+    assert rel_err(xd.grad, want_dx) < TOL
+    for d_, r_ in ((Wd, Wr), (bd, br), (rd, rr), (gd, gr), (bed, ber)):
+        assert rel_err(d_.grad, r_.grad) < TOL

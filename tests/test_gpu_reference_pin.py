@@ -153,8 +153,25 @@ def _loss(name, out, labels):
     return F.binary_cross_entropy_with_logits(out.reshape(-1), labels.reshape(-1).to(out.dtype))
 
 
+@pytest.fixture(params=["library_gemm", "tcgen05_linear"])
+def linear_path(request, monkeypatch):
+    """The layer's Linear layers through the library GEMM or through csrc/linear_tc5.cu (tcgen05, incl. the fused
+    Linear + residual + LayerNorm launches)."""
+    from feta_tmlr_b200 import ops
+    monkeypatch.setattr(ops, "LINEAR_TC5", request.param == "tcgen05_linear")
+    return request.param
+
+
+# Stated tolerance of the opt-in tcgen05 Linear path for GRADIENTS: a 3xTF32 product (hi.hi + hi.lo + lo.hi, the
+# lo parts themselves rounded to 11 bits) carries ~2^-21.5 relative error against 2^-24 of an fp32 FMA, and the
+# worst-conditioned gradient of the set (PATTERN `encoder.gcn.weight`: a sum with heavy cancellation behind the
+# softmax of 188-node graphs) turns that into 2.9e-4 where the fp32 library GEMM sits just under 1e-4.
+# Forward outputs, filter coefficients and the loss keep 1e-4 on both paths.
+GRAD_TOL = {"library_gemm": TOL, "tcgen05_linear": 5e-4}
+
+
 @pytest.mark.parametrize("tag", MODEL_FIXTURES)
-def test_model_matches_reference_run(cuda, tag):
+def test_model_matches_reference_run(cuda, tag, linear_path):
     """Whole models at the BASELINE shapes (full d=64, reference hyper-parameters): the reference ran its literal
     op sequence (host loop, all-pairs GCNConv, per-node filter materialisation) in fp64; the CUDA path runs with
     its default switches in fp32."""
@@ -180,7 +197,7 @@ def test_model_matches_reference_run(cuda, tag):
     for k, want in fx['grads'].items():
         assert k in got, k
         try:
-            check_grad(got[k], want, TOL, k, floor=floor)
+            check_grad(got[k], want, GRAD_TOL[linear_path], k, floor=floor)
         except AssertionError as e:
             worst = max(worst, (k, e.args[0][-1]), key=lambda t: t[1])
     assert worst[1] == 0.0, worst
