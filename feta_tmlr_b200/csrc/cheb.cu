@@ -32,6 +32,10 @@ int cheb_bwd_dense_try(const float* dout, const float* x, const int32_t* rowptr,
 int cheb_fwd_warp_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                       const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias,
                       float* out, int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
+// csrc/cheb_lane.cu: second-generation warp-per-graph forward (F = 8, 16; K <= 4; graphs of <= 64 rows)
+int cheb_fwd_lane_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                      const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias,
+                      float* out, int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
 
 template <int F>
 constexpr int fused_max_threads() {
@@ -436,6 +440,9 @@ extern "C" int feta_cheb_fwd(const float* x, const int32_t* rowptr, const int32_
     if (rc <= 0) return rc;
   }
   if (fin == fout && block_diagonal && aligned && getenv("FETA_CHEB_NO_WARP_KERNEL") == nullptr) {
+    rc = cheb_fwd_lane_try(x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, fin, max_nodes,
+                           plan_meta, st);
+    if (rc <= 0) return rc;
     rc = cheb_fwd_warp_try(x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G, K, fin, max_nodes,
                            plan_meta, st);
     if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = shape not eligible

@@ -205,19 +205,23 @@ def test_guard_refusal_is_visible(cuda, sizes):
         plan.validate()
 
 
-@pytest.mark.parametrize("family", ["tile", "no_dense", "no_tile_no_dense", "chunk_only"])
+@pytest.mark.parametrize("family", ["tile", "no_dense", "no_tile_no_dense", "warp_v1", "chunk_only"])
 @pytest.mark.parametrize("F,K,sizes", [(16, 4, [5, 7, 1, 4, 38, 23, 1, 2, 64]), (8, 4, [30, 31, 32, 33, 9, 12] * 6),
                                        (16, 3, [90, 17, 128, 1, 66]), (8, 2, [200, 129, 256, 70]),
                                        (16, 4, [188, 44, 120, 97, 188])])
 def test_cheb_every_kernel_family(cuda, monkeypatch, family, F, K, sizes):
-    """The dispatcher picks one of four forward families (tcgen05 tile kernel, CTA-per-graph dense kernel,
-    warp-per-graph kernel, chunk kernel) by shape; every family is forced here on shapes the others would take."""
+    """The dispatcher picks one of five forward families (tcgen05 tile kernel, CTA-per-graph dense kernel, the two
+    generations of the warp-per-graph kernel -- cheb_lane.cu, cheb_warp.cu --, chunk kernel) by shape; every family is
+    forced here on shapes the others would take."""
     env = {"tile": {"FETA_CHEB_TILE": "1", "FETA_CHEB_NO_DENSE_KERNEL": "1"},
            "no_dense": {"FETA_CHEB_NO_DENSE_KERNEL": "1"},
            "no_tile_no_dense": {"FETA_CHEB_NO_DENSE_KERNEL": "1", "FETA_CHEB_NO_TILE_KERNEL": "1"},
+           "warp_v1": {"FETA_CHEB_NO_DENSE_KERNEL": "1", "FETA_CHEB_NO_TILE_KERNEL": "1",
+                       "FETA_CHEB_NO_LANE_KERNEL": "1"},
            "chunk_only": {"FETA_CHEB_NO_DENSE_KERNEL": "1", "FETA_CHEB_NO_TILE_KERNEL": "1",
                           "FETA_CHEB_NO_WARP_KERNEL": "1"}}[family]
-    for k in ("FETA_CHEB_TILE", "FETA_CHEB_NO_DENSE_KERNEL", "FETA_CHEB_NO_TILE_KERNEL", "FETA_CHEB_NO_WARP_KERNEL"):
+    for k in ("FETA_CHEB_TILE", "FETA_CHEB_NO_DENSE_KERNEL", "FETA_CHEB_NO_TILE_KERNEL", "FETA_CHEB_NO_WARP_KERNEL",
+              "FETA_CHEB_NO_LANE_KERNEL"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
