@@ -32,6 +32,12 @@ int cheb_bwd_dense_try(const float* dout, const float* x, const int32_t* rowptr,
 int cheb_fwd_warp_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                       const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias,
                       float* out, int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
+int cheb_bwd_dx_lane_try(const float* dout, const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t,
+                         const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, float* dx, int64_t R,
+                         int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
+int cheb_bwd_dtheta_lane_try(const float* x, const float* dout, const int32_t* rowptr, const int32_t* colidx,
+                             const float* vals, const int32_t* graph_ptr, float* dtheta, int64_t sk, int64_t sg,
+                             int64_t R, int64_t G, int K, int F, int max_nodes, int32_t* meta, cudaStream_t st);
 // csrc/cheb_lane.cu: second-generation warp-per-graph forward (F = 8, 16; K <= 4; graphs of <= 64 rows)
 int cheb_fwd_lane_try(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                       const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias,
@@ -521,10 +527,18 @@ extern "C" int feta_cheb_bwd(const float* dout, const float* x, const int32_t* r
     if (rc < 0) return rc;
     if (rc == 0) return FETA_OK;
   }
+  const bool lane_ok = fusable && getenv("FETA_CHEB_NO_WARP_KERNEL") == nullptr;
   if (dx != nullptr) {
     FusedCfg cfg = fused_config(fin, max_nodes, 2, false);
     bool done = false;
-    if (fusable && cfg.ok) {
+    if (lane_ok) {   // warp-per-graph kernel (graphs <= 64 rows): the forward recursion over L^T against Theta^T
+      rc = cheb_bwd_dx_lane_try(dout, rowptr_t, colidx_t, vals_t, graph_ptr, theta, sk, sg, dx, R, G, K, fin, max_nodes,
+                                plan_meta, st);
+      if (rc < 0) return rc;
+      done = rc == 0;
+      rc = 0;
+    }
+    if (!done && fusable && cfg.ok) {
       FETA_DISPATCH_F(fin, {
         rc = launch_bwd_dx<FF>(cfg, dout, rowptr_t, colidx_t, vals_t, graph_ptr, row_graph, theta, sk, sg, dx, R, K,
                                plan_meta, G, max_nodes, st);
@@ -556,7 +570,14 @@ extern "C" int feta_cheb_bwd(const float* dout, const float* x, const int32_t* r
   if (dtheta != nullptr) {
     FusedCfg cfg = fused_config(fin, max_nodes, 3, true);
     bool done = false;
-    if (fusable && cfg.ok) {
+    if (lane_ok) {
+      rc = cheb_bwd_dtheta_lane_try(x, dout, rowptr, colidx, vals, graph_ptr, dtheta, sk, sg, R, G, K, fin, max_nodes,
+                                    plan_meta, st);
+      if (rc < 0) return rc;
+      done = rc == 0;
+      rc = 0;
+    }
+    if (!done && fusable && cfg.ok) {
       FETA_DISPATCH_F(fin, {
         rc = launch_bwd_dtheta<FF>(cfg, x, dout, rowptr, colidx, vals, graph_ptr, row_graph, dtheta, sk, sg, R, K,
                                    plan_meta, G, max_nodes, st);

@@ -2,6 +2,4 @@
 timeout 900 python -m pytest tests/test_gpu_cheb.py tests/test_gpu_reference_pin.py tests/test_gpu_golden.py tests/test_gpu_model.py -m gpu -q -x --timeout 600 2>&1 | tail -15
 for f in 16 8; do
   echo "== sweep F=$f lane"; timeout 300 python bench.py --sweep-only --sweep-f $f 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:(v['achieved'],v['frac'],v['ms_per_launch']) for k,v in d.items()})"
-  echo "== sweep F=$f warp v1"; FETA_CHEB_NO_LANE_KERNEL=1 timeout 300 python bench.py --sweep-only --sweep-f $f 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:(v['achieved'],v['frac'],v['ms_per_launch']) for k,v in d.items()})"
 done
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:cheb_fwd_lane -c 1 -o gpurun_out/r2_lane_f16 python bench.py --sweep-only --sweep-f 16 --sweep-rows 1500000 > gpurun_out/ncu_lane.log 2>&1; tail -2 gpurun_out/ncu_lane.log
