@@ -277,19 +277,19 @@ def cheb_sweep(dev, hbm_gbs, F=16, K=4, target_rows=3_000_000, backward=True):
                 "traffic": tr, "traffic_source": why, "ms_per_launch": round(ms, 4), "algorithmic_bytes": int(nbytes)}
     out = {}
     ms = _time_loop(lambda: ops.cheb_filter(x, theta, bias, plan))
-    out["fwd"] = entry("cheb_fwd_warp_kernel<%d,2>" % F, ms, cheb_algorithmic_bytes(R, F, nnz, G, K),
+    out["fwd"] = entry("cheb_fwd_lane_kernel<%d,2,%d,fwd>" % (F, K), ms, cheb_algorithmic_bytes(R, F, nnz, G, K),
                        "cheb_sweep_fwd_f%d_%d" % (F, target_rows))
     if backward:
         xr = x.detach().requires_grad_()
         y = ops.cheb_filter(xr, theta, bias, plan)
         ms = _time_loop(lambda: torch.autograd.grad(y, xr, go, retain_graph=True))
-        out["bwd_dx"] = entry("cheb_bwd_dx_fused_kernel<%d>" % F, ms, cheb_bwd_bytes(R, F, nnz, G, K),
+        out["bwd_dx"] = entry("cheb_fwd_lane_kernel<%d,2,%d,transposed> (dx)" % (F, K), ms, cheb_bwd_bytes(R, F, nnz, G, K),
                               "cheb_sweep_dx_f%d_%d" % (F, target_rows))
         del y, xr
         tr_ = theta.detach().requires_grad_()
         y = ops.cheb_filter(x, tr_, bias, plan)
         ms = _time_loop(lambda: torch.autograd.grad(y, tr_, go, retain_graph=True))
-        out["bwd_dtheta"] = entry("cheb_bwd_dtheta_fused_kernel<%d>" % F, ms, cheb_bwd_bytes(R, F, nnz, G, K),
+        out["bwd_dtheta"] = entry("cheb_dtheta_lane_kernel<%d,2,%d>" % (F, K), ms, cheb_bwd_bytes(R, F, nnz, G, K),
                                   "cheb_sweep_dtheta_f%d_%d" % (F, target_rows))
     return out
 
@@ -611,7 +611,7 @@ def main():
                         "largest share of the step among this repo's kernels (profiles/); " + small % (attn_bytes / 1e6),
                         "attn_fwd_%s" % args.config)
         roofline["attn_bwd_us_per_launch"] = round(kern_us["attn_bwd"], 2)
-        roofline_cheb = roof("cheb_fwd_%s_kernel<%d>" % ("warp" if nm <= 64 else "graph", dh), cheb_bytes,
+        roofline_cheb = roof("cheb_fwd_%s_kernel<%d>" % ("lane" if nm <= 64 else "graph", dh), cheb_bytes,
                              kern_us["cheb_fwd"], 1,
                              small % (cheb_bytes / 1e6) + "; roofline_sweep is the same kernel family on an HBM-sized "
                              "batch; rows = %d (padded-domain static layout)" % res["cheb_rows"],

@@ -93,6 +93,9 @@ struct Cfg {
 };
 
 constexpr uint32_t kBarBytes = 64;
+// lanes past a graph's last row still run the (branch-free) gather on their own row's address with weight 0; that
+// address may lie up to 64 rows past a slab -- inside the next warp's region, or, for the last warp, this pad
+constexpr size_t kTailPad = 4096;
 
 static inline uint32_t csr_bytes_of(int nnz_cap) { return (uint32_t)align_up((size_t)(nnz_cap + 8) * 4, 64); }
 
@@ -100,16 +103,21 @@ static Cfg config(int F, int K, int max_nodes) {
   Cfg c{0, 0, 0, 0, 0, 0, false};
   if (!(F == 8 || F == 16) || K < 1 || K > 4 || max_nodes < 1 || max_nodes > 64) return c;
   c.rpl = max_nodes <= 32 ? 1 : 2;
-  c.rows_cap = (max_nodes + 15) / 16 * 16;       // whole m16 tiles
-  c.nnz_cap = c.rows_cap * 4;
+  // slabs hold whole 8-row groups; the last m16 tile of a graph may READ up to 8 rows past its slab (the next
+  // region of the same warp; those output rows are never stored) but nothing is written there
+  c.rows_cap = (max_nodes + 7) / 8 * 8;
+  c.nnz_cap = c.rows_cap * 3;                     // molecules: ~2.2 entries per row; larger slices are read through L2
+  if (const char* e = getenv("FETA_LANE_NNZ_PER_ROW")) c.nnz_cap = c.rows_cap * atoi(e);
   const size_t slab = (size_t)c.rows_cap * F * 4;
   const size_t stage = slab + 2 * csr_bytes_of(c.nnz_cap);
   c.per_warp = (uint32_t)align_up(kBarBytes + slab + (size_t)K * F * F * 4 + 2 * stage, 128);
-  int w = (int)((227 * 1024) / c.per_warp);
-  if (w > (c.rpl == 1 ? 16 : 12)) w = c.rpl == 1 ? 16 : 12;
+  int w = (int)((227 * 1024 - kTailPad) / c.per_warp);
+  int wmax = 16;
+  if (const char* e = getenv("FETA_LANE_WARPS")) wmax = atoi(e);
+  if (w > wmax) w = wmax;
   if (w < 4) return c;
   c.warps = w;
-  c.smem = (size_t)c.per_warp * w;
+  c.smem = (size_t)c.per_warp * w + kTailPad;
   c.ok = true;
   return c;
 }
@@ -120,9 +128,14 @@ struct GraphDesc {  // scalars of one graph, fetched ahead of use
   int e0[RPL], e1[RPL];
 };
 
-// acc[mt][nt] += T[16mt .. 16mt+15, :] . Theta_k  (3xTF32).  `ta[j]` = shared-memory byte address of this lane's
-// A-fragment word in 16-byte chunk j of row g (rows 16mt + g, + 8 are immediates); `tb` = address of
-// Theta_k[tq][g].
+// acc[mt][nt] += T[16mt .. 16mt+15, :] . Theta_k (or Theta_k^T), 3xTF32: hi.hi + hi.lo + lo.hi.
+// Forward variant, scalar fragment loads in the textbook mapping (k-step ks, half h -> contraction index
+// 8 ks + 4 h + tq).  `ta[j]` = address of this lane's word in 16-byte chunk j of row g (rows 16 mt + g, + 8 are
+// immediates); `tb` = address of Theta_k[tq][first own output channel].  F = 16 permutes the OUTPUT channels (n-tile
+// nt, column n' <-> channel 2 n' + nt) so that a lane ends up with four consecutive channels of a row.
+// Vector loads are NOT a win here: HMMA wants {a0..a3} in one aligned register quad and {b0, b1} in a pair, and
+// values that arrive through one LDS.128 / LDS.64 per row have to be MOVed into place (measured: -100 LDS,
+// +270 MOV/IMAD per graph) -- except where one load delivers the pair in order, as for Theta^T below.
 template <int F, int MTMAX>
 __device__ __forceinline__ void mma_order(float (&acc)[MTMAX][F / 8][4], const uint32_t (&ta)[F / 4], uint32_t tb,
                                           int MT) {
@@ -132,8 +145,8 @@ __device__ __forceinline__ void mma_order(float (&acc)[MTMAX][F / 8][4], const u
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      split_tf32(lds32(tb + ((8 * ks) * F + 8 * nt) * 4), bh[nt][ks][0], bl[nt][ks][0]);
-      split_tf32(lds32(tb + ((8 * ks + 4) * F + 8 * nt) * 4), bh[nt][ks][1], bl[nt][ks][1]);
+      split_tf32(lds32(tb + ((8 * ks) * F + nt) * 4), bh[nt][ks][0], bl[nt][ks][0]);
+      split_tf32(lds32(tb + ((8 * ks + 4) * F + nt) * 4), bh[nt][ks][1], bl[nt][ks][1]);
     }
 #pragma unroll
   for (int mt = 0; mt < MTMAX; ++mt) {
@@ -156,12 +169,12 @@ __device__ __forceinline__ void mma_order(float (&acc)[MTMAX][F / 8][4], const u
   }
 }
 
-// Same product against Theta_k^T (the dx kernel: dx = sum_k T_k(L^T) dOut . Theta_k^T).  The contraction index of an
-// MMA may be permuted freely as long as A and B agree; here lane (g, tq) owns the CONTIGUOUS indices
-// F/4 * tq .. F/4 * tq + F/4 - 1 (k-step ks, half h -> F/4 * tq + 2 ks + h), so its A values of a row are one
-// vector load of that row's slab and its B values one vector load of row g of Theta_k -- both conflict-free
-// (a scalar B-fragment load of Theta^T would be 8-way bank conflicted).  `ta` = address of (row g, first own
-// channel) in the slab, `tb` = address of Theta_k[g][first own channel].
+// The product against Theta_k^T (the dx kernel) with vector fragment loads: the contraction index of an MMA may be
+// permuted freely as long as A and B agree; here lane (g, tq) owns the CONTIGUOUS indices F/4 * tq .. F/4 * tq +
+// F/4 - 1 (k-step ks, half h -> F/4 * tq + 2 ks + h), so its B values are one vector load of a filter row that
+// delivers every {b0, b1} pair in register order, conflict-free (a scalar B-fragment load of Theta^T would be 8-way
+// bank conflicted); its A values are scalar loads (a vector load would have to be MOVed into the {a0..a3} quad).
+// `ta` = address of (row g, first own channel) in the slab, `tb` = address of the filter row's first own channel.
 template <int F, int MTMAX>
 __device__ __forceinline__ void mma_order_t(float (&acc)[MTMAX][F / 8][4], uint32_t ta, uint32_t tb, int MT) {
   constexpr int NT = F / 8, KS = F / 8, V = F / 4;   // V own contraction indices per lane
@@ -170,10 +183,10 @@ __device__ __forceinline__ void mma_order_t(float (&acc)[MTMAX][F / 8][4], uint3
   for (int nt = 0; nt < NT; ++nt) {
     float v[V];
     if constexpr (F == 16) {
-      const float4 t = lds128(tb + (8 * nt) * F * 4);
+      const float4 t = lds128(tb + (2 * nt) * F * 4);   // filter row 4 (g / 2) + 2 nt + g % 2, see the kernel
       v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
     } else {
-      const float2 t = lds64(tb + (8 * nt) * F * 4);
+      const float2 t = lds64(tb);
       v[0] = t.x, v[1] = t.y;
     }
 #pragma unroll
@@ -185,23 +198,14 @@ __device__ __forceinline__ void mma_order_t(float (&acc)[MTMAX][F / 8][4], uint3
 #pragma unroll
   for (int mt = 0; mt < MTMAX; ++mt) {
     if (mt < MT) {
-      float r0[V], r1[V];
-      if constexpr (F == 16) {
-        const float4 t0 = lds128(ta + (16 * mt) * F * 4), t1 = lds128(ta + (16 * mt + 8) * F * 4);
-        r0[0] = t0.x, r0[1] = t0.y, r0[2] = t0.z, r0[3] = t0.w;
-        r1[0] = t1.x, r1[1] = t1.y, r1[2] = t1.z, r1[3] = t1.w;
-      } else {
-        const float2 t0 = lds64(ta + (16 * mt) * F * 4), t1 = lds64(ta + (16 * mt + 8) * F * 4);
-        r0[0] = t0.x, r0[1] = t0.y;
-        r1[0] = t1.x, r1[1] = t1.y;
-      }
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
+        // scalar loads straight into the {a0..a3} register quad (own indices 2 ks, 2 ks + 1 of rows g, g + 8)
         uint32_t ah[4], al[4];
-        split_tf32(r0[2 * ks], ah[0], al[0]);
-        split_tf32(r1[2 * ks], ah[1], al[1]);
-        split_tf32(r0[2 * ks + 1], ah[2], al[2]);
-        split_tf32(r1[2 * ks + 1], ah[3], al[3]);
+        split_tf32(lds32(ta + (16 * mt) * F * 4 + (2 * ks) * 4), ah[0], al[0]);
+        split_tf32(lds32(ta + (16 * mt + 8) * F * 4 + (2 * ks) * 4), ah[1], al[1]);
+        split_tf32(lds32(ta + (16 * mt) * F * 4 + (2 * ks + 1) * 4), ah[2], al[2]);
+        split_tf32(lds32(ta + (16 * mt + 8) * F * 4 + (2 * ks + 1) * 4), ah[3], al[3]);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], ah, bh[nt][ks]);
 #pragma unroll
@@ -215,11 +219,119 @@ __device__ __forceinline__ void mma_order_t(float (&acc)[MTMAX][F / 8][4], uint3
 
 constexpr int kSlots = 4;   // CSR entries of a row decoded into registers once per graph
 
+// The edges of one own row, decoded once per graph: shared-memory offset of the neighbour row (chunk 0, swizzled)
+// inside a slab + weight.
+struct RowEdges {
+  uint32_t nb[kSlots];
+  float wt[kSlots];
+  int e0, e1, nslot;
+};
+
+template <int F>
+__device__ __forceinline__ void decode_edges(RowEdges& re, int e0, int e1, bool staged, uint32_t a_ci, uint32_t a_cv,
+                                             int a_lo, int r0) {
+  constexpr uint32_t ROWB = F * 4;
+  re.e0 = e0;
+  re.e1 = e1;
+  re.nslot = staged ? min(e1 - e0, kSlots) : 0;         // e1 == e0 for lanes past the graph
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j) re.nb[j] = 0u, re.wt[j] = 0.0f;
+  if (re.nslot > 0) {   // up to 3 entries past the row are read (inside the staged slice + slack), never used
+    const uint32_t el = (uint32_t)(e0 - a_lo) * 4;
+#pragma unroll
+    for (int j = 0; j < kSlots; ++j) {
+      const uint32_t c = (uint32_t)(lds32i(a_ci + el + 4 * j) - r0);
+      re.wt[j] = lds32(a_cv + el + 4 * j);
+      re.nb[j] = c * ROWB + (swz<F>(c) << 4);
+    }
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void gather_slot(float2 (&a2)[F / 2], uint32_t p, float w, bool first) {
+  constexpr int Q = F / 4;
+  const float2 ww = make_float2(w, w);
+  float4 a[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) a[q] = lds128(p ^ ((uint32_t)q << 4));   // 64-byte aligned slabs: the XOR stays in the row
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    a2[2 * q] = __ffma2_rn(ww, make_float2(a[q].x, a[q].y), first ? make_float2(0.f, 0.f) : a2[2 * q]);
+    a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a[q].z, a[q].w), first ? make_float2(0.f, 0.f) : a2[2 * q + 1]);
+  }
+}
+
+// One row of T_k = c L T_{k-1} (- T_{k-2}): the decoded slots, then longer rows (or a CSR slice that was not staged)
+// in a generic loop; `dst` = the own row's chunk addresses in the buffer that holds T_{k-2} and receives T_k.
+template <int F, bool SUB>
+__device__ __forceinline__ void propagate_row(const RowEdges& re, uint32_t a_src, const uint32_t* dst,
+                                              uint32_t dst_off, bool staged,
+                                              uint32_t a_ci, uint32_t a_cv, int a_lo, int r0,
+                                              const int32_t* __restrict__ colidx, const float* __restrict__ vals) {
+  constexpr int Q = F / 4;
+  constexpr uint32_t ROWB = F * 4;
+  float2 a2[F / 2];
+#pragma unroll
+  for (int i = 0; i < F / 2; ++i) a2[i] = make_float2(0.f, 0.f);
+  // per-slot divergent branches on purpose (a branch-free variant with weight-0 dummy slots measured 23 % slower:
+  // more instructions for the many lanes / slots without an edge)
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j)
+    if (j < re.nslot) gather_slot<F>(a2, a_src + re.nb[j], re.wt[j], false);
+  if (re.e1 - re.e0 > re.nslot) {
+    for (int e = re.e0 + re.nslot; e < re.e1; ++e) {
+      uint32_t c;
+      float w;
+      if (staged) {
+        c = (uint32_t)(lds32i(a_ci + (uint32_t)(e - a_lo) * 4) - r0);
+        w = lds32(a_cv + (uint32_t)(e - a_lo) * 4);
+      } else {
+        c = (uint32_t)(__ldg(colidx + e) - r0);
+        w = __ldg(vals + e);
+      }
+      gather_slot<F>(a2, a_src + c * ROWB + (swz<F>(c) << 4), w, false);
+    }
+  }
+  if (SUB) {     // T_k = 2 L T_{k-1} - T_{k-2}; T_{k-2}'s own row is where T_k goes
+    const float2 two = make_float2(2.0f, 2.0f);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const float4 o = lds128(dst[q] + dst_off);
+      a2[2 * q] = __ffma2_rn(two, a2[2 * q], make_float2(-o.x, -o.y));
+      a2[2 * q + 1] = __ffma2_rn(two, a2[2 * q + 1], make_float2(-o.z, -o.w));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+    sts128(dst[q] + dst_off, make_float4(a2[2 * q].x, a2[2 * q].y, a2[2 * q + 1].x, a2[2 * q + 1].y));
+}
+
+// The dense [n, F] slab a bulk copy landed -> XOR-swizzled rows, in place, each lane its own row(s): the permutation
+// stays inside a row, so no synchronisation is needed.  (A coalesced lane-per-chunk pass would avoid the 4-way bank
+// conflict of the dense read, but costs two __syncwarp and ~40 more instructions per graph -- the kernel is bound by
+// the per-warp instruction rate, not by shared-memory wavefronts: measured slower.)
+template <int F, int RPL>
+__device__ __forceinline__ void relay_rows(uint32_t a_slab, int n, int lane, const uint32_t (&own)[F / 4]) {
+  constexpr int Q = F / 4;
+  constexpr uint32_t ROWB = F * 4;
+#pragma unroll
+  for (int m = 0; m < RPL; ++m) {
+    if (lane + 32 * m < n) {
+      float4 v[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) v[q] = lds128(a_slab + (uint32_t)(lane + 32 * m) * ROWB + 16 * q);
+#pragma unroll
+      for (int q = 0; q < Q; ++q) sts128(a_slab + own[q] + 32 * m * ROWB, v[q]);
+    }
+  }
+  __syncwarp();
+}
+
 // TRANS = false: out = sum_k T_k(L) x . Theta_k + bias (forward).  TRANS = true: the same recursion against
 // Theta_k^T -- called with (dOut, the source-grouped CSR = L^T, no bias) it is the input gradient, because the
 // operator acts on rows and the filters on channels: dx = sum_k T_k(L^T) dOut . Theta_k^T.
-template <int F, int RPL, int K, bool TRANS>
-__global__ void __launch_bounds__(RPL == 1 ? 512 : 384, 1) cheb_fwd_lane_kernel(
+template <int F, int RPL, int K, bool TRANS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) cheb_fwd_lane_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
     const float* __restrict__ vals, const int32_t* __restrict__ graph_ptr, const float* __restrict__ theta,
     int64_t sk, int64_t sg, const float* __restrict__ bias, float* __restrict__ out, int64_t R, int64_t G,
@@ -257,23 +369,24 @@ __global__ void __launch_bounds__(RPL == 1 ? 512 : 384, 1) cheb_fwd_lane_kernel(
   uint32_t own[Q];                                               // own row, chunk q: byte offset inside a slab
 #pragma unroll
   for (int q = 0; q < Q; ++q) own[q] = (uint32_t)lane * ROWB + (((uint32_t)q ^ sw_row) << 4);
-  uint32_t afr[Q];                                               // A fragment: row g, chunk j, word tq
+  // A fragments: one vector of own contraction indices of row g (see mma_order_t)
+  const uint32_t afr_t = F == 16 ? g * ROWB + ((tq ^ swz<F>(g)) << 4) : g * ROWB + (((tq >> 1) ^ swz<F>(g)) << 4) + (tq & 1u) * 8;
+  // B fragments.  F = 16 permutes the OUTPUT channels so that a lane ends up with four consecutive channels of a row
+  // (one STS.128 per row in the epilogue instead of two 4-way conflicted STS.64): forward -- n-tile nt, column n'
+  // <-> channel 2 n' + nt (Theta_k[tq][2g, 2g + 1] is one 64-bit load); TRANS -- <-> 4 (n' / 2) + 2 nt + n' % 2
+  // (the quarter-warp's filter rows stay adjacent: conflict-free 128-bit loads).
+  const uint32_t bfr = TRANS ? (F == 16 ? a_th + ((4 * (g >> 1) + (g & 1u)) * F + 4 * tq) * 4 : a_th + (g * F + 2 * tq) * 4)
+                             : (F == 16 ? a_th + (tq * F + 2 * g) * 4 : a_th + (tq * F + g) * 4);
+  const uint32_t ofr = F == 16 ? a_odd + (g * F + 4 * tq) * 4 : a_odd + (g * F + 2 * tq) * 4;   // output staging (dense)
+  uint32_t afr[Q];                                               // forward A fragment: row g, chunk j, word tq
 #pragma unroll
   for (int j = 0; j < Q; ++j) afr[j] = g * ROWB + (((uint32_t)j ^ swz<F>(g)) << 4) + tq * 4;
-  // TRANS: one vector of own contraction indices (see mma_order_t)
-  const uint32_t afr_t = F == 16 ? g * ROWB + ((tq ^ swz<F>(g)) << 4) : g * ROWB + (((tq >> 1) ^ swz<F>(g)) << 4) + (tq & 1u) * 8;
-  const uint32_t bfr = TRANS ? a_th + (g * F + (F / 4) * tq) * 4   // Theta_k[g][own channels]
-                             : a_th + (tq * F + g) * 4;            // Theta_k[tq][g] (+ k F F 4 + immediates)
-  const uint32_t ofr = a_odd + (g * F + 2 * tq) * 4;             // output staging (dense) in the odd buffer
-  uint32_t own_o[Q], ta_o[Q];                                    // the odd buffer never moves
+  uint32_t own_o[Q];                                             // the odd buffer never moves
 #pragma unroll
-  for (int q = 0; q < Q; ++q) own_o[q] = a_odd + own[q], ta_o[q] = a_odd + afr[q];
-  float bias_m[NT][2];
+  for (int q = 0; q < Q; ++q) own_o[q] = a_odd + own[q];
+  float bias_m[F / 4];                                           // the F / 4 consecutive channels this lane stores
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    bias_m[nt][0] = bias ? __ldg(bias + 8 * nt + 2 * tq) : 0.0f;
-    bias_m[nt][1] = bias ? __ldg(bias + 8 * nt + 2 * tq + 1) : 0.0f;
-  }
+  for (int i = 0; i < F / 4; ++i) bias_m[i] = bias ? __ldg(bias + (F / 4) * tq + i) : 0.0f;
 
   auto fetch_a = [&](int it, GraphDesc<RPL>& d) {
     d.r0 = d.r1 = 0;
@@ -359,49 +472,22 @@ __global__ void __launch_bounds__(RPL == 1 ? 512 : 384, 1) cheb_fwd_lane_kernel(
     const int MT = (n + 15) >> 4;
     int a_lo, a_hi;
     const bool staged = staged_csr(d0, a_lo, a_hi);
-    uint32_t own_e[Q], ta_e[Q];
+    uint32_t own_e[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) own_e[q] = a_even + own[q], ta_e[q] = a_even + afr[q];
+    for (int q = 0; q < Q; ++q) own_e[q] = a_even + own[q];
     mbar_wait_parity(a_bar + 8u * (uint32_t)(it & 1), (uint32_t)((it >> 1) & 1));
     if (lane == 0) bulk_wait_read0();   // the previous graph's output store has drained the odd buffer
     __syncwarp();
 
-    // ---- decode the first kSlots CSR entries of every own row: neighbour-row offset (chunk 0, swizzled) + weight
-    uint32_t nb[RPL][kSlots];
-    float wt[RPL][kSlots];
-    int deg[RPL], nslot[RPL];
+    // ---- decode the first kSlots CSR entries of every own row (neighbour-row offset + weight)
+    RowEdges re[RPL];
 #pragma unroll
     for (int m = 0; m < RPL; ++m) {
-      deg[m] = d0.e1[m] - d0.e0[m];                  // 0 for lanes past the graph
-      nslot[m] = staged ? min(deg[m], kSlots) : 0;
-      const uint32_t el = (uint32_t)(d0.e0[m] - a_lo) * 4;
-#pragma unroll
-      for (int j = 0; j < kSlots; ++j) {
-        nb[m][j] = 0;
-        wt[m][j] = 0.0f;
-      }
-      if (nslot[m] > 0) {   // up to 3 entries past the row are read (inside the staged slice + slack), never used
-        const uint32_t c0 = (uint32_t)(lds32i(a_ci + el + 0) - d0.r0), c1 = (uint32_t)(lds32i(a_ci + el + 4) - d0.r0);
-        const uint32_t c2 = (uint32_t)(lds32i(a_ci + el + 8) - d0.r0), c3 = (uint32_t)(lds32i(a_ci + el + 12) - d0.r0);
-        wt[m][0] = lds32(a_cv + el + 0), wt[m][1] = lds32(a_cv + el + 4);
-        wt[m][2] = lds32(a_cv + el + 8), wt[m][3] = lds32(a_cv + el + 12);
-        nb[m][0] = c0 * ROWB + (swz<F>(c0) << 4), nb[m][1] = c1 * ROWB + (swz<F>(c1) << 4);
-        nb[m][2] = c2 * ROWB + (swz<F>(c2) << 4), nb[m][3] = c3 * ROWB + (swz<F>(c3) << 4);
-      }
+      decode_edges<F>(re[m], d0.e0[m], d0.e1[m], staged, a_ci, a_cv, a_lo, d0.r0);
     }
 
-    // ---- T_0: re-lay the own row(s) of the dense x slab into the swizzled layout, in place
-#pragma unroll
-    for (int m = 0; m < RPL; ++m) {
-      if (lane + 32 * m < n) {
-        float4 v[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) v[q] = lds128(a_even + (uint32_t)(lane + 32 * m) * ROWB + 16 * q);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) sts128(own_e[q] + 32 * m * ROWB, v[q]);
-      }
-    }
-    __syncwarp();
+    // ---- T_0: the dense x slab -> swizzled rows, in place
+    relay_rows<F, RPL>(a_even, n, lane, own);
 
     float acc[MTMAX][NT][4];
 #pragma unroll
@@ -411,79 +497,38 @@ __global__ void __launch_bounds__(RPL == 1 ? 512 : 384, 1) cheb_fwd_lane_kernel(
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[mt][nt][q] = 0.0f;
 
+    auto mma_ord = [&](uint32_t a_buf, int k) {     // acc += T_k . Theta_k (or Theta_k^T) out of slab `a_buf`
+      if constexpr (TRANS) {
+        mma_order_t<F, MTMAX>(acc, a_buf + afr_t, bfr + (uint32_t)k * F * F * 4, MT);
+      } else {
+        uint32_t ta[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) ta[j] = a_buf + afr[j];
+        mma_order<F, MTMAX>(acc, ta, bfr + (uint32_t)k * F * F * 4, MT);
+      }
+    };
 #pragma unroll
     for (int k = 1; k < K; ++k) {
       const uint32_t a_src = (k & 1) ? a_even : a_odd;   // T_{k-1}
 #pragma unroll
       for (int m = 0; m < RPL; ++m) {
         if (lane + 32 * m < n) {
-          float2 a2[F / 2];
-#pragma unroll
-          for (int i = 0; i < F / 2; ++i) a2[i] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < kSlots; ++j) {
-            if (j < nslot[m]) {
-              const uint32_t p = a_src + nb[m][j];    // buffers are 64-byte aligned: the XOR stays inside the row
-              const float2 ww = make_float2(wt[m][j], wt[m][j]);
-              float4 a[Q];
-#pragma unroll
-              for (int q = 0; q < Q; ++q) a[q] = lds128(p ^ ((uint32_t)q << 4));
-#pragma unroll
-              for (int q = 0; q < Q; ++q) {
-                a2[2 * q] = __ffma2_rn(ww, make_float2(a[q].x, a[q].y), a2[2 * q]);
-                a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a[q].z, a[q].w), a2[2 * q + 1]);
-              }
-            }
-          }
-          if (deg[m] > nslot[m]) {   // rows with more than kSlots neighbours, or a CSR slice that was not staged
-            for (int e = d0.e0[m] + nslot[m]; e < d0.e1[m]; ++e) {
-              uint32_t c;
-              float w;
-              if (staged) {
-                c = (uint32_t)(lds32i(a_ci + (uint32_t)(e - a_lo) * 4) - d0.r0);
-                w = lds32(a_cv + (uint32_t)(e - a_lo) * 4);
-              } else {
-                c = (uint32_t)(__ldg(colidx + e) - d0.r0);
-                w = __ldg(vals + e);
-              }
-              const uint32_t p = a_src + c * ROWB + (swz<F>(c) << 4);
-              const float2 ww = make_float2(w, w);
-#pragma unroll
-              for (int q = 0; q < Q; ++q) {
-                const float4 a = lds128(p ^ ((uint32_t)q << 4));
-                a2[2 * q] = __ffma2_rn(ww, make_float2(a.x, a.y), a2[2 * q]);
-                a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a.z, a.w), a2[2 * q + 1]);
-              }
-            }
-          }
-          if (k >= 2) {     // T_k = 2 L T_{k-1} - T_{k-2}; T_{k-2}'s own row is where T_k goes
-            const float2 two = make_float2(2.0f, 2.0f);
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              const float4 o = lds128(((k & 1) ? own_o[q] : own_e[q]) + 32 * m * ROWB);
-              a2[2 * q] = __ffma2_rn(two, a2[2 * q], make_float2(-o.x, -o.y));
-              a2[2 * q + 1] = __ffma2_rn(two, a2[2 * q + 1], make_float2(-o.z, -o.w));
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < Q; ++q)
-            sts128(((k & 1) ? own_o[q] : own_e[q]) + 32 * m * ROWB,
-                   make_float4(a2[2 * q].x, a2[2 * q].y, a2[2 * q + 1].x, a2[2 * q + 1].y));
+          if (k >= 2)
+            propagate_row<F, true>(re[m], a_src, (k & 1) ? own_o : own_e, 32 * m * ROWB, staged, a_ci, a_cv, a_lo, d0.r0, colidx, vals);
+          else
+            propagate_row<F, false>(re[m], a_src, (k & 1) ? own_o : own_e, 32 * m * ROWB, staged, a_ci, a_cv, a_lo, d0.r0, colidx, vals);
         }
       }
       __syncwarp();
       if (k == 1) {   // order 0 is applied here: the Theta copy had the previous epilogue + one propagation to land
         mbar_wait_parity(a_bar + 16, (uint32_t)(it & 1));
-        if constexpr (TRANS) mma_order_t<F, MTMAX>(acc, a_even + afr_t, bfr, MT);
-        else mma_order<F, MTMAX>(acc, ta_e, bfr, MT);
+        mma_ord(a_even, 0);
       }
-      if constexpr (TRANS) mma_order_t<F, MTMAX>(acc, ((k & 1) ? a_odd : a_even) + afr_t, bfr + (uint32_t)k * F * F * 4, MT);
-      else mma_order<F, MTMAX>(acc, (k & 1) ? ta_o : ta_e, bfr + (uint32_t)k * F * F * 4, MT);
+      mma_ord((k & 1) ? a_odd : a_even, k);
     }
     if (K == 1) {
       mbar_wait_parity(a_bar + 16, (uint32_t)(it & 1));
-      if constexpr (TRANS) mma_order_t<F, MTMAX>(acc, a_even + afr_t, bfr, MT);
-      else mma_order<F, MTMAX>(acc, ta_e, bfr, MT);
+      mma_ord(a_even, 0);
     }
     __syncwarp();            // every lane has read its last Theta / T fragment
     issue_theta(it + 1);
@@ -491,11 +536,22 @@ __global__ void __launch_bounds__(RPL == 1 ? 512 : 384, 1) cheb_fwd_lane_kernel(
 #pragma unroll
     for (int mt = 0; mt < MTMAX; ++mt) {
       if (mt < MT) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const uint32_t o = ofr + ((16 * mt) * F + 8 * nt) * 4;
-          sts64(o, make_float2(acc[mt][nt][0] + bias_m[nt][0], acc[mt][nt][1] + bias_m[nt][1]));
-          sts64(o + 8 * ROWB, make_float2(acc[mt][nt][2] + bias_m[nt][0], acc[mt][nt][3] + bias_m[nt][1]));
+        const uint32_t o = ofr + (16 * mt) * ROWB;
+        const bool lo_ok = 16 * mt + (int)g < n, hi_ok = 16 * mt + 8 + (int)g < n;
+        if constexpr (F == 16) {
+          // channels 4 tq .. 4 tq + 3 of rows g, g + 8: forward (c0 nt0, c0 nt1, c1 nt0, c1 nt1); TRANS (c0 nt0, c1 nt0, c0 nt1, c1 nt1)
+          const float (&a0)[4] = acc[mt][0];
+          const float (&a1)[4] = acc[mt][NT - 1];
+          if (lo_ok)
+            sts128(o, TRANS ? make_float4(a0[0] + bias_m[0], a0[1] + bias_m[1], a1[0] + bias_m[2], a1[1] + bias_m[3])
+                            : make_float4(a0[0] + bias_m[0], a1[0] + bias_m[1], a0[1] + bias_m[2], a1[1] + bias_m[3]));
+          if (hi_ok)
+            sts128(o + 8 * ROWB,
+                   TRANS ? make_float4(a0[2] + bias_m[0], a0[3] + bias_m[1], a1[2] + bias_m[2], a1[3] + bias_m[3])
+                         : make_float4(a0[2] + bias_m[0], a1[2] + bias_m[1], a0[3] + bias_m[2], a1[3] + bias_m[3]));
+        } else {
+          if (lo_ok) sts64(o, make_float2(acc[mt][0][0] + bias_m[0], acc[mt][0][1] + bias_m[1]));
+          if (hi_ok) sts64(o + 8 * ROWB, make_float2(acc[mt][0][2] + bias_m[0], acc[mt][0][3] + bias_m[1]));
         }
       }
     }
@@ -512,16 +568,18 @@ __global__ void __launch_bounds__(RPL == 1 ? 512 : 384, 1) cheb_fwd_lane_kernel(
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
 }
 
-template <int F, int RPL, int K, bool TRANS>
+template <int F, int RPL, int K, bool TRANS, int MAXT = 512>
 static int launch(const Cfg& c, const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                   const int32_t* graph_ptr, const float* theta, int64_t sk, int64_t sg, const float* bias, float* out,
                   int64_t R, int64_t G, int32_t* meta, int max_nodes, cudaStream_t st) {
-  auto kern = cheb_fwd_lane_kernel<F, RPL, K, TRANS>;
+  auto kern = cheb_fwd_lane_kernel<F, RPL, K, TRANS, MAXT>;
   FETA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-  int64_t grid = ceil_div(G, c.warps);
+  const int warps = c.warps * 32 > MAXT ? MAXT / 32 : c.warps;
+  int64_t grid = ceil_div(G, warps);
   if (grid > kNumSMs) grid = kNumSMs;
-  kern<<<(unsigned)grid, c.warps * 32, c.smem, st>>>(x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G,
-                                                    c.nnz_cap, c.rows_cap, c.per_warp, meta, max_nodes);
+  kern<<<(unsigned)grid, warps * 32, (size_t)c.per_warp * warps + kTailPad, st>>>(x, rowptr, colidx, vals, graph_ptr, theta, sk, sg,
+                                                                      bias, out, R, G, c.nnz_cap, c.rows_cap, c.per_warp,
+                                                                      meta, max_nodes);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
@@ -539,16 +597,19 @@ static Cfg config_dtheta(int F, int K, int max_nodes) {
   Cfg c{0, 0, 0, 0, 0, 0, false};
   if (!(F == 8 || F == 16) || K < 1 || K > 4 || max_nodes < 1 || max_nodes > 64) return c;
   c.rpl = max_nodes <= 32 ? 1 : 2;
-  c.rows_cap = (max_nodes + 15) / 16 * 16;
-  c.nnz_cap = c.rows_cap * 4;
+  c.rows_cap = (max_nodes + 7) / 8 * 8;         // the contraction walks whole 8-row k-steps
+  c.nnz_cap = c.rows_cap * 3;
+  if (const char* e = getenv("FETA_LANE_NNZ_PER_ROW")) c.nnz_cap = c.rows_cap * atoi(e);
   const size_t slab = (size_t)c.rows_cap * F * 4;
   const size_t stage = 2 * slab + 2 * csr_bytes_of(c.nnz_cap);
   c.per_warp = (uint32_t)align_up(kBarBytes + slab + (size_t)K * F * F * 4 + 2 * stage, 128);
-  int w = (int)((227 * 1024) / c.per_warp);
-  if (w > 12) w = 12;
+  int w = (int)((227 * 1024 - kTailPad) / c.per_warp);
+  int wmax = 12;
+  if (const char* e = getenv("FETA_LANE_WARPS")) wmax = atoi(e) < 12 ? atoi(e) : 12;
+  if (w > wmax) w = wmax;
   if (w < 4) return c;
   c.warps = w;
-  c.smem = (size_t)c.per_warp * w;
+  c.smem = (size_t)c.per_warp * w + kTailPad;
   c.ok = true;
   return c;
 }
@@ -684,39 +745,17 @@ __global__ void __launch_bounds__(384, 1) cheb_dtheta_lane_kernel(
     if (lane == 0) bulk_wait_read0();   // the previous graph's dTheta store has drained the staging block
     __syncwarp();
 
-    uint32_t nb[RPL][kSlots];
-    float wt[RPL][kSlots];
-    int deg[RPL], nslot[RPL];
+    RowEdges re[RPL];
 #pragma unroll
     for (int m = 0; m < RPL; ++m) {
-      deg[m] = d0.e1[m] - d0.e0[m];
-      nslot[m] = staged ? min(deg[m], kSlots) : 0;
-      const uint32_t el = (uint32_t)(d0.e0[m] - a_lo) * 4;
-#pragma unroll
-      for (int j = 0; j < kSlots; ++j) {
-        nb[m][j] = 0;
-        wt[m][j] = 0.0f;
-      }
-      if (nslot[m] > 0) {
-        const uint32_t c0 = (uint32_t)(lds32i(a_ci + el + 0) - d0.r0), c1 = (uint32_t)(lds32i(a_ci + el + 4) - d0.r0);
-        const uint32_t c2 = (uint32_t)(lds32i(a_ci + el + 8) - d0.r0), c3 = (uint32_t)(lds32i(a_ci + el + 12) - d0.r0);
-        wt[m][0] = lds32(a_cv + el + 0), wt[m][1] = lds32(a_cv + el + 4);
-        wt[m][2] = lds32(a_cv + el + 8), wt[m][3] = lds32(a_cv + el + 12);
-        nb[m][0] = c0 * ROWB + (swz<F>(c0) << 4), nb[m][1] = c1 * ROWB + (swz<F>(c1) << 4);
-        nb[m][2] = c2 * ROWB + (swz<F>(c2) << 4), nb[m][3] = c3 * ROWB + (swz<F>(c3) << 4);
-      }
+      decode_edges<F>(re[m], d0.e0[m], d0.e1[m], staged, a_ci, a_cv, a_lo, d0.r0);
     }
-    // T_0: re-lay the own row of x (swizzled, in place); rows n .. 8 KSu - 1 enter the products: zero them everywhere
+    // T_0: the dense x slab -> swizzled rows, in place; rows n .. 8 KSu - 1 enter the products: zero them in every slab
+    relay_rows<F, RPL>(a_even, n, lane, own);
 #pragma unroll
     for (int m = 0; m < RPL; ++m) {
       const int row = lane + 32 * m;
-      if (row < n) {
-        float4 v[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) v[q] = lds128(a_even + (uint32_t)row * ROWB + 16 * q);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) sts128(own_e[q] + 32 * m * ROWB, v[q]);
-      } else if (row < 8 * KSu) {
+      if (row >= n && row < 8 * KSu) {
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -757,58 +796,10 @@ __global__ void __launch_bounds__(384, 1) cheb_dtheta_lane_kernel(
 #pragma unroll
         for (int m = 0; m < RPL; ++m) {
           if (lane + 32 * m < n) {
-            float2 a2[F / 2];
-#pragma unroll
-            for (int i = 0; i < F / 2; ++i) a2[i] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < kSlots; ++j) {
-              if (j < nslot[m]) {
-                const uint32_t p = a_src + nb[m][j];
-                const float2 ww = make_float2(wt[m][j], wt[m][j]);
-                float4 a[Q];
-#pragma unroll
-                for (int q = 0; q < Q; ++q) a[q] = lds128(p ^ ((uint32_t)q << 4));
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                  a2[2 * q] = __ffma2_rn(ww, make_float2(a[q].x, a[q].y), a2[2 * q]);
-                  a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a[q].z, a[q].w), a2[2 * q + 1]);
-                }
-              }
-            }
-            if (deg[m] > nslot[m]) {
-              for (int e = d0.e0[m] + nslot[m]; e < d0.e1[m]; ++e) {
-                uint32_t c;
-                float w;
-                if (staged) {
-                  c = (uint32_t)(lds32i(a_ci + (uint32_t)(e - a_lo) * 4) - d0.r0);
-                  w = lds32(a_cv + (uint32_t)(e - a_lo) * 4);
-                } else {
-                  c = (uint32_t)(__ldg(colidx + e) - d0.r0);
-                  w = __ldg(vals + e);
-                }
-                const uint32_t p = a_src + c * ROWB + (swz<F>(c) << 4);
-                const float2 ww = make_float2(w, w);
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                  const float4 a = lds128(p ^ ((uint32_t)q << 4));
-                  a2[2 * q] = __ffma2_rn(ww, make_float2(a.x, a.y), a2[2 * q]);
-                  a2[2 * q + 1] = __ffma2_rn(ww, make_float2(a.z, a.w), a2[2 * q + 1]);
-                }
-              }
-            }
-            if (k >= 2) {
-              const float2 two = make_float2(2.0f, 2.0f);
-#pragma unroll
-              for (int q = 0; q < Q; ++q) {
-                const float4 o = lds128(((k & 1) ? own_o[q] : own_e[q]) + 32 * m * ROWB);
-                a2[2 * q] = __ffma2_rn(two, a2[2 * q], make_float2(-o.x, -o.y));
-                a2[2 * q + 1] = __ffma2_rn(two, a2[2 * q + 1], make_float2(-o.z, -o.w));
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < Q; ++q)
-              sts128(((k & 1) ? own_o[q] : own_e[q]) + 32 * m * ROWB,
-                     make_float4(a2[2 * q].x, a2[2 * q].y, a2[2 * q + 1].x, a2[2 * q + 1].y));
+            if (k >= 2)
+              propagate_row<F, true>(re[m], a_src, (k & 1) ? own_o : own_e, 32 * m * ROWB, staged, a_ci, a_cv, a_lo, d0.r0, colidx, vals);
+            else
+              propagate_row<F, false>(re[m], a_src, (k & 1) ? own_o : own_e, 32 * m * ROWB, staged, a_ci, a_cv, a_lo, d0.r0, colidx, vals);
           }
         }
         __syncwarp();
@@ -896,10 +887,13 @@ static int lane_dispatch(bool trans, const float* x, const int32_t* rowptr, cons
 #define FETA_LANE_CASE(F_, R_, K_)                                                                                    \
   if (F == F_ && c.rpl == R_ && K == K_) {                                                                            \
     if (trans)                                                                                                        \
-      return lane::launch<F_, R_, K_, true>(c, x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G,    \
-                                            meta, max_nodes, st);                                                     \
-    return lane::launch<F_, R_, K_, false>(c, x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R, G,     \
-                                           meta, max_nodes, st);                                                      \
+      return lane::launch<F_, R_, K_, true, 512>(c, x, rowptr, colidx, vals, graph_ptr, theta, sk, sg, bias, out, R,  \
+                                                 G, meta, max_nodes, st);                                             \
+    /* measured (profiles/r2_cheb_lane.md): the F = 16 two-rows-per-lane forward is faster with 12 warps x 165   */  \
+    /* registers than with 16 x 128; every other variant wants the 16 warps (13..15 cap registers at 128 too)    */  \
+    return lane::launch<F_, R_, K_, false, (F_ == 16 && R_ == 2) ? 384 : 512>(c, x, rowptr, colidx, vals, graph_ptr, \
+                                                                              theta, sk, sg, bias, out, R, G, meta,  \
+                                                                              max_nodes, st);                        \
   }
 #define FETA_LANE_CASES(F_, R_) FETA_LANE_CASE(F_, R_, 1) FETA_LANE_CASE(F_, R_, 2) FETA_LANE_CASE(F_, R_, 3) FETA_LANE_CASE(F_, R_, 4)
   FETA_LANE_CASES(8, 1) FETA_LANE_CASES(8, 2) FETA_LANE_CASES(16, 1) FETA_LANE_CASES(16, 2)
