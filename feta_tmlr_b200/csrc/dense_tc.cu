@@ -204,8 +204,25 @@ extern "C" int feta_linear_tc_supported(int in, int out) {
   return in >= 8 && out >= 8 && in % 8 == 0 && out % 8 == 0 && in <= 256 && out <= 256;
 }
 
+namespace feta {
+int linear_simt_fwd_try(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out, int relu,
+                        cudaStream_t st);
+int linear_simt_dx_try(const float* dY, const float* W, const float* dres, const float* mask_src, float* dX, int64_t T,
+                       int in, int out, cudaStream_t st);
+}
+
 extern "C" int feta_linear_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out,
                                int relu, void* stream_) {
+  return feta_linear_fwd_ex(X, W, bias, Y, T, in, out, relu, FETA_LINEAR_AUTO, stream_);
+}
+
+extern "C" int feta_linear_dx(const float* dY, const float* W, const float* dres, const float* mask_src, float* dX,
+                              int64_t T, int in, int out, void* stream_) {
+  return feta_linear_dx_ex(dY, W, dres, mask_src, dX, T, in, out, FETA_LINEAR_AUTO, stream_);
+}
+
+extern "C" int feta_linear_fwd_ex(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out,
+                                  int relu, int impl, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(T >= 0 && (feta_linear_tc_supported(in, out) || feta_linear_tc5_supported(in, out)),
                "linear_fwd: unsupported shape T=%lld in=%d out=%d",
@@ -214,7 +231,11 @@ extern "C" int feta_linear_fwd(const float* X, const float* W, const float* bias
   FETA_REQUIRE(X && W && Y, "linear_fwd: NULL pointer argument");
   FETA_REQUIRE(((uintptr_t)X % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)Y % 8) == 0,
                "linear_fwd: X/W must be 16-byte aligned");
-  {   // tcgen05 path (linear_tc5.cu) when the shape is a multiple of its 128 x 64 x 64 tiles
+  if (impl == FETA_LINEAR_AUTO || impl == FETA_LINEAR_SIMT) {   // fp32 CUDA-core latency kernel (linear_simt.cu)
+    const int rc = linear_simt_fwd_try(X, W, bias, Y, T, in, out, relu, st);
+    if (rc <= 0) return rc;
+  }
+  if (impl != FETA_LINEAR_MMA) {   // tcgen05 path (linear_tc5.cu) when the shape is a multiple of its 128 x 64 x 64 tiles
     const int rc = linear5_fwd_try(X, W, bias, Y, T, in, out, relu, st);
     if (rc <= 0) return rc;
   }
@@ -234,8 +255,8 @@ extern "C" int feta_linear_fwd(const float* X, const float* W, const float* bias
   return FETA_OK;
 }
 
-extern "C" int feta_linear_dx(const float* dY, const float* W, const float* dres, const float* mask_src, float* dX,
-                              int64_t T, int in, int out, void* stream_) {
+extern "C" int feta_linear_dx_ex(const float* dY, const float* W, const float* dres, const float* mask_src, float* dX,
+                                 int64_t T, int in, int out, int impl, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FETA_REQUIRE(T >= 0 && (feta_linear_tc_supported(in, out) || feta_linear_tc5_supported(in, out)),
                "linear_dx: unsupported shape T=%lld in=%d out=%d",
@@ -245,7 +266,11 @@ extern "C" int feta_linear_dx(const float* dY, const float* W, const float* dres
   FETA_REQUIRE(((uintptr_t)dY % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)dX % 8) == 0 &&
                    ((uintptr_t)dres % 8) == 0 && ((uintptr_t)mask_src % 8) == 0,
                "linear_dx: pointers must be 16-byte (dY, W) / 8-byte aligned");
-  {
+  if (impl == FETA_LINEAR_AUTO || impl == FETA_LINEAR_SIMT) {
+    const int rc = linear_simt_dx_try(dY, W, dres, mask_src, dX, T, in, out, st);
+    if (rc <= 0) return rc;
+  }
+  if (impl != FETA_LINEAR_MMA) {
     const int rc = linear5_dx_try(dY, W, dres, mask_src, dX, T, in, out, st);
     if (rc <= 0) return rc;
   }

@@ -752,10 +752,27 @@ LINEAR_TENSOR_CORES = _os.environ.get("FETA_LINEAR_TC", "0") == "1"
 LINEAR_TC5 = _os.environ.get("FETA_LINEAR_TC5", "0") == "1"
 
 
-def linear_tc_enabled(in_f, out_f):
+# Default: the layer's projections (forward and dX) through this repo's fp32 CUDA-core latency kernel
+# (csrc/linear_simt.cu) whenever (in, out) are multiples of 64 up to 256 -- every projection of every BASELINE
+# config; FETA_LINEAR_SIMT=0 returns them to the library GEMM.
+LINEAR_SIMT = _os.environ.get("FETA_LINEAR_SIMT", "1") == "1"
+_IMPL_SIMT, _IMPL_TC5, _IMPL_MMA = 1, 2, 3
+
+
+def linear_impl(in_f, out_f):
+    """0: library GEMM; else the FETA_LINEAR_* kernel family that runs this projection (explicit opt-ins win)."""
     lib = _lib.load()
-    return bool((LINEAR_TENSOR_CORES and lib.feta_linear_tc_supported(int(in_f), int(out_f))) or
-                (LINEAR_TC5 and lib.feta_linear_tc5_supported(int(in_f), int(out_f))))
+    if LINEAR_TC5 and lib.feta_linear_tc5_supported(int(in_f), int(out_f)):
+        return _IMPL_TC5
+    if LINEAR_TENSOR_CORES and lib.feta_linear_tc_supported(int(in_f), int(out_f)):
+        return _IMPL_MMA
+    if LINEAR_SIMT and lib.feta_linear_simt_supported(int(in_f), int(out_f)):
+        return _IMPL_SIMT
+    return 0
+
+
+def linear_tc_enabled(in_f, out_f):
+    return linear_impl(in_f, out_f) != 0
 _SIDE = {}
 _JOIN_TASK = {}          # device -> id of the autograd graph task that already queued its join
 
@@ -864,15 +881,15 @@ class LinearFn(torch.autograd.Function):
         ctx.premasked = bool(grad_premasked)
         ctx.set_materialize_grads(False)
         out_f, in_f = weight.shape
-        ctx.tc = bool(x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
-                      and linear_tc_enabled(in_f, out_f))
+        ctx.tc = linear_impl(in_f, out_f) if (x.is_cuda and x.dtype == torch.float32
+                                               and weight.dtype == torch.float32) else 0
         if ctx.tc:
             x2 = _f32c(x.reshape(-1, in_f))
             w = _f32c(weight)
             bc = None if bias is None else _f32c(bias)
             y = torch.empty(x.shape[:-1] + (out_f,), dtype=torch.float32, device=x.device)
-            check(lib.feta_linear_fwd(_ptr(x2), _ptr(w), _ptr(bc), _ptr(y), x2.shape[0], in_f, out_f, int(ctx.relu),
-                                      _stream()), "feta_linear_fwd")
+            check(lib.feta_linear_fwd_ex(_ptr(x2), _ptr(w), _ptr(bc), _ptr(y), x2.shape[0], in_f, out_f,
+                                         int(ctx.relu), ctx.tc, _stream()), "feta_linear_fwd")
         elif relu and bias is not None and x.is_cuda:
             y = torch._addmm_activation(bias, x.reshape(-1, in_f), weight.t()).view(*x.shape[:-1], out_f)
         else:
@@ -900,8 +917,8 @@ class LinearFn(torch.autograd.Function):
                 x2 = _f32c(x.reshape(-1, in_f)) if ctx.mask_in else None
                 dr = None if dres is None else _f32c(dres.reshape(-1, in_f))
                 dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
-                check(lib.feta_linear_dx(_ptr(dy2), _ptr(_f32c(weight)), _ptr(dr), _ptr(x2), _ptr(dx), dy2.shape[0],
-                                         in_f, out_f, _stream()), "feta_linear_dx")
+                check(lib.feta_linear_dx_ex(_ptr(dy2), _ptr(_f32c(weight)), _ptr(dr), _ptr(x2), _ptr(dx),
+                                            dy2.shape[0], in_f, out_f, ctx.tc, _stream()), "feta_linear_dx")
             else:
                 dx = dy.matmul(weight)
                 if ctx.mask_in:

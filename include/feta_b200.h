@@ -267,6 +267,18 @@ int feta_layer_tail_fwd(const float* o, const float* res, const float* bscale, c
                         const float* b2, const float* g2, const float* be2, float* z1, float* mean1, float* rstd1,
                         float* y1, float* h, float* z2, float* mean2, float* rstd2, float* y2, int64_t T, int d_model,
                         int dff, float eps1, float eps2, void* stream);
+/* Which kernel family runs a projection.  AUTO: the fp32 CUDA-core latency kernel (csrc/linear_simt.cu: whole
+ * reduction dimension staged by one wave of cp.async, exact fp32) when the shape is eligible (in, out multiples of 64,
+ * <= 256), else tcgen05 (3xTF32), else legacy mma.sync (3xTF32).  feta_linear_fwd / feta_linear_dx = AUTO. */
+#define FETA_LINEAR_AUTO 0
+#define FETA_LINEAR_SIMT 1
+#define FETA_LINEAR_TC5 2
+#define FETA_LINEAR_MMA 3
+int feta_linear_simt_supported(int in, int out);
+int feta_linear_fwd_ex(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out,
+                       int relu, int impl, void* stream);
+int feta_linear_dx_ex(const float* dY, const float* W, const float* dres, const float* mask_src, float* dX, int64_t T,
+                      int in, int out, int impl, void* stream);
 /* 1 when feta_linear_fwd / feta_linear_dx run this (in, out) pair on the tcgen05 path (csrc/linear_tc5.cu:
  * 128 x 64 x 64 tiles, 3xTF32 in TMEM): both multiples of 64. */
 int feta_linear_tc5_supported(int in, int out);

@@ -72,19 +72,50 @@ def test_linear_parity(cuda, side, tc, T, fin, fout, relu, with_res):
     assert rel_err(bd.grad, br.grad) <= TOL
 
 
-@pytest.fixture(params=["tcgen05", "mma_sync", "library_gemm"])
+@pytest.fixture(params=["simt", "tcgen05", "mma_sync", "library_gemm"])
 def tc(request, monkeypatch):
-    """tcgen05: csrc/linear_tc5.cu where the shape is a multiple of its tiles (else mma.sync);  mma_sync:
-    csrc/dense_tc.cu only;  library_gemm: torch / cuBLAS."""
+    """simt: csrc/linear_simt.cu (the default: exact-fp32 CUDA-core latency kernel; shapes it does not take fall back
+    to the library);  tcgen05: csrc/linear_tc5.cu where the shape is a multiple of its tiles (else mma.sync);
+    mma_sync: csrc/dense_tc.cu only;  library_gemm: torch / cuBLAS."""
     from feta_tmlr_b200 import ops
-    old = ops.LINEAR_TENSOR_CORES
-    ops.LINEAR_TENSOR_CORES = request.param != "library_gemm"
-    if request.param == "mma_sync":
-        monkeypatch.setenv("FETA_LINEAR_NO_TC5", "1")
-    else:
-        monkeypatch.delenv("FETA_LINEAR_NO_TC5", raising=False)
+    monkeypatch.setattr(ops, "LINEAR_SIMT", request.param == "simt")
+    monkeypatch.setattr(ops, "LINEAR_TC5", request.param == "tcgen05")
+    monkeypatch.setattr(ops, "LINEAR_TENSOR_CORES", request.param in ("tcgen05", "mma_sync"))
     yield request.param != "library_gemm"
-    ops.LINEAR_TENSOR_CORES = old
+
+
+@pytest.mark.parametrize("T", [1, 31, 33, 4736, 12032])
+@pytest.mark.parametrize("fin,fout", [(64, 64), (64, 192), (64, 128), (128, 64), (192, 64), (256, 256)])
+def test_linear_simt_kernel(cuda, T, fin, fout):
+    """csrc/linear_simt.cu through the C ABI (impl = SIMT): forward with bias + ReLU, dX with ReLU mask and residual,
+    against fp64 -- exact-fp32 arithmetic, so the tolerance is fp32 rounding of a <= 256-term sum."""
+    from feta_tmlr_b200 import ops, _lib
+    lib = _lib.load()
+    assert lib.feta_linear_simt_supported(fin, fout)
+    g = torch.Generator().manual_seed(T * 7 + fin + fout)
+    x = torch.randn(T, fin, generator=g).to(cuda)
+    W = (torch.randn(fout, fin, generator=g) * 0.2).to(cuda)
+    b = torch.randn(fout, generator=g).to(cuda)
+    dy = torch.randn(T, fout, generator=g).to(cuda)
+    dres = torch.randn(T, fin, generator=g).to(cuda)
+    msk = torch.randn(T, fin, generator=g).to(cuda)
+    y = torch.empty(T, fout, device=cuda)
+    dx = torch.empty(T, fin, device=cuda)
+    st = torch.cuda.current_stream().cuda_stream
+    P = ops._ptr
+    for relu in (0, 1):
+        ops.check(lib.feta_linear_fwd_ex(P(x), P(W), P(b), P(y), T, fin, fout, relu, 1, st), "fwd")
+        ref = x.double() @ W.double().t() + b.double()
+        if relu:
+            ref = torch.relu(ref)
+        assert rel_err(y, ref) < 2e-6
+    ops.check(lib.feta_linear_fwd_ex(P(x), P(W), None, P(y), T, fin, fout, 0, 1, st), "fwd no bias")
+    assert rel_err(y, x.double() @ W.double().t()) < 2e-6
+    ops.check(lib.feta_linear_dx_ex(P(dy), P(W), P(dres), P(msk), P(dx), T, fin, fout, 1, st), "dx")
+    ref = (dy.double() @ W.double()) * (msk > 0).double() + dres.double()
+    assert rel_err(dx, ref) < 2e-6
+    ops.check(lib.feta_linear_dx_ex(P(dy), P(W), None, None, P(dx), T, fin, fout, 1, st), "dx plain")
+    assert rel_err(dx, dy.double() @ W.double()) < 2e-6
 
 
 @pytest.mark.parametrize("T,d,dff", [(1, 8, 16), (4352, 64, 128), (10752, 64, 128), (37, 128, 256), (90, 24, 40)])
