@@ -40,6 +40,11 @@ SIGNATURES = {
                                       c_int, c_int, c_int, c_int, c_float, _P]),
     "feta_attn_bwd_dropout": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P,
                                       _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, _P]),
+    "feta_attn_rows_supported": (c_int, [c_int, c_int]),
+    "feta_attn_rows_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, c_int64, _P,
+                                   c_int, c_int, c_int, c_int, c_float, _P]),
+    "feta_attn_rows_bwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P,
+                                   c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, _P]),
     "feta_linear_wgrad_slices": (c_int, [c_int64]),
     "feta_linear_wgrad": (c_int, [_P, _P, _P, _P, _P, c_size_t, _P, c_int64, c_int, c_int, _P]),
     "feta_linear_tc_supported": (c_int, [c_int, c_int]),

@@ -41,6 +41,18 @@ __device__ __forceinline__ float slice_reduce(float v) {
   return v;
 }
 
+// first key position whose score equals the row maximum (lane j + 32 ch holds sraw[ch])
+template <int NCH>
+__device__ __forceinline__ int clamped_argmax(const float (&sraw)[NCH], float m, int lane) {
+  int best = 0x7fffffff;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+    if (sraw[ch] == m && m != -INFINITY) best = min(best, lane + 32 * ch);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  return best == 0x7fffffff ? 0 : best;
+}
+
 // ------------------------------------------------------------------ forward -------------
 template <int DH, int NCH>
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
@@ -90,7 +102,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
     const float* qp = q + (int64_t)i * sn + (int64_t)b * sb + h * DH;
 #pragma unroll
     for (int c = 0; c < DH; ++c) qr[c] = __ldg(qp + c) * scale;  // q * scaling before the product
-    float s[NCH];
+    float s[NCH], sraw[NCH];
     float m = -INFINITY;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -103,6 +115,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
         a += pen[j];
       }
       s[ch] = a;
+      sraw[ch] = a;
       m = fmaxf(m, a);
     }
     m = warp_max(m);
@@ -134,7 +147,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(
       if (j < nmax) arow[j] = p;
       if (j < n) pr[j] = pd;
     }
-    if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = sum > 1e-6f ? 1.0f : 0.0f;
+    {
+      // rowflag: 1 = normalised row; -(1 + argmax_j S_ij) = row under the clamp (constant denominator, but the row
+      // maximum still carries a gradient: oracle/layers.py:61-66 does not detach it); 0 = padded query
+      float rf = 1.0f;
+      if (!(sum > 1e-6f)) rf = -(float)(1 + clamped_argmax<NCH>(sraw, m, lane));
+      if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = rf;
+    }
     __syncwarp();
     if (DH <= 32) {
       constexpr int NS = DH <= 32 ? 32 / DH : 1;
@@ -208,7 +227,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_tiled_kernel(
     const float* qp = q + (int64_t)i * sn + (int64_t)b * sb + h * DH;
 #pragma unroll
     for (int c = 0; c < DH; ++c) qr[c] = __ldg(qp + c) * scale;  // q * scaling before the product
-    float s[NCH];
+    float s[NCH], sraw[NCH];
     float m = -INFINITY;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -225,6 +244,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_tiled_kernel(
         a += pen[j];
       }
       s[ch] = a;
+      sraw[ch] = a;
       m = fmaxf(m, a);
     }
     m = warp_max(m);
@@ -256,7 +276,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_tiled_kernel(
       if (j < nmax) arow[j] = p;
       if (j < n) pr[j] = pd;
     }
-    if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = sum > 1e-6f ? 1.0f : 0.0f;
+    {
+      // rowflag: 1 = normalised row; -(1 + argmax_j S_ij) = row under the clamp (constant denominator, but the row
+      // maximum still carries a gradient: oracle/layers.py:61-66 does not detach it); 0 = padded query
+      float rf = 1.0f;
+      if (!(sum > 1e-6f)) rf = -(float)(1 + clamped_argmax<NCH>(sraw, m, lane));
+      if (lane == 0) rowflag[((size_t)b * H + h) * nmax + i] = rf;
+    }
     __syncwarp();
     {  // O_i = sum_j P[j] V[j]: lanes = (4-channel group, key slice), one 128-bit V load per 4 FMAs
       constexpr int NS = 32 / C4;
@@ -362,13 +388,17 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(
         pp[ch] = ppv;
         delta = fmaf(pv, dpv, delta);
       }
-      delta = warp_sum(delta) * __ldg(rowflag + ((size_t)b * H + h) * nmax + i);
+      // rowflag 1: dS = P (dP - delta); rowflag -(1 + j*): clamped row, dS = P dP - [j = j*] delta (see forward)
+      const float rf = __ldg(rowflag + ((size_t)b * H + h) * nmax + i);
+      const float dsum = warp_sum(delta);
+      delta = rf == 1.0f ? dsum : 0.0f;
+      const int jstar = rf < 0.0f ? (int)(-rf) - 1 : -1;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int j = lane + 32 * ch;
         if (j < n) {
           pr[j] = pp[ch];
-          ds[j] = p[ch] * (dp[ch] - delta);
+          ds[j] = p[ch] * (dp[ch] - delta) - (j == jstar ? dsum : 0.0f);
         }
       }
       __syncwarp();
@@ -519,13 +549,17 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_tiled_kernel(
           delta = fmaf(p[ch], a, delta);
         }
       }
-      delta = warp_sum(delta) * __ldg(rowflag + ((size_t)b * H + h) * nmax + i);
+      // rowflag 1: dS = P (dP - delta); rowflag -(1 + j*): clamped row, dS = P dP - [j = j*] delta (see forward)
+      const float rf = __ldg(rowflag + ((size_t)b * H + h) * nmax + i);
+      const float dsum = warp_sum(delta);
+      delta = rf == 1.0f ? dsum : 0.0f;
+      const int jstar = rf < 0.0f ? (int)(-rf) - 1 : -1;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int j = lane + 32 * ch;
         if (j < n) {
           pr[j] = pp[ch];
-          ds[j] = p[ch] * (dp[ch] - delta);
+          ds[j] = p[ch] * (dp[ch] - delta) - (j == jstar ? dsum : 0.0f);
         }
       }
       __syncwarp();

@@ -169,7 +169,13 @@ template <int MODE, int BM>
 static int launch_bm(const float* A, const float* W, const float* bias, const float* dres, const float* mask_src,
                      float* Y, int64_t T, int KR, int NOUT, int ldw, int relu, cudaStream_t st) {
   const size_t smem = ((size_t)BM * (KR + 4) + (MODE == 0 ? (size_t)kBN * (KR + 4) : (size_t)KR * (kBN + 4))) * 4;
-  FETA_CUDA(cudaFuncSetAttribute(linear_simt_kernel<MODE, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the opt-in limit only ever grows: lowering it after a launch with a larger tile was captured into a CUDA graph
+  // makes a profiler's stand-alone replay of that graph node fail (ncu: LaunchFailed)
+  static std::atomic<int> granted{0};
+  if ((int)smem > granted.load(std::memory_order_relaxed)) {
+    FETA_CUDA(cudaFuncSetAttribute(linear_simt_kernel<MODE, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    granted.store((int)smem, std::memory_order_relaxed);
+  }
   dim3 grid((unsigned)ceil_div(T, BM), (unsigned)(NOUT / kBN));
   linear_simt_kernel<MODE, BM><<<grid, kThreads, smem, st>>>(A, W, bias, dres, mask_src, Y, T, KR, NOUT, ldw, relu);
   FETA_LAUNCH_CHECK();

@@ -45,7 +45,8 @@ class DiffMultiheadAttention(nn.Module):
         if bias:
             nn.init.constant_(self.out_proj.bias, 0.0)
 
-    def forward(self, src, pe=None, key_padding_mask=None, with_residual=False, drop=None, defer_out_proj=False):
+    def forward(self, src, pe=None, key_padding_mask=None, with_residual=False, drop=None, defer_out_proj=False,
+                need_attn=True):
         """src [Nmax, B, d] -> (out [Nmax, B, d], attn [B, H, Nmax, Nmax], heads [B, Nmax, H, dh]).
         ``with_residual``: a 4th output, ``src`` routed through the in-projection's autograd node (its
         gradient is then folded into the in-projection's dX GEMM, ops.LinearFn)."""
@@ -60,7 +61,8 @@ class DiffMultiheadAttention(nn.Module):
         else:
             qkv = ops.linear(src, self.in_proj_weight, self.in_proj_bias)    # library GEMM (+ own wgrad)
         attn, o_sf = ops.diff_attention(qkv, pe, key_padding_mask, self.num_heads,
-                                        float(self.head_dim) ** -0.5, self.share_qk, drop=drop)
+                                        float(self.head_dim) ** -0.5, self.share_qk, drop=drop,
+                                        need_attn=need_attn)
         # the kernel writes O seq-first, so concat-heads -> out_proj needs no copy; `heads` is the
         # [B, Nmax, H, dh] view the FeTA encoder consumes (models.py:179)
         # defer_out_proj: the caller fuses out_proj with the degree scale, the residual and norm1 (one launch)
@@ -96,10 +98,12 @@ class DiffTransformerEncoderLayer(nn.Module):
         self.scaling = None
 
     def forward(self, src, pe=None, degree=None, src_mask=None, src_key_padding_mask=None,
-                need_heads=False, rowscale=None, bn_rows=None):
+                need_heads=False, rowscale=None, bn_rows=None, need_attn=True):
         """``rowscale`` (extension): the seq-first ``degree.t().contiguous()`` precomputed once per forward by
         the encoder instead of once per layer.  ``bn_rows`` (extension, BatchNorm variant): 0/1 weight per
-        flattened row ``[Nmax * B]``; rows with 0 stay out of the batch statistics (static-shape batches)."""
+        flattened row ``[Nmax * B]``; rows with 0 stay out of the batch statistics (static-shape batches).
+        ``need_attn=False`` (extension): the caller does not read the attention matrix of this layer; it comes back as
+        None and is never materialised (matrix-free attention kernels)."""
         if src_mask is not None:
             raise NotImplementedError("src_mask (attn_mask) is never passed by the reference "
                                       "(models.py:166) and is not implemented")
@@ -110,9 +114,10 @@ class DiffTransformerEncoderLayer(nn.Module):
             and ops.linear_layernorm_enabled(self.linear1.weight.shape[0], dm)
         if fused:
             src2, attn, heads, src = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask,
-                                                    with_residual=True, defer_out_proj=fuse_ln)
+                                                    with_residual=True, defer_out_proj=fuse_ln, need_attn=need_attn)
         else:
-            src2, attn, heads = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask)
+            src2, attn, heads = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask,
+                                               need_attn=need_attn)
         if rowscale is not None:
             pass
         elif degree is not None:

@@ -153,9 +153,13 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         attn = None
         rowscale = None if degree is None else degree.transpose(0, 1).contiguous()   # once, not per layer
         for layer_num, mod in enumerate(self.layers):
+            # the attention matrix is read only where the coefficients are built from it (:169-173) and, for the
+            # last layer, returned (:238): the other layers never materialise it
+            last = layer_num + 1 == num_layers
             output, attn, out_each_head = mod(output, pe=pe, degree=degree, src_mask=mask,
                                               src_key_padding_mask=src_key_padding_mask,
-                                              need_heads=True, rowscale=rowscale)
+                                              need_heads=True, rowscale=rowscale,
+                                              need_attn=last or not self.last_layer_filter)
             if self.last_layer_filter and layer_num + 1 != num_layers:              # :169-171
                 continue
             if ctx is None:
@@ -257,8 +261,10 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         attn = None
         rowscale = None if degree is None else degree.transpose(0, 1).contiguous()
         for layer_num, mod in enumerate(self.layers):
+            last = layer_num + 1 == num_layers
             output, attn, out_each_head = mod(output, pe=pe, degree=degree, src_key_padding_mask=masks,
-                                              need_heads=True, rowscale=rowscale, bn_rows=bn_rows)
+                                              need_heads=True, rowscale=rowscale, bn_rows=bn_rows,
+                                              need_attn=last or not self.last_layer_filter)
             if self.last_layer_filter and layer_num + 1 != num_layers:
                 continue
             if ctx is None:

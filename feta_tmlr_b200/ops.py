@@ -435,17 +435,80 @@ class DiffAttentionFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None
 
 
+# Layers whose attention matrix nobody reads (models.py:169-173) run the matrix-free kernels of
+# csrc/attention_rows.cu; FETA_ATTN_ROWS=0 returns them to the matrix-writing kernels.
+ATTN_ROWS = _os.environ.get("FETA_ATTN_ROWS", "1") == "1"
+
+
+def attn_rows_enabled(nmax, dh):
+    return bool(ATTN_ROWS and _lib.load().feta_attn_rows_supported(int(nmax), int(dh)))
+
+
+class DiffAttentionRowsFn(torch.autograd.Function):
+    """o [N,B,H,dh] (seq-first) = the same attention core as DiffAttentionFn without the attention matrix: the
+    forward pass keeps (row max, 1/clamped sum, flag) per query row, the backward pass recomputes P.
+    For the layers of models.py:166-173 whose matrix is not consumed."""
+
+    @staticmethod
+    def forward(ctx, qkv, pe, mask_u8, num_heads, scale, share_qk):
+        _need_cuda(qkv, pe, mask_u8)
+        lib = _lib.load()
+        qkv = _f32c(qkv)
+        N, B, d3 = qkv.shape
+        d = d3 // 3
+        H = num_heads
+        dh = d // H
+        pec = None if pe is None else _f32c(pe)
+        if pec is not None and tuple(pec.shape) != (B, N, N):
+            raise ValueError("pe must be [B, Nmax, Nmax] = %s, got %s" % ((B, N, N), tuple(pec.shape)))
+        o_heads = torch.empty((N, B, H, dh), dtype=torch.float32, device=qkv.device)   # seq-first
+        stats = torch.empty((B, H, N, 4), dtype=torch.float32, device=qkv.device)
+        base = qkv.data_ptr()
+        qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
+        with _timed("attn_fwd"):
+            check(lib.feta_attn_rows_fwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(o_heads), B * d, d,
+                                         _ptr(stats), B, H, N, dh, float(scale), _stream()), "feta_attn_rows_fwd")
+        ctx.save_for_backward(qkv, pec, mask_u8, stats, o_heads)
+        ctx.cfg = (H, float(scale), bool(share_qk))
+        return o_heads
+
+    @staticmethod
+    def backward(ctx, d_o_heads):
+        lib = _lib.load()
+        qkv, pec, mask_u8, stats, o_heads = ctx.saved_tensors
+        H, scale, share_qk = ctx.cfg
+        N, B, d3 = qkv.shape
+        d = d3 // 3
+        dh = d // H
+        d_o_heads = _f32c(d_o_heads)
+        dqkv = torch.empty_like(qkv)
+        base = qkv.data_ptr()
+        qp, kp, vp = base, base + (0 if share_qk else d * 4), base + 2 * d * 4
+        db = dqkv.data_ptr()
+        with _timed("attn_bwd"):
+            check(lib.feta_attn_rows_bwd(qp, kp, vp, B * d3, d3, _ptr(pec), _ptr(mask_u8), _ptr(stats), _ptr(o_heads),
+                                         _ptr(d_o_heads), B * d, d, db, db + d * 4, db + 2 * d * 4, B * d3, d3,
+                                         B, H, N, dh, scale, _stream()), "feta_attn_rows_bwd")
+        if share_qk:
+            dqkv[..., :d] += dqkv[..., d:2 * d]
+            dqkv[..., d:2 * d] = 0
+        return dqkv, None, None, None, None, None
+
+
 def dropout_multiplier(shape, p, device, generator=None):
     """0 or 1/(1-p) per attention weight (what ``F.dropout`` multiplies by); capture-safe (torch's Philox state)."""
     keep = torch.rand(shape, device=device, generator=generator) >= p
     return keep.to(torch.float32) * (1.0 / (1.0 - p))
 
 
-def diff_attention(qkv, pe, key_padding_mask, num_heads, scale, share_qk=False, drop=None):
+def diff_attention(qkv, pe, key_padding_mask, num_heads, scale, share_qk=False, drop=None, need_attn=True):
     """``drop`` (optional, [B, H, Nmax, Nmax]): attention-weight dropout multipliers; the returned attention is the
-    dropped one (``F.dropout(P)``), the saved one the un-dropped P."""
-    N, B, _ = qkv.shape
+    dropped one (``F.dropout(P)``), the saved one the un-dropped P.  ``need_attn=False``: the caller does not read
+    the attention matrix -- it is returned as None when the matrix-free kernels cover the shape."""
+    N, B, d3 = qkv.shape
     mask_u8 = _mask_u8(key_padding_mask, B, N, qkv.device)
+    if not need_attn and drop is None and qkv.is_cuda and attn_rows_enabled(N, d3 // 3 // num_heads):
+        return None, DiffAttentionRowsFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk)
     attn, o_sf, _ = DiffAttentionFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk, drop)
     return attn, o_sf            # o_sf [Nmax, B, H, dh]; out_each_head = o_sf.permute(1, 0, 2, 3)
 

@@ -173,8 +173,9 @@ int feta_arma_bwd(const float* dout /* [R, F] */, const float* prop, const float
  * Writes attn [B, H, Nmax, Nmax] (rows of padded queries are written as 0), o_heads
  * (= `out_each_head`, models.py:179; addressed o[n*o_stride_n + b*o_stride_b + h*dh + c], so the
  * caller picks [B, Nmax, H, dh] or the seq-first [Nmax, B, H*dh] the out-projection consumes without a
- * copy) and rowflag [B, H, Nmax]
- * (1 where rowsum > 1e-6, 0 where the clamp was active or the query is padding) for the backward.
+ * copy) and rowflag [B, H, Nmax] for the backward pass: 1 where rowsum > 1e-6; -(1 + argmax_j S_ij) where the clamp
+ * was active (the denominator is then a constant but the row maximum still carries a gradient to its argmax --
+ * the reference does not detach it; the tcgen05 variant writes 0 there and drops that term); 0 for a padded query.
  * use_tensor_cores != 0: QK^T and PV run as tcgen05.mma kind::tf32 with a 3xTF32 split (fp32-grade
  * accuracy), accumulators and P in TMEM (csrc/attention_tc.cu), when dh in {8,16,32} and
  * Nmax <= 224; otherwise, or with 0, the fp32 CUDA-core kernel (csrc/attention.cu).
@@ -206,6 +207,23 @@ int feta_attn_bwd_dropout(const float* q, const float* k, const float* v, int64_
                           const float* d_o_heads, int64_t o_stride_n, int64_t o_stride_b, const float* d_attn_post,
                           float* dq, float* dk, float* dv, int64_t dstride_n, int64_t dstride_b, int B, int H,
                           int nmax, int dh, float scale, void* stream);
+
+/* A6 / N1: the same attention core for the layers whose attention matrix nobody reads (transformer/models.py:169-173:
+ * under `last_layer_filter` only the LAST layer's matrix feeds get_filter_coefficients; the others use O alone).
+ * No [B, H, Nmax, Nmax] tensor is written or read: the forward pass keeps `stats` [B, H, Nmax, 4] = (row maximum of
+ * log2(e)*scale*q.k, 1/max(sum, 1e-6), sum > 1e-6, row is real) and the backward pass recomputes P from q, k and
+ * `pe` (csrc/attention_rows.cu: one thread per query / key row, K/V/Q/dO of the (graph, head) broadcast from shared
+ * memory).  Same argument meaning as feta_attn_fwd / feta_attn_bwd; `o_heads` in the backward pass is the forward
+ * output (delta_i = dO_i . O_i).  Needs nmax <= 256, dh in {4, 8, 16, 32}, 16-byte aligned head slices
+ * (feta_attn_rows_supported), else FETA_EUNSUPPORTED.  No dropout, no gradient of the attention matrix. */
+int feta_attn_rows_supported(int nmax, int dh);
+int feta_attn_rows_fwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
+                       const float* pe, const uint8_t* mask, float* o_heads, int64_t o_stride_n, int64_t o_stride_b,
+                       float* stats, int B, int H, int nmax, int dh, float scale, void* stream);
+int feta_attn_rows_bwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
+                       const float* pe, const uint8_t* mask, const float* stats, const float* o_heads,
+                       const float* d_o_heads, int64_t o_stride_n, int64_t o_stride_b, float* dq, float* dk, float* dv,
+                       int64_t dstride_n, int64_t dstride_b, int B, int H, int nmax, int dh, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * A6 (layer glue)  token-axis reductions of the layer's backward (the residual + norm1 / FFN +

@@ -35,14 +35,16 @@ def main():
     qkv = torch.randn(nmax, B, 3 * d, device=dev, requires_grad=True)
     scale = (d // H) ** -0.5
     go = torch.randn(nmax, B, H, d // H, device=dev)
-    def fwd(): ops.diff_attention(qkv.detach(), pe, mask, H, scale)
-    def fwd_bwd():                     # forward + backward in one captured region (same stream)
-        x = qkv.detach().requires_grad_()
-        a, o = ops.diff_attention(x, pe, mask, H, scale)
-        torch.autograd.grad(o, x, go)
-    f, fb = time_graphed(fwd), time_graphed(fwd_bwd)
-    out = {"config": name, "variant": variant, "B": B, "H": H, "nmax": nmax, "dh": d // H,
-           "fwd_us": round(f, 2), "bwd_us": round(fb - f, 2)}
+    out = {"config": name, "variant": variant, "B": B, "H": H, "nmax": nmax, "dh": d // H}
+    for tag, need in (("", True), ("rows_", False)):      # matrix-writing kernels / matrix-free kernels
+        def fwd(): ops.diff_attention(qkv.detach(), pe, mask, H, scale, need_attn=need)
+        def fwd_bwd():                     # forward + backward in one captured region (same stream)
+            x = qkv.detach().requires_grad_()
+            a, o = ops.diff_attention(x, pe, mask, H, scale, need_attn=need)
+            torch.autograd.grad(o, x, go)
+        f, fb = time_graphed(fwd), time_graphed(fwd_bwd)
+        out[tag + "fwd_us"] = round(f, 2)
+        out[tag + "bwd_us"] = round(fb - f, 2)
     print(json.dumps(out))
 
 if __name__ == "__main__":

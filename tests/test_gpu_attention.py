@@ -193,3 +193,108 @@ def test_attention_dropout_trains_and_is_off_in_eval(cuda):
         a, _ = m(src.to(cuda), **args)
         b, _ = m(src.to(cuda), **args)
     assert torch.equal(a, b)
+
+
+# ---- matrix-free kernels (csrc/attention_rows.cu): need_attn=False layers --------------------------------------
+@pytest.mark.parametrize("d,H", [(64, 8), (64, 4), (32, 1), (16, 4), (32, 8)])
+@pytest.mark.parametrize("nmax,with_pe", [(7, True), (37, True), (38, False), (100, True), (188, False), (256, True)])
+def test_attention_rows_layer_parity(cuda, d, H, nmax, with_pe):
+    """``need_attn=False``: no attention matrix is written; output, heads and every gradient still equal the oracle
+    layer's (whose matrix is simply not used)."""
+    from feta_tmlr_b200 import ops
+    assert ops.attn_rows_enabled(nmax, d // H)
+    o, m = _pair(cuda, d, H, seed=d + H + nmax)
+    src, pe, degree, mask = _inputs(nmax + 1, 4, nmax, d, with_pe=with_pe)
+    so = src.clone().requires_grad_()
+    oo, _, oh = o(so, pe=pe, degree=degree, src_key_padding_mask=mask, need_heads=True)
+    sg = src.to(cuda).requires_grad_()
+    go, ga, gh = m(sg, pe=None if pe is None else pe.to(cuda), degree=degree.to(cuda),
+                   src_key_padding_mask=mask.to(cuda), need_heads=True, need_attn=False)
+    assert ga is None
+    assert rel_err(gh, oh) < TOL and rel_err(go, oo) < TOL
+    w = torch.randn(oo.shape, generator=torch.Generator().manual_seed(1))
+    wh = torch.randn(oh.shape, generator=torch.Generator().manual_seed(2))
+    ((oo * w).sum() + (oh * wh).sum()).backward()
+    ((go * w.to(cuda)).sum() + (gh * wh.to(cuda)).sum()).backward()
+    assert rel_err(sg.grad, so.grad) < TOL
+    for (n1, p1), (n2, p2) in zip(o.named_parameters(), m.named_parameters()):
+        assert rel_err(p2.grad, p1.grad) < 2e-4, n1
+
+
+def _attn_core_oracle(qkv, pe, mask, H, scale):
+    """fp64 restatement of the attention core (oracle/layers.py: scores, key mask, max, exp * pe, clamp, P V) with
+    the product's zero-row convention for masked queries."""
+    N, B, d3 = qkv.shape
+    d, dh = d3 // 3, d3 // 3 // H
+    q, k, v = [t.reshape(N, B, H, dh).permute(1, 2, 0, 3) for t in qkv.split(d, dim=-1)]      # [B,H,N,dh]
+    s = (q * scale) @ k.transpose(-1, -2)
+    s = s.masked_fill(mask[:, None, None, :], float('-inf'))
+    mx = s.max(dim=-1, keepdim=True).values
+    e = torch.exp(s - torch.where(torch.isinf(mx), torch.zeros_like(mx), mx))      # a graph without a real key: e = 0
+    if pe is not None:
+        e = e * pe[:, None]
+    p = e / e.sum(dim=-1, keepdim=True).clamp(min=1e-6)
+    o = (p @ v) * (~mask)[:, None, :, None]
+    return o.permute(2, 0, 1, 3)                                                              # [N,B,H,dh]
+
+
+@pytest.mark.parametrize("case", ["interior_mask", "all_masked_graph", "clamped_rows", "share_qk"])
+def test_attention_rows_core_edge_cases(cuda, case):
+    """The core through ops.diff_attention(need_attn=False): a padding mask that is not a suffix (generic loops), a
+    graph with no real node, rows whose kernel-weighted sum falls under the 1e-6 clamp, shared q/k projections."""
+    from feta_tmlr_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    B, N, H, dh = 3, 45, 4, 8
+    d = H * dh
+    qkv = torch.randn(N, B, 3 * d, generator=g, dtype=torch.float64)
+    lens = torch.tensor([45, 20, 33])
+    mask = torch.arange(N)[None, :] >= lens[:, None]
+    a = torch.rand(B, N, N, generator=g, dtype=torch.float64)
+    pe = (a + a.transpose(1, 2)) * 0.5 * (torch.rand(B, N, N, generator=g) > 0.3)
+    share = case == "share_qk"
+    if case == "interior_mask":
+        mask[0, 3] = True
+        mask[0, 17] = True
+        mask[2, 0] = True
+    if case == "all_masked_graph":
+        mask[1, :] = True
+    if case == "clamped_rows":
+        pe[0, 5, :] = 0.0                          # sum 0: P = 0 / 1e-6
+        pe[2, 7, :] *= 1e-9                        # sum under the clamp: P = e * pe / 1e-6, no delta term
+    pe = pe * ((~mask)[:, :, None] & (~mask)[:, None, :])
+    if share:
+        qkv[..., d:2 * d] = qkv[..., :d]
+    scale = dh ** -0.5
+    ref_in = qkv.clone().requires_grad_()
+    if share:
+        qq = ref_in[..., :d]
+        o_ref = _attn_core_oracle(torch.cat([qq, qq, ref_in[..., 2 * d:]], dim=-1), pe, mask, H, scale)
+    else:
+        o_ref = _attn_core_oracle(ref_in, pe, mask, H, scale)
+    w = torch.randn(o_ref.shape, generator=g, dtype=torch.float64)
+    (o_ref * w).sum().backward()
+    x = qkv.float().to(cuda).requires_grad_()
+    attn, o = ops.diff_attention(x, pe.float().to(cuda), mask.to(cuda), H, scale, share_qk=share, need_attn=False)
+    assert attn is None
+    assert rel_err(o, o_ref.float()) < TOL
+    (o * w.float().to(cuda)).sum().backward()
+    gref = ref_in.grad.float()
+    if share:
+        gref = gref.clone()
+        gref[..., d:2 * d] = 0
+    assert rel_err(x.grad, gref) < TOL
+    # the matrix-writing kernels agree on the same inputs
+    x2 = qkv.float().to(cuda).requires_grad_()
+    _, o2 = ops.diff_attention(x2, pe.float().to(cuda), mask.to(cuda), H, scale, share_qk=share, need_attn=True)
+    (o2 * w.float().to(cuda)).sum().backward()
+    assert rel_err(o, o2) < 1e-5 and rel_err(x.grad, x2.grad) < 1e-4
+
+
+def test_attention_rows_switch_off(cuda, monkeypatch):
+    from feta_tmlr_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_ROWS", False)
+    o, m = _pair(cuda, 32, 4, seed=3)
+    src, pe, degree, mask = _inputs(3, 3, 12, 32)
+    go, ga = m(src.to(cuda), pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda),
+               need_attn=False)
+    assert ga is not None                                   # falls back to the matrix-writing kernels
