@@ -307,15 +307,36 @@ def kernel_times(cfg, B, model, bq, dev, use_graph):
     sc = float(d_ // H_) ** -0.5
     us = {}
 
-    def attn_f():
-        ops.diff_attention(qkv_t, pe_b, mask_b, H_, sc)
+    # the step runs the matrix-free kernels (csrc/attention_rows.cu) in every layer whose attention matrix nobody
+    # reads (all but the last under last_layer_filter) and the matrix-writing kernels (csrc/attention.cu) in the rest
+    for tag, need in (("attn", False), ("attn_matrix", True)):
+        def attn_f():
+            ops.diff_attention(qkv_t, pe_b, mask_b, H_, sc, need_attn=need)
 
-    def attn_fb():
-        xq = qkv_t.detach().requires_grad_()
-        _, o_ = ops.diff_attention(xq, pe_b, mask_b, H_, sc)
-        torch.autograd.grad(o_, xq, go_t)
-    us["attn_fwd"] = time_graphed(attn_f, dev)
-    us["attn_bwd"] = time_graphed(attn_fb, dev) - us["attn_fwd"]
+        def attn_fb():
+            xq = qkv_t.detach().requires_grad_()
+            _, o_ = ops.diff_attention(xq, pe_b, mask_b, H_, sc, need_attn=need)
+            torch.autograd.grad(o_, xq, go_t)
+        us[tag + "_fwd"] = time_graphed(attn_f, dev)
+        us[tag + "_bwd"] = time_graphed(attn_fb, dev) - us[tag + "_fwd"]
+    # the layer's four projections (forward and input gradient), csrc/linear_simt.cu
+    T_ = nm * B
+    lin_bytes = 0
+    us["linear_fwd_layer"] = us["linear_dx_layer"] = 0.0
+    for (fi, fo, relu) in ((d_, 3 * d_, False), (d_, d_, False), (d_, 2 * d_, True), (2 * d_, d_, False)):
+        xl = torch.randn(T_, fi, device=dev, generator=gq)
+        wl = torch.randn(fo, fi, device=dev, generator=gq) * 0.1
+        bl = torch.zeros(fo, device=dev)
+        gl = torch.randn(T_, fo, device=dev, generator=gq)
+        tf = time_graphed(lambda: ops.linear(xl, wl, bl, relu=relu), dev)
+
+        def lin_fb():
+            xr = xl.detach().requires_grad_()
+            torch.autograd.grad(ops.linear(xr, wl, bl, relu=relu), xr, gl)
+        us["linear_fwd_layer"] += tf
+        us["linear_dx_layer"] += time_graphed(lin_fb, dev) - tf
+        lin_bytes += 4 * (T_ * fi + fi * fo + T_ * fo)
+    us["linear_bytes_layer"] = float(lin_bytes)
     if use_graph:
         ctx_t = model.encoder.static_context(bq[6], mask_b, nm)
         Rt, Gt, dh_ = H_ * B * nm, H_ * B, d_ // H_
@@ -464,7 +485,10 @@ def run_config(name, args, dev, rank, world, steps, warmup, repeats, with_e2e=Tr
                                          "h2d_bytes_per_step": 8 * (3 * B + 2), "d2h_bytes_per_step": 4,
                                          "ms_per_step": round(ms_b / steps, 4), "spread": spread_b}
             if eng.plan_guard_tripped():
-                res["e2e_device_builder"] = {"error": "device-side plan guard tripped on a builder batch"}
+                enc = eng.model.encoder
+                metas = [list(p_.meta_host()[:8]) for p_ in getattr(enc, '_static_plans', [])]
+                res["e2e_device_builder"] = {"error": "device-side plan guard tripped on a builder batch",
+                                             "plan_meta": metas, "caps": list(caps)}
         except ValueError as e:                     # a batch beyond the static capacities of the host pool
             res["e2e_device_builder"] = {"error": str(e)[:120]}
     if with_kernels and rank == 0:
@@ -476,8 +500,11 @@ def run_config(name, args, dev, rank, world, steps, warmup, repeats, with_e2e=Tr
             lens = (~b[1]).sum(1).double()
             N, sumsq = int(lens.sum()), float((lens * lens).sum())
             # q,k,v + pe + attn write + O
-            attn_rows.append(3 * 4 * N * d + (4 * sumsq if b[2] is not None else 0) + 4 * H * sumsq + 4 * N * d)
-        res["attn_bytes"] = float(np.mean(attn_rows))
+            attn_rows.append((3 * 4 * N * d + (4 * sumsq if b[2] is not None else 0) + 4 * H * sumsq + 4 * N * d,
+                              4 * H * sumsq, N))
+        res["attn_bytes"] = float(np.mean([a[0] for a in attn_rows]))
+        res["attn_matrix_bytes"] = float(np.mean([a[1] for a in attn_rows]))     # the attention-matrix write alone
+        res["attn_tokens"] = float(np.mean([a[2] for a in attn_rows]))
     return res, eng
 
 
@@ -585,7 +612,8 @@ def main():
                             "unit": UNIT, "ms_per_step": round(pres["ms"] / args.steps, 4), "spread": pres["spread"],
                             "e2e": pres.get("e2e"), "gpu_launches": pres["launches"],
                             "allreduce_bytes_per_step": pres["bucket_bytes"] if world > 1 else 0,
-                            "kernels_us": {k: round(v, 2) for k, v in pres.get("kern_us", {}).items()}}
+                            "kernels_us": {k: round(v, 2) for k, v in pres.get("kern_us", {}).items()
+                                           if not k.endswith("_bytes_layer")}}
 
     line = None
     if rank == 0:
@@ -606,11 +634,39 @@ def main():
         small = ("%.2f MB per launch: L2-resident, instruction/latency bound at the BASELINE shape (SURVEY.md F5); "
                  "timed as CUDA-graph replays of the kernel ALONE on one of the step's batches (random q/k/v), not "
                  "inside the step graph")
-        attn_name = "attn_fwd_tiled_kernel<%d>" if (nm > 64 and dh in (8, 16)) else "attn_fwd_kernel<%d>"
-        roofline = roof(attn_name % dh, attn_bytes, kern_us["attn_fwd"], L,
-                        "largest share of the step among this repo's kernels (profiles/); " + small % (attn_bytes / 1e6),
-                        "attn_fwd_%s" % args.config)
-        roofline["attn_bwd_us_per_launch"] = round(kern_us["attn_bwd"], 2)
+        from feta_tmlr_b200 import ops as _ops
+        rows_on = bool(_ops.attn_rows_enabled(nm, dh)) and L > 1
+        # the dominant kernel = the largest (time per launch x launches per step) among this repo's kernels
+        lin_us = kern_us.pop("linear_fwd_layer")
+        lin_dx_us = kern_us.pop("linear_dx_layer")
+        lin_bytes = kern_us.pop("linear_bytes_layer")
+        n_rows_layers = (L - 1) if rows_on else 0
+        rows_bytes = attn_bytes - res["attn_matrix_bytes"]
+        cands = {
+            "linear_fwd": (lin_us / 4.0, 4 * L, lin_bytes / 4.0, "lsimt::linear_simt_kernel<0> (the layer's four "
+                           "projections; average of in_proj / out_proj / linear1 / linear2)"),
+            "linear_dx": (lin_dx_us / 4.0, 4 * L, lin_bytes / 4.0, "lsimt::linear_simt_kernel<1> (input gradients of "
+                          "the four projections, ReLU mask / residual gradient fused)"),
+            "attn_fwd": (kern_us["attn_fwd"], n_rows_layers, rows_bytes, "arows::attn_rows_fwd_kernel<%d>" % dh),
+            "attn_bwd": (kern_us["attn_bwd"], n_rows_layers, rows_bytes + 4.0 * res["attn_tokens"] * cfg['d_model'],
+                         "arows::attn_rows_bwd_kernel<%d>" % dh),
+            "attn_matrix_fwd": (kern_us["attn_matrix_fwd"], L - n_rows_layers, attn_bytes,
+                                ("attn_fwd_tiled_kernel<%d>" if (nm > 64 and dh in (8, 16)) else "attn_fwd_kernel<%d>")
+                                % dh),
+        }
+        shares = {k_: v_[0] * v_[1] for k_, v_ in cands.items()}
+        top = max(shares, key=shares.get)
+        t_us, t_n, t_bytes, t_name = cands[top]
+        roofline = roof(t_name, t_bytes, t_us, t_n,
+                        "largest (us per launch x launches per step) among this repo's kernels: %s; "
+                        % ", ".join("%s %.0f us/step" % (k_, v_) for k_, v_ in sorted(shares.items(), key=lambda kv: -kv[1]))
+                        + small % (t_bytes / 1e6), "%s_%s" % (top, args.config))
+        roofline["attn_rows_fwd_us_per_launch"] = round(kern_us["attn_fwd"], 2)
+        roofline["attn_rows_bwd_us_per_launch"] = round(kern_us["attn_bwd"], 2)
+        roofline["attn_matrix_fwd_us_per_launch"] = round(kern_us["attn_matrix_fwd"], 2)
+        roofline["attn_matrix_bwd_us_per_launch"] = round(kern_us["attn_matrix_bwd"], 2)
+        roofline["linear_fwd_us_per_layer"] = round(lin_us, 2)
+        roofline["linear_dx_us_per_layer"] = round(lin_dx_us, 2)
         roofline_cheb = roof("cheb_fwd_%s_kernel<%d>" % ("lane" if nm <= 64 else "graph", dh), cheb_bytes,
                              kern_us["cheb_fwd"], 1,
                              small % (cheb_bytes / 1e6) + "; roofline_sweep is the same kernel family on an HBM-sized "

@@ -335,15 +335,49 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
     y[i] = fmaf(a, x[i], y[i]);
 }
 
-// deterministic two-stage column sum: partial[b, c] then out[c]
-__global__ void colsum_partial_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ partial) {
+// deterministic two-stage column sum: partial[b, c] then out[c].  The array is walked flat (coalesced): a thread's
+// stride is a multiple of C, so it stays on one column; its CTA folds the 256 / C threads of each column in shared
+// memory, and one CTA folds the per-CTA partials the same way.  (C must divide 256: every head width does.)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int64_t R, int C,
+                                                             float* __restrict__ partial) {
+  __shared__ float red[256];
+  const int64_t n = R * C;
+  float s0 = 0.0f, s1 = 0.0f;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + stride < n; i += 2 * stride) s0 += x[i], s1 += x[i + stride];
+  if (i < n) s0 += x[i];
+  red[threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.0f;
+    for (int k = threadIdx.x; k < 256; k += C) s += red[k];
+    partial[(int64_t)blockIdx.x * C + threadIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nblk, int C,
+                                                           float* __restrict__ out) {
+  __shared__ float red[256];
+  const int c = threadIdx.x % C, slice = threadIdx.x / C, nsl = 256 / C;
+  float s = 0.0f;
+  for (int b = slice; b < nblk; b += nsl) s += partial[(int64_t)b * C + c];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.0f;
+    for (int k = threadIdx.x; k < 256; k += C) t += red[k];
+    out[threadIdx.x] = t;
+  }
+}
+// any C (un-tuned shapes)
+__global__ void colsum_partial_any_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ partial) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.0f;
     for (int64_t r = blockIdx.x; r < R; r += gridDim.x) s += x[r * C + c];
     partial[(int64_t)blockIdx.x * C + c] = s;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+__global__ void colsum_final_any_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     float s = 0.0f;
     for (int b = 0; b < nblk; ++b) s += partial[(int64_t)b * C + c];
@@ -352,6 +386,25 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int nblk,
 }
 
 constexpr int kColsumBlocks = 256;
+
+// out[c] = sum_r x[r, c];  `partial`: kColsumBlocks * C floats
+int colsum_launch(const float* x, int64_t R, int C, float* out, float* partial, cudaStream_t st) {
+  if (C >= 1 && C <= 256 && 256 % C == 0) {
+    int64_t want = ceil_div(R * C > 0 ? R * C : 1, 256 * 8);
+    const int nblk = (int)(want < kColsumBlocks ? want : kColsumBlocks);
+    colsum_partial_kernel<<<nblk, 256, 0, st>>>(x, R, C, partial);
+    FETA_LAUNCH_CHECK();
+    colsum_final_kernel<<<1, 256, 0, st>>>(partial, nblk, C, out);
+    FETA_LAUNCH_CHECK();
+    return FETA_OK;
+  }
+  const int nblk = (int)(R < kColsumBlocks ? (R > 0 ? R : 1) : kColsumBlocks);
+  colsum_partial_any_kernel<<<nblk, 64, 0, st>>>(x, R, C, partial);
+  FETA_LAUNCH_CHECK();
+  colsum_final_any_kernel<<<1, 64, 0, st>>>(partial, R > 0 ? nblk : 0, C, out);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
 
 static inline unsigned grid1d(int64_t n, int threads = 256) {
   int64_t b = ceil_div(n > 0 ? n : 1, threads);
@@ -508,11 +561,8 @@ extern "C" int feta_cheb_bwd(const float* dout, const float* x, const int32_t* r
   FETA_REQUIRE(partial != nullptr, "cheb_bwd: workspace carve failed");
 
   if (dbias != nullptr) {
-    const int nblk = (int)(R < kColsumBlocks ? (R > 0 ? R : 1) : kColsumBlocks);
-    colsum_partial_kernel<<<nblk, 64, 0, st>>>(dout, R, fout, partial);
-    FETA_LAUNCH_CHECK();
-    colsum_final_kernel<<<1, 64, 0, st>>>(partial, R > 0 ? nblk : 0, fout, dbias);
-    FETA_LAUNCH_CHECK();
+    const int rc = colsum_launch(dout, R, fout, dbias, partial, st);
+    if (rc != FETA_OK) return rc;
   }
   if (R == 0) {
     return FETA_OK;
@@ -605,3 +655,12 @@ extern "C" int feta_cheb_bwd(const float* dout, const float* x, const int32_t* r
   }
   return FETA_OK;
 }
+
+// out[c] = sum_r x[r, c] (deterministic two-stage sum); `partial`: feta_colsum_partial_floats(C) floats
+extern "C" int64_t feta_colsum_partial_floats(int C) { return (int64_t)feta::kColsumBlocks * (C > 0 ? C : 1); }
+extern "C" int feta_colsum(const float* x, int64_t R, int C, float* out, float* partial, void* stream) {
+  FETA_REQUIRE(R >= 0 && C >= 1, "colsum: bad sizes");
+  FETA_REQUIRE(x && out && partial, "colsum: NULL pointer argument");
+  return feta::colsum_launch(x, R, C, out, partial, (cudaStream_t)stream);
+}
+

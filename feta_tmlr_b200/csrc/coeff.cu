@@ -40,30 +40,57 @@ __global__ void __launch_bounds__(kCoeffThreads) coeff_scalar_kernel(const float
     }
   }
   __syncthreads();
+  // thread (j, slice): column j (coalesced across j), rows slice, slice + nsl, ...; the slices of a column are folded
+  // in shared memory in a fixed order.  Small graphs get several slices per column (ZINC: 4 x 64 threads), so the
+  // per-thread chain of dependent loads is nmax / nsl long instead of nmax.
+  float* red = reinterpret_cast<float*>(rank + nmax);  // [blockDim.x]
+  const int jw = nmax >= (int)blockDim.x ? (int)blockDim.x : ((nmax + 31) & ~31);
+  const int nsl = (int)blockDim.x / jw;
+  const int jl = (int)threadIdx.x % jw, slice = (int)threadIdx.x / jw;
   // pass 1: deg_j = sum_{i != j} a_ij + loop_j  (gcn_norm: degree over the TARGET index)
-  for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
-    float d = 0.0f, lw = 0.0f;
-    if (rank[j] >= 0) {
-      const float ajj = a[(size_t)j * nmax + j];
-      lw = (ajj != 0.0f) ? ajj : 1.0f;  // add_remaining_self_loops keeps an existing loop weight
-      float acc = 0.0f;
-      for (int i = 0; i < nmax; ++i)
+  for (int j0 = 0; j0 < nmax; j0 += jw) {
+    const int j = j0 + jl;
+    const bool real = slice < nsl && j < nmax && rank[j] >= 0;
+    float acc = 0.0f;
+    if (real) {
+#pragma unroll 4
+      for (int i = slice; i < nmax; i += nsl)
         if (i != j && rank[i] >= 0) acc += a[(size_t)i * nmax + j];
-      const float deg = acc + lw;
-      d = deg > 0.0f ? 1.0f / sqrtf(deg) : 0.0f;
     }
-    dis[j] = d;
-    loopw[j] = lw;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (slice == 0 && j < nmax) {
+      float d = 0.0f, lw = 0.0f;
+      if (real) {
+        for (int k = 1; k < nsl; ++k) acc += red[k * jw + jl];
+        const float ajj = a[(size_t)j * nmax + j];
+        lw = (ajj != 0.0f) ? ajj : 1.0f;  // add_remaining_self_loops keeps an existing loop weight
+        const float deg = acc + lw;
+        d = deg > 0.0f ? 1.0f / sqrtf(deg) : 0.0f;
+      }
+      dis[j] = d;
+      loopw[j] = lw;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // pass 2: s_j = dis_j * (sum_{i != j} dis_i a_ij + dis_j loop_j)
   const int64_t base = (int64_t)h * N + node_ptr[b];
-  for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
-    if (rank[j] < 0) continue;
+  for (int j0 = 0; j0 < nmax; j0 += jw) {
+    const int j = j0 + jl;
+    const bool real = slice < nsl && j < nmax && rank[j] >= 0;
     float acc = 0.0f;
-    for (int i = 0; i < nmax; ++i)
-      if (i != j && rank[i] >= 0) acc = fmaf(dis[i], a[(size_t)i * nmax + j], acc);
-    s[base + rank[j]] = dis[j] * (acc + dis[j] * loopw[j]);
+    if (real) {
+#pragma unroll 4
+      for (int i = slice; i < nmax; i += nsl)
+        if (i != j && rank[i] >= 0) acc = fmaf(dis[i], a[(size_t)i * nmax + j], acc);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (slice == 0 && real) {
+      for (int k = 1; k < nsl; ++k) acc += red[k * jw + jl];
+      s[base + rank[j]] = dis[j] * (acc + dis[j] * loopw[j]);
+    }
+    __syncthreads();
   }
 }
 
@@ -114,19 +141,24 @@ __global__ void __launch_bounds__(kCoeffThreads) coeff_pool_bwd_kernel(
   partial[((size_t)blockIdx.x * 2 + 1) * C + c] = ab;
 }
 
+// one warp per column: lanes walk the per-CTA partials, folded by shuffles (fixed order)
 __global__ void __launch_bounds__(kCoeffThreads) coeff_pool_bwd_final_kernel(const float* __restrict__ partial,
                                                                             int nblk, int C,
                                                                             float* __restrict__ d_wbar,
                                                                             float* __restrict__ d_gbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (kCoeffThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   float aw = 0.0f, ab = 0.0f;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     aw += partial[((size_t)b * 2 + 0) * C + c];
     ab += partial[((size_t)b * 2 + 1) * C + c];
   }
-  d_wbar[c] = aw;
-  d_gbias[c] = ab;
+  aw = warp_sum(aw);
+  ab = warp_sum(ab);
+  if (lane == 0) {
+    d_wbar[c] = aw;
+    d_gbias[c] = ab;
+  }
 }
 
 }  // namespace feta
@@ -139,7 +171,7 @@ extern "C" int feta_coeff_scalar(const float* attn, const uint8_t* mask, const i
   FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && N >= 0, "coeff_scalar: bad sizes");
   if (B == 0 || nmax == 0 || N == 0) return FETA_OK;
   FETA_REQUIRE(attn && mask && node_ptr && s, "coeff_scalar: NULL pointer argument");
-  const size_t smem = (size_t)nmax * 3 * sizeof(float);
+  const size_t smem = ((size_t)nmax * 3 + kCoeffThreads) * sizeof(float);
   FETA_REQUIRE(smem <= 200 * 1024, "coeff_scalar: nmax=%d too large", nmax);
   if (smem > 48 * 1024)
     FETA_CUDA(cudaFuncSetAttribute(coeff_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -172,7 +204,7 @@ extern "C" int feta_coeff_pool_bwd(const float* s, const int32_t* seg_lo, const 
   dim3 grid((unsigned)nblk, (unsigned)ceil_div(C, kCoeffThreads));
   coeff_pool_bwd_kernel<<<grid, kCoeffThreads, 0, st>>>(s, seg_lo, seg_hi, wbar, gbias, d_pooled, partial, G, C);
   FETA_LAUNCH_CHECK();
-  coeff_pool_bwd_final_kernel<<<(unsigned)ceil_div(C, kCoeffThreads), kCoeffThreads, 0, st>>>(partial, nblk, C,
+  coeff_pool_bwd_final_kernel<<<(unsigned)ceil_div(C, kCoeffThreads / 32), kCoeffThreads, 0, st>>>(partial, nblk, C,
                                                                                               d_wbar, d_gbias);
   FETA_LAUNCH_CHECK();
   return FETA_OK;

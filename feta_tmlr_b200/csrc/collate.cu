@@ -174,3 +174,120 @@ extern "C" int feta_collate_pad_pe(const int64_t* graph_ids, const int64_t* ds_n
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Static-shape batches (engine.GraphedTrainStep): everything DiffTransformerEncoderGenGCN.forward_static derives from
+// the padding mask and the packed edge list -- graph sizes, their prefix, the packed-id -> padded-slot map of every
+// edge endpoint, the segment bounds of the coefficient pooling and the real-row weights -- in two launches instead
+// of ~15 tiny tensor ops (each a ~2 us link of the step's dependent chain).
+// ---------------------------------------------------------------------------------------------------------------
+namespace feta {
+
+// one CTA: lens[b] = # un-masked positions, node_end = inclusive prefix; seg bounds; real-row weights
+__global__ void __launch_bounds__(1024) static_sizes_kernel(const uint8_t* __restrict__ mask, int B, int nmax, int H,
+                                                            int32_t* __restrict__ node_end, int32_t* __restrict__ lens,
+                                                            int32_t* __restrict__ slot_ptr, int32_t* __restrict__ seg_lo,
+                                                            int32_t* __restrict__ seg_hi, float* __restrict__ real) {
+  extern __shared__ int32_t sl[];                       // [B] lens, then their inclusive prefix
+  __shared__ int32_t wsum[32];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nw = blockDim.x >> 5;
+  for (int b = warp; b < B; b += nw) {                  // warp per graph
+    int c = 0;
+    for (int j = lane; j < nmax; j += 32) c += mask[(size_t)b * nmax + j] == 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) sl[b] = c, lens[b] = c;
+  }
+  __syncthreads();
+  // inclusive scan of sl[0..B) in chunks of blockDim.x
+  int32_t carry = 0;
+  for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+    const int b = b0 + t;
+    int32_t v = b < B ? sl[b] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = lane < nw ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += u;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const int32_t incl = v + (warp > 0 ? wsum[warp - 1] : 0) + carry;
+    if (b < B) node_end[b] = incl;
+    carry += wsum[nw - 1];
+    __syncthreads();
+  }
+  for (int b = t; b < B; b += blockDim.x) slot_ptr[b] = b * nmax;
+  for (int g = t; g < H * B; g += blockDim.x) {
+    seg_lo[g] = g * nmax;
+    seg_hi[g] = g * nmax + sl[g % B];
+  }
+  for (int idx = t; idx < nmax * B; idx += blockDim.x) {          // real [nmax, B]
+    const int i = idx / B, b = idx - i * B;
+    real[idx] = mask[(size_t)b * nmax + i] == 0 ? 1.0f : 0.0f;
+  }
+}
+
+// packed node id -> padded slot id (b * nmax + i) of every edge endpoint; (-1, -1) padding columns stay -1
+template <typename IT>
+__global__ void __launch_bounds__(256) static_edges_kernel(const IT* __restrict__ ei, int64_t ecap,
+                                                           const int32_t* __restrict__ node_end,
+                                                           const int32_t* __restrict__ lens, int B, int nmax, int heads,
+                                                           int64_t* __restrict__ out) {
+  const int64_t n = 2 * ecap;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = (int64_t)ei[idx];
+    int64_t r = -1;
+    if (v >= 0) {
+      int lo = 0, hi = B;                               // first b with node_end[b] > v  (searchsorted right=True)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(node_end + mid) > v) hi = mid;
+        else lo = mid + 1;
+      }
+      const int b = lo < B - 1 ? lo : B - 1;
+      r = v - ((int64_t)__ldg(node_end + b) - __ldg(lens + b)) + (int64_t)b * nmax;
+    }
+    const int64_t row = idx / ecap, col = idx - row * ecap;
+    for (int h = 0; h < heads; ++h)                     // per-head tiling (opt-in): head h's copy sits h * B * nmax further
+      out[row * ecap * heads + (int64_t)h * ecap + col] = r < 0 ? -1 : r + (int64_t)h * B * nmax;
+  }
+}
+
+}  // namespace feta
+
+extern "C" int feta_static_context(const uint8_t* mask, const void* edge_index, int edge_dtype, int64_t ecap, int B,
+                                   int nmax, int H, int tile_heads, int64_t* ei_out, int32_t* node_end, int32_t* lens,
+                                   int32_t* slot_ptr, int32_t* seg_lo, int32_t* seg_hi, float* real, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  FETA_REQUIRE(B >= 1 && nmax >= 1 && H >= 1 && ecap >= 0, "static_context: bad sizes");
+  FETA_REQUIRE(mask && ei_out && node_end && lens && slot_ptr && seg_lo && seg_hi && real && (edge_index || ecap == 0),
+               "static_context: NULL pointer argument");
+  FETA_REQUIRE(edge_dtype == FETA_DT_I32 || edge_dtype == FETA_DT_I64, "static_context: edge dtype must be int32/int64");
+  FETA_REQUIRE((size_t)B * sizeof(int32_t) <= 48 * 1024, "static_context: B=%d too large", B);
+  feta::static_sizes_kernel<<<1, 1024, (size_t)B * sizeof(int32_t), st>>>(mask, B, nmax, H, node_end, lens, slot_ptr,
+                                                                        seg_lo, seg_hi, real);
+  FETA_LAUNCH_CHECK();
+  if (ecap > 0) {
+    const int heads = tile_heads ? H : 1;
+    int64_t blocks = feta::ceil_div(2 * ecap, 256);
+    if (blocks > 4 * feta::kNumSMs) blocks = 4 * feta::kNumSMs;
+    if (edge_dtype == FETA_DT_I32)
+      feta::static_edges_kernel<int32_t><<<(unsigned)blocks, 256, 0, st>>>((const int32_t*)edge_index, ecap, node_end,
+                                                                          lens, B, nmax, heads, ei_out);
+    else
+      feta::static_edges_kernel<int64_t><<<(unsigned)blocks, 256, 0, st>>>((const int64_t*)edge_index, ecap, node_end,
+                                                                          lens, B, nmax, heads, ei_out);
+    FETA_LAUNCH_CHECK();
+  }
+  return FETA_OK;
+}

@@ -100,11 +100,25 @@ __global__ void __launch_bounds__(kSegThreads) masked_mean_fwd_kernel(const floa
   if (loc) atomicAdd(&s_cnt, loc);
   __syncthreads();
   const float cnt = (float)s_cnt;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  // thread (slice, c): rows slice, slice + nsl, ... of column c (coalesced across c), slices folded in shared memory
+  // in a fixed order
+  extern __shared__ float red[];                       // [blockDim.x]
+  const int nsl = C <= (int)blockDim.x ? (int)blockDim.x / C : 1;
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = c0 + (int)threadIdx.x % (C < (int)blockDim.x ? C : (int)blockDim.x);
+    const int slice = C < (int)blockDim.x ? (int)threadIdx.x / C : 0;
     float acc = 0.0f;
-    for (int n = 0; n < nmax; ++n)
-      if (mk[n] == 0) acc += x[(int64_t)b * sb + (int64_t)n * sn + c];
-    out[(size_t)b * C + c] = acc / cnt;  // the reference divides by mask.sum() un-clamped
+    if (c < C && slice < nsl)
+      for (int n = slice; n < nmax; n += nsl)
+        if (mk[n] == 0) acc += x[(int64_t)b * sb + (int64_t)n * sn + c];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (slice == 0 && c < C) {
+      float t = acc;
+      for (int k = 1; k < nsl; ++k) t += red[k * C + (c - c0)];
+      out[(size_t)b * C + c] = t / cnt;  // the reference divides by mask.sum() un-clamped
+    }
+    __syncthreads();
   }
 }
 
@@ -219,7 +233,8 @@ extern "C" int feta_masked_mean_fwd(const float* x, int64_t sb, int64_t sn, cons
                                     int nmax, int C, void* stream_) {
   if (B == 0) return FETA_OK;
   FETA_REQUIRE(x && mask && out && C >= 1 && nmax >= 1, "masked_mean_fwd: bad argument");
-  masked_mean_fwd_kernel<<<(unsigned)B, kSegThreads, 0, (cudaStream_t)stream_>>>(x, sb, sn, mask, out, nmax, C);
+  masked_mean_fwd_kernel<<<(unsigned)B, kSegThreads, kSegThreads * sizeof(float), (cudaStream_t)stream_>>>(
+      x, sb, sn, mask, out, nmax, C);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }

@@ -104,6 +104,10 @@ class GraphedTrainStep(object):
         self._slices, self._hooks, self._works = [], [], []
         self.losses = [None] * self.nsets
         self.loss = None
+        # guard words of the plans every step rebuilds, accumulated where no graph temporary can alias them: the two
+        # captured graphs share one memory pool, so a tensor allocated inside one capture (the plan's meta array) is
+        # only defined until the other graph's next replay
+        self._guard_acc = torch.zeros(1, dtype=torch.int32, device=dev)
         self.launches_per_step = 0
         self.cur = 0
         self._in_body = False
@@ -213,6 +217,9 @@ class GraphedTrainStep(object):
                 for p, v in live:
                     p.grad = v
             self.opt.step()
+        sp = getattr(self.model.encoder, '_static_plans', None)
+        if sp:
+            self._guard_acc.add_(sp[-1].meta[7:8])          # FETA_META_GUARD of the plan this step built
         self.losses[s] = loss.detach()
         self.loss = self.losses[s]
 
@@ -253,6 +260,4 @@ class GraphedTrainStep(object):
 
     def plan_guard_tripped(self):
         """Synchronising check of the device-side plan guard (see include/feta_b200.h)."""
-        enc = self.model.encoder
-        plans = list(enc.spectral_gnns._plans.values()) + list(getattr(enc, '_static_plans', []))
-        return any(p.meta_host()[7] for p in plans)
+        return bool(int(self._guard_acc.item()))

@@ -118,7 +118,7 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         if ctx is None:
             ctx = self.batch_context(edge_index, feature_indices, batch, masks, attn_weights.shape[2])
         s = ops.coeff_scalar(attn_weights, masks, ctx.node_ptr, ctx.N)             # :252-282, collapsed
-        wbar = self.gcn.weight.sum(dim=0)                                           # ones @ W
+        wbar = ops.colsum(self.gcn.weight)                                           # ones @ W
         pooled = ops.coeff_pool(s, ctx.plan.graph_ptr, wbar, self.gcn.bias)         # tanh + gap, :282-283
         pooled_coeff = self.linear(pooled)                                          # :284
         return pooled_coeff.reshape((self.num_heads, attn_weights.shape[0], pooled_coeff.shape[-1]))
@@ -206,31 +206,21 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         B, H = masks.shape[0], self.num_heads
         dev = masks.device
         ctx.N, ctx.B, ctx.nmax, ctx.H = B * nmax, B, nmax, H
-        if edge_index.dtype != torch.int64:                                         # int32 over the wire
-            edge_index = edge_index.long()
-        lens = (~masks).sum(dim=1)
-        node_ptr = torch.cumsum(lens, dim=0)                                        # packed end offsets
-        starts = (torch.arange(B, device=dev) * nmax)
-        ctx.node_ptr = starts.to(torch.int32)                                       # slot offset of graph b
-        g = torch.arange(H * B, device=dev)
-        ctx.seg_lo = (g * nmax).to(torch.int32)
-        ctx.seg_hi = (g * nmax + lens.repeat(H)).to(torch.int32)
-        # packed node id -> padded slot id  (b * nmax + i)
-        pad = edge_index < 0                                                        # (-1, -1) padding columns
-        b_of = torch.searchsorted(node_ptr, edge_index, right=True).clamp_(max=B - 1)
-        first = node_ptr - lens
-        ei = edge_index - first[b_of] + b_of * nmax
-        if self.tile_edges_per_head:
-            heads = torch.arange(H, device=dev, dtype=torch.int64)
-            ei = (ei.view(2, 1, -1) + (heads * B * nmax).view(1, H, 1)).reshape(2, -1)
-            pad = pad.view(2, 1, -1).expand(2, H, -1).reshape(2, -1)
-        ei = ei.masked_fill(pad, -1)
+        # graph sizes, their prefix, packed node id -> padded slot id (b * nmax + i) of every edge endpoint ((-1, -1)
+        # padding columns stay -1; int32 edge lists -- the static batches' wire format -- are widened here), the
+        # pooling segments and the real-row weights: two launches (csrc/collate.cu, feta_static_context)
+        ei, ctx.node_ptr, ctx.seg_lo, ctx.seg_hi, ctx.real = ops.static_context_tensors(
+            masks, edge_index, nmax, H, tile_heads=self.tile_edges_per_head)
         ctx.edge_index = ei
-        ctx.batch_all_heads = torch.arange(H * B * nmax, device=dev, dtype=torch.int64) // nmax
+        key = (H, B, nmax, dev)
+        cache = self.__dict__.setdefault('_static_batch_index', {})            # depends on the shapes only
+        if key not in cache:
+            cache.clear()
+            cache[key] = torch.arange(H * B * nmax, device=dev, dtype=torch.int64) // nmax
+        ctx.batch_all_heads = cache[key]
         ctx.plan = ops.build_cheb_plan(ei, ctx.batch_all_heads, H * B * nmax, H * B, 2.0,
                                        hints={'max_nodes': int(nmax), 'block_diagonal': True},
                                        norm=getattr(self.spectral_gnns, '_plan_norm', ops.NORM_CHEB_SYM))
-        ctx.real = (~masks).t().unsqueeze(-1).to(torch.float32)                     # [nmax, B, 1]
         # kept so that engine.GraphedTrainStep.plan_guard_tripped() can read the guard word of the plans its
         # captured graphs rebuild in place on every replay
         sp = self.__dict__.setdefault('_static_plans', [])
@@ -270,7 +260,7 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
             if ctx is None:
                 ctx = self.static_context(edge_index, masks, nmax)
             s = ops.coeff_scalar(attn, masks, ctx.node_ptr, B * nmax, zero_fill=True)
-            pooled = ops.coeff_pool(s, ctx.seg_lo, self.gcn.weight.sum(dim=0), self.gcn.bias, seg_hi=ctx.seg_hi)
+            pooled = ops.coeff_pool(s, ctx.seg_lo, ops.colsum(self.gcn.weight), self.gcn.bias, seg_hi=ctx.seg_hi)
             coeff_all_heads = self.linear(pooled).reshape((H, B, -1))
             coeff = coeff_all_heads.reshape((H * B, coeff_all_heads.shape[2]))
             x = out_each_head.permute(2, 0, 1, 3).reshape(H * B * nmax, -1)          # padded-domain stacking

@@ -568,6 +568,56 @@ class CoeffPoolFn(torch.autograd.Function):
         return None, None, None, d_w, d_b
 
 
+def static_context_tensors(masks, edge_index, nmax, num_heads, tile_heads=False):
+    """(ei [2, Ecap(*H)] int64 padded-slot ids, slot_ptr [B], seg_lo [H*B], seg_hi [H*B], real [nmax, B, 1]) of a
+    static-shape batch through feta_static_context (two launches)."""
+    _need_cuda(masks, edge_index)
+    lib = _lib.load()
+    B = masks.shape[0]
+    H = int(num_heads)
+    dev = masks.device
+    mask_u8 = _mask_u8(masks, B, nmax, dev)
+    if edge_index.dtype not in (torch.int32, torch.int64):
+        edge_index = edge_index.long()
+    edge_index = edge_index.contiguous()
+    ecap = edge_index.shape[1]
+    heads = H if tile_heads else 1
+    ei = torch.empty((2, ecap * heads), dtype=torch.int64, device=dev)
+    i32 = torch.empty(3 * B + 2 * H * B, dtype=torch.int32, device=dev)
+    node_end, lens, slot_ptr = i32[:B], i32[B:2 * B], i32[2 * B:3 * B]
+    seg_lo, seg_hi = i32[3 * B:3 * B + H * B], i32[3 * B + H * B:]
+    real = torch.empty((nmax, B, 1), dtype=torch.float32, device=dev)
+    check(lib.feta_static_context(_ptr(mask_u8), _ptr(edge_index), 1 if edge_index.dtype == torch.int32 else 0, ecap,
+                                  B, int(nmax), H, int(bool(tile_heads)), _ptr(ei), _ptr(node_end), _ptr(lens),
+                                  _ptr(slot_ptr), _ptr(seg_lo), _ptr(seg_hi), _ptr(real), _stream()),
+          "feta_static_context")
+    return ei, slot_ptr, seg_lo, seg_hi, real
+
+
+class ColSumFn(torch.autograd.Function):
+    """``w.sum(dim=0)`` of a 2-D fp32 tensor through feta_colsum (the all-ones GCN's ``colsum(W)``, coeff.cu)."""
+
+    @staticmethod
+    def forward(ctx, w):
+        _need_cuda(w)
+        lib = _lib.load()
+        w = _f32c(w)
+        R, C = w.shape
+        out = torch.empty(C, dtype=torch.float32, device=w.device)
+        partial = torch.empty(int(lib.feta_colsum_partial_floats(C)), dtype=torch.float32, device=w.device)
+        check(lib.feta_colsum(_ptr(w), R, C, _ptr(out), _ptr(partial), _stream()), "feta_colsum")
+        ctx.rows = R
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        return d_out.unsqueeze(0).expand(ctx.rows, -1)
+
+
+def colsum(w):
+    return ColSumFn.apply(w)
+
+
 def coeff_pool(s, graph_ptr, wbar, gbias, seg_hi=None):
     """``graph_ptr`` [G+1] (packed plan) or, with ``seg_hi``, explicit [G] segment starts / ends."""
     if seg_hi is None:

@@ -208,6 +208,23 @@ int feta_attn_bwd_dropout(const float* q, const float* k, const float* v, int64_
                           float* dq, float* dk, float* dv, int64_t dstride_n, int64_t dstride_b, int B, int H,
                           int nmax, int dh, float scale, void* stream);
 
+/* A7 / N2, static-shape batches (the collate of transformer/data.py:161-225 padded to dataset-wide capacities, see
+ * DESIGN.md section 5): what the padded-domain forward derives from the padding mask [B, Nmax] and the packed edge
+ * list [2, Ecap] (int32 or int64 node ids of the reference's packed numbering, (-1, -1) in unused columns):
+ *   lens[b], node_end[b] (inclusive prefix), slot_ptr[b] = b*Nmax, seg_lo/seg_hi [H*B] (rows g*Nmax .. g*Nmax+lens of
+ *   the coefficient pooling, models.py:283), real [Nmax, B] (1 = real row), and ei_out [2, Ecap (* H)]: every endpoint
+ *   re-numbered to its padded slot b*Nmax + i (tile_heads != 0: one copy per head, offset h*B*Nmax -- the per-head
+ *   edge tiling the reference omits).  Two launches; replaces ~15 tensor ops of the step's chain. */
+int feta_static_context(const uint8_t* mask, const void* edge_index, int edge_dtype, int64_t ecap, int B, int nmax,
+                        int H, int tile_heads, int64_t* ei_out, int32_t* node_end, int32_t* lens, int32_t* slot_ptr,
+                        int32_t* seg_lo, int32_t* seg_hi, float* real, void* stream);
+
+/* out[c] = sum_r x[r, c], x [R, C] row-major: the `gcn.weight.sum(dim=0)` of the collapsed coefficient path
+ * (transformer/models.py:252-282 with an all-ones feature matrix) and the bias gradient of ChebConvDynamic
+ * (ChebNetDynamic.py:187).  Deterministic two-stage sum; `partial` holds feta_colsum_partial_floats(C) floats. */
+int64_t feta_colsum_partial_floats(int C);
+int feta_colsum(const float* x, int64_t R, int C, float* out, float* partial, void* stream);
+
 /* A6 / N1: the same attention core for the layers whose attention matrix nobody reads (transformer/models.py:169-173:
  * under `last_layer_filter` only the LAST layer's matrix feeds get_filter_coefficients; the others use O alone).
  * No [B, H, Nmax, Nmax] tensor is written or read: the forward pass keeps `stats` [B, H, Nmax, 4] = (row maximum of

@@ -187,3 +187,44 @@ def test_graphed_step_fed_by_device_batch_builder(cuda):
         l1 = float(e1.step(host[i]))
         l2 = float(e2.step(builder.build(idsets[i], static=caps)))
         assert abs(l1 - l2) <= 1e-6 * max(1.0, abs(l1)), (i, l1, l2)
+
+
+@pytest.mark.parametrize("edge_dtype", [torch.int32, torch.int64])
+@pytest.mark.parametrize("tile", [False, True])
+@pytest.mark.parametrize("B,nmax,H", [(5, 9, 2), (128, 37, 8), (1000, 40, 4)])
+def test_static_context_tensors_bit_exact(cuda, B, nmax, H, tile, edge_dtype):
+    """feta_static_context (two launches) == the tensor-op formulation of the padded-domain context: graph sizes,
+    packed id -> padded slot id of every edge endpoint (searchsorted over the size prefix), (-1, -1) padding columns,
+    pooling segments, real-row weights."""
+    from feta_tmlr_b200 import ops
+    g = torch.Generator().manual_seed(B + nmax)
+    lens = torch.randint(1, nmax + 1, (B,), generator=g)
+    lens[0] = nmax
+    masks = torch.arange(nmax)[None, :] >= lens[:, None]
+    node_ptr = torch.cumsum(lens, 0)
+    first = node_ptr - lens
+    cols = []
+    for b in range(B):
+        e = int(torch.randint(0, 3 * int(lens[b]) + 1, (1,), generator=g))
+        cols.append(first[b] + torch.randint(0, int(lens[b]), (2, e), generator=g))
+    edges = torch.cat(cols, dim=1)
+    ecap = edges.shape[1] + 17
+    ei_in = torch.full((2, ecap), -1, dtype=torch.int64)
+    ei_in[:, :edges.shape[1]] = edges
+    # tensor-op formulation (what forward_static ran before)
+    pad = ei_in < 0
+    b_of = torch.searchsorted(node_ptr, ei_in, right=True).clamp_(max=B - 1)
+    ref = ei_in - first[b_of] + b_of * nmax
+    if tile:
+        heads = torch.arange(H, dtype=torch.int64)
+        ref = (ref.view(2, 1, -1) + (heads * B * nmax).view(1, H, 1)).reshape(2, -1)
+        pad = pad.view(2, 1, -1).expand(2, H, -1).reshape(2, -1)
+    ref = ref.masked_fill(pad, -1)
+    gidx = torch.arange(H * B)
+    ei, slot_ptr, seg_lo, seg_hi, real = ops.static_context_tensors(masks.to(cuda), ei_in.to(edge_dtype).to(cuda), nmax,
+                                                                     H, tile_heads=tile)
+    assert ei.dtype == torch.int64 and torch.equal(ei.cpu(), ref)
+    assert torch.equal(slot_ptr.cpu().long(), torch.arange(B) * nmax)
+    assert torch.equal(seg_lo.cpu().long(), gidx * nmax)
+    assert torch.equal(seg_hi.cpu().long(), gidx * nmax + lens.repeat(H))
+    assert torch.equal(real.cpu(), (~masks).t().unsqueeze(-1).float())
