@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(kMaxN) attn_rows_fwd_kernel(
   float* vals = Vs + (size_t)nmax * DH;              // [nr4]  1 = real key
   float* pes = vals + nr4 + (size_t)warp * kTile;
 
+  pdl_trigger();
+  pdl_wait();          // q / k / v come from the previous kernel of the chain
   // every load that does not wait for the mask is issued before the mask barriers (one memory round trip)
   const int64_t hb = (int64_t)b * sb + h * DH;
   float qr[DH];
@@ -259,6 +261,8 @@ __global__ void __launch_bounds__(kMaxN) attn_rows_bwd_kernel(
   float* pes = vals + nr4 + (size_t)warp * kTile;
 
   const int64_t hb = (int64_t)b * sb + h * DH, hob = (int64_t)b * osb + h * DH;
+  pdl_trigger();
+  pdl_wait();          // dO comes from the previous kernel of the chain
   float qr[DH], kr[DH], vr[DH], dor[DH];
 #pragma unroll
   for (int c = 0; c < DH; ++c) qr[c] = kr[c] = vr[c] = dor[c] = 0.0f;
@@ -424,8 +428,9 @@ static int launch_fwd(const float* q, const float* k, const float* v, int64_t sn
   static std::atomic<int> granted{48 * 1024};
   const int rc = grant_smem(attn_rows_fwd_kernel<DH, PE>, granted, smem);
   if (rc != FETA_OK) return rc;
-  attn_rows_fwd_kernel<DH, PE><<<(unsigned)(B * H), 32 * ((nmax + 31) / 32), smem, st>>>(
-      q, k, v, sn, sb, pe, mask, o_heads, osn, osb, reinterpret_cast<float4*>(stats), H, nmax, scale);
+  FETA_CUDA(launch_chain(attn_rows_fwd_kernel<DH, PE>, dim3((unsigned)(B * H)), dim3(32 * ((nmax + 31) / 32)), smem, st,
+                         q, k, v, sn, sb, pe, mask, o_heads, osn, osb, reinterpret_cast<float4*>(stats), H, nmax,
+                         scale));
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
@@ -439,9 +444,9 @@ static int launch_bwd(const float* q, const float* k, const float* v, int64_t sn
   static std::atomic<int> granted{48 * 1024};
   const int rc = grant_smem(attn_rows_bwd_kernel<DH, PE>, granted, smem);
   if (rc != FETA_OK) return rc;
-  attn_rows_bwd_kernel<DH, PE><<<(unsigned)(B * H), 32 * ((nmax + 31) / 32), smem, st>>>(
-      q, k, v, sn, sb, pe, mask, reinterpret_cast<const float4*>(stats), o_heads, d_o, osn, osb, dq, dk, dv, dsn, dsb,
-      H, nmax, scale);
+  FETA_CUDA(launch_chain(attn_rows_bwd_kernel<DH, PE>, dim3((unsigned)(B * H)), dim3(32 * ((nmax + 31) / 32)), smem, st,
+                         q, k, v, sn, sb, pe, mask, reinterpret_cast<const float4*>(stats), o_heads, d_o, osn, osb, dq,
+                         dk, dv, dsn, dsb, H, nmax, scale));
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }

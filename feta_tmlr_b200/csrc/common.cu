@@ -1,5 +1,6 @@
 // Library-wide state (error text, launch counter) and a small int32 device scan.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -11,6 +12,14 @@ std::atomic<int64_t> g_launch_count{0};
 char* last_error_buf() {
   static thread_local char buf[512] = "ok";
   return buf;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FETA_PDL");     // opt-in: measured SLOWER inside the step graph (see common.cuh)
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
 }
 
 void set_last_error(const char* fmt, ...) {

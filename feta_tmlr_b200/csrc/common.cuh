@@ -77,6 +77,37 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// The training step is a dependent chain of a few hundred 5-20 us kernels; between two of them the GPU idles for the
+// launch latency of the second.  A kernel launched with launch_chain() may start while its predecessor in the stream
+// drains: its CTAs are scheduled, run their prologue (index math, shared-memory carve-up) and block in pdl_wait()
+// until the predecessor has completed and flushed its writes.  Rules every such kernel follows: pdl_trigger() first,
+// then no global read of producer data and NO global write before pdl_wait().  Launched without the attribute
+// both calls are no-ops.
+// MEASURED, and therefore opt-in (FETA_PDL=1): inside the step's CUDA graph the early-scheduled CTAs spin in
+// pdl_wait() on SM slots that the graph's parallel branches (weight-gradient reductions, gradient all-reduce slices)
+// would otherwise use -- ZINC step 1.49 -> 1.83 ms, PATTERN 1.67 -> 1.79 ms with it on.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // common.cu: FETA_PDL == "1"
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // int32 exclusive scan of n elements (out may alias in); out[n] receives the total when
 // write_total != 0.  `scratch` needs scan_scratch_ints(n) int32 words.
 size_t scan_scratch_ints(int64_t n);

@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_fwd_kernel(
     float* __restrict__ mean, float* __restrict__ rstd, int64_t T, int D, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();          // a / b come from the previous kernel of the chain
   if (row >= T) return;
   float v[kLnMaxPerLane];
   float s = 0.0f;
@@ -169,12 +171,14 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_layernorm_bwd_kernel(
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float dg[PER], db[PER], gm[PER];
+  pdl_trigger();
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     dg[j] = db[j] = 0.0f;
     const int c = lane + 32 * j;
-    gm[j] = c < D ? gamma[c] : 0.0f;
+    gm[j] = c < D ? gamma[c] : 0.0f;             // a parameter: not written by the chain
   }
+  pdl_wait();          // dy comes from the previous kernel of the chain
   for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < T; row += (int64_t)gridDim.x * kLnWarps) {
     const float mu = mean[row], rs = rstd[row];
     float g[PER], xh[PER];
@@ -309,8 +313,8 @@ extern "C" int feta_add_layernorm_fwd(const float* a, const float* b, const floa
   if (T == 0) return FETA_OK;
   FETA_REQUIRE(a && gamma && beta && y && z && mean && rstd && (b || !bscale),
                "add_layernorm_fwd: NULL pointer argument");
-  add_layernorm_fwd_kernel<<<(unsigned)ceil_div(T, kLnWarps), kLnWarps * 32, 0, (cudaStream_t)stream_>>>(
-      a, b, bscale, gamma, beta, y, z, mean, rstd, T, D, eps);
+  FETA_CUDA(launch_chain(add_layernorm_fwd_kernel, dim3((unsigned)ceil_div(T, kLnWarps)), dim3(kLnWarps * 32), 0,
+                         (cudaStream_t)stream_, a, b, bscale, gamma, beta, y, z, mean, rstd, T, D, eps));
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
@@ -325,12 +329,11 @@ static void launch_ln_bwd(bool fold, int nblk, cudaStream_t st, const float* dy,
                           const float* rstd, const float* gamma, const float* bscale, float* dz, float* db_scaled,
                           float* partial, float* dgamma, float* dbeta, int32_t* counter, int64_t T, int D) {
   if (fold)
-    add_layernorm_bwd_kernel<PER, true><<<nblk, kLnWarps * 32, 0, st>>>(dy, z, mean, rstd, gamma, bscale, dz, db_scaled,
-                                                                        partial, dgamma, dbeta, counter, T, D);
+    launch_chain(add_layernorm_bwd_kernel<PER, true>, dim3(nblk), dim3(kLnWarps * 32), 0, st, dy, z, mean, rstd, gamma,
+                 bscale, dz, db_scaled, partial, dgamma, dbeta, counter, T, D);
   else
-    add_layernorm_bwd_kernel<PER, false><<<nblk, kLnWarps * 32, 0, st>>>(dy, z, mean, rstd, gamma, bscale, dz,
-                                                                         db_scaled, partial, dgamma, dbeta, counter, T,
-                                                                         D);
+    launch_chain(add_layernorm_bwd_kernel<PER, false>, dim3(nblk), dim3(kLnWarps * 32), 0, st, dy, z, mean, rstd, gamma,
+                 bscale, dz, db_scaled, partial, dgamma, dbeta, counter, T, D);
 }
 
 extern "C" int feta_add_layernorm_bwd(const float* dy, const float* z, const float* mean, const float* rstd,

@@ -45,13 +45,9 @@ __global__ void __launch_bounds__(kThreads) linear_simt_kernel(const float* __re
   const int n0 = blockIdx.y * kBN;
   const int kq = KR >> 2;                        // float4 per A row
 
-  // ---- one wave of asynchronous copies: the A tile and the whole B panel
-  for (int i = tid; i < kBM * kq; i += kThreads) {
-    const int r = i / kq, q = i - r * kq;
-    float* dst = As + r * lda + 4 * q;
-    if (row0 + r < T) cp_async16(dst, A + (row0 + r) * KR + 4 * q);
-    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  // ---- one wave of asynchronous copies: the whole B panel (a parameter: nothing in the chain writes it, so it is
+  // requested while the previous kernel of the chain drains), then -- once that kernel has completed -- the A tile
+  pdl_trigger();
   if (MODE == 0) {
     for (int i = tid; i < kBN * kq; i += kThreads) {
       const int n = i / kq, q = i - n * kq;
@@ -63,6 +59,13 @@ __global__ void __launch_bounds__(kThreads) linear_simt_kernel(const float* __re
       const int k = i / NQ, q = i - k * NQ;
       cp_async16(Ws + k * (kBN + 4) + 4 * q, W + (int64_t)k * ldw + n0 + 4 * q);
     }
+  }
+  pdl_wait();
+  for (int i = tid; i < kBM * kq; i += kThreads) {
+    const int r = i / kq, q = i - r * kq;
+    float* dst = As + r * lda + 4 * q;
+    if (row0 + r < T) cp_async16(dst, A + (row0 + r) * KR + 4 * q);
+    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   cp_async_wait_all();
   __syncthreads();
@@ -177,7 +180,8 @@ static int launch_bm(const float* A, const float* W, const float* bias, const fl
     granted.store((int)smem, std::memory_order_relaxed);
   }
   dim3 grid((unsigned)ceil_div(T, BM), (unsigned)(NOUT / kBN));
-  linear_simt_kernel<MODE, BM><<<grid, kThreads, smem, st>>>(A, W, bias, dres, mask_src, Y, T, KR, NOUT, ldw, relu);
+  FETA_CUDA(launch_chain(linear_simt_kernel<MODE, BM>, grid, dim3(kThreads), smem, st, A, W, bias, dres, mask_src, Y, T,
+                         KR, NOUT, ldw, relu));
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }

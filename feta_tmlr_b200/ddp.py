@@ -57,3 +57,32 @@ def shard_indices(num_items, rank, world_size):
     base, rem = divmod(num_items, world_size)
     start = rank * base + min(rank, rem)
     return range(start, start + base + (1 if rank < rem else 0))
+
+
+def gather_predictions(*tensors, process_group=None):
+    """Epoch-end exchange for the metrics the reference computes over the WHOLE evaluation set on one process --
+    ``accuracy_SBM``'s confusion matrix (experiments/run_transformer_gengcn_SBM_cv.py:126-143, called per batch at
+    :209/:255) and the OGB ``Evaluator`` ROC-AUC over all predictions (run_transformer_gengcn_molhiv.py:215-219):
+    every rank contributes the rows its shard produced (row counts may differ), every rank receives the
+    concatenation in rank order.  One ``all_gather`` of the row counts and one padded ``all_gather`` per tensor
+    (NCCL has no variable-size gather); not on the training path.  Single process: returns the inputs."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) == 1:
+        return tensors if len(tensors) > 1 else tensors[0]
+    world = dist.get_world_size(process_group)
+    n = tensors[0].shape[0]
+    for t in tensors:
+        if t.shape[0] != n:
+            raise ValueError("gather_predictions: tensors must share their first dimension")
+    dev = tensors[0].device
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=dev), group=process_group)
+    counts = [int(c) for c in counts]
+    cap = max(counts)
+    out = []
+    for t in tensors:
+        pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        pad[:n] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=process_group)
+        out.append(torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0))
+    return tuple(out) if len(out) > 1 else out[0]

@@ -185,6 +185,12 @@ ref.load_state_dict(model.state_dict())
 ref_flat = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
 assert torch.allclose(bucket.flat * world, ref_flat, atol=1e-6), (bucket.flat * world - ref_flat).abs().max()
 assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in model.parameters())
+# epoch-end metric exchange: ragged shards come back concatenated in rank order on every rank
+full_pred = torch.arange(11 * 3, dtype=torch.float32).view(11, 3)
+full_lab = torch.arange(11)
+mine = list(ddp.shard_indices(11, rank, world))
+pred, lab = ddp.gather_predictions(full_pred[mine], full_lab[mine])
+assert torch.equal(pred, full_pred) and torch.equal(lab, full_lab), (pred, lab)
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 '''
