@@ -161,6 +161,100 @@ __global__ void __launch_bounds__(kThreads) linear_simt_kernel(const float* __re
   }
 }
 
+// Forward projection onto the model width (NOUT = 64 = one column tile, so a CTA owns whole output rows) with the
+// layer's degree scale, residual add and LayerNorm in the epilogue:
+//   z = res + bscale[row] * (X . W^T + b),   y = (z - mean) * rstd * gamma + beta
+// A row's 64 columns sit in the 16 threads of one half warp (4 columns each): mean and variance are two xor-shuffle
+// folds.  Replaces the projection launch + the add_layernorm launch of out_proj -> norm1 and linear2 -> norm2.
+template <int kBM>
+__global__ void __launch_bounds__(kThreads) linear_simt_ln_kernel(
+    const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
+    const float* __restrict__ res, const float* __restrict__ bscale, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float* __restrict__ Y, float* __restrict__ Z, float* __restrict__ mean,
+    float* __restrict__ rstd, int64_t T, int KR, float eps) {
+  extern __shared__ __align__(16) float smem[];
+  const int lda = KR + 4;
+  float* As = smem;                              // [kBM][lda]
+  float* Ws = smem + kBM * lda;                  // [kBN][lda]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)blockIdx.x * kBM;
+  const int kq = KR >> 2;
+  pdl_trigger();
+  for (int i = tid; i < kBN * kq; i += kThreads) {
+    const int n = i / kq, q = i - n * kq;
+    cp_async16(Ws + n * lda + 4 * q, W + (int64_t)n * KR + 4 * q);
+  }
+  pdl_wait();
+  for (int i = tid; i < kBM * kq; i += kThreads) {
+    const int r = i / kq, q = i - r * kq;
+    float* dst = As + r * lda + 4 * q;
+    if (row0 + r < T) cp_async16(dst, A + (row0 + r) * KR + 4 * q);
+    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  constexpr int RT = kBM / 8;
+  float2 p[RT][4];
+#pragma unroll
+  for (int i = 0; i < RT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[i][j] = make_float2(0.f, 0.f);
+  const float* a0 = As + ty * lda;
+  const float* w0 = Ws + tx * lda;
+#pragma unroll 4
+  for (int kk = 0; kk < KR; kk += 4) {
+    float4 a[RT], b[4];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + (8 * i) * lda + kk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(w0 + (16 * j) * lda + kk);
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p[i][j] = __ffma2_rn(make_float2(a[i].x, a[i].y), make_float2(b[j].x, b[j].y), p[i][j]);
+        p[i][j] = __ffma2_rn(make_float2(a[i].z, a[i].w), make_float2(b[j].z, b[j].w), p[i][j]);
+      }
+  }
+  float gm[4], bt[4], bi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = tx + 16 * j;
+    gm[j] = __ldg(gamma + col), bt[j] = __ldg(beta + col), bi[j] = bias ? __ldg(bias + col) : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < RT; ++i) {
+    const int64_t row = row0 + ty + 8 * i;
+    const bool live = row < T;
+    const float bs = (live && bscale) ? __ldg(bscale + row) : 1.0f;
+    float v[4], s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lin = p[i][j].x + p[i][j].y + bi[j];
+      v[j] = live ? fmaf(bs, lin, __ldg(res + row * kBN + tx + 16 * j)) : 0.0f;
+      s += v[j];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s * (1.0f / kBN);
+    float q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q = fmaf(v[j] - mu, v[j] - mu, q);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rs = rsqrtf(q * (1.0f / kBN) + eps);
+    if (!live) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = tx + 16 * j;
+      Z[row * kBN + col] = v[j];
+      Y[row * kBN + col] = fmaf((v[j] - mu) * rs, gm[j], bt[j]);
+    }
+    if (tx == 0) mean[row] = mu, rstd[row] = rs;
+  }
+}
+
 static bool eligible(int64_t T, int KR, int NOUT, const void* a, const void* w, const void* y, const void* p1,
                      const void* p2) {
   const uintptr_t ptrs = (uintptr_t)a | (uintptr_t)w | (uintptr_t)y | (uintptr_t)p1 | (uintptr_t)p2;
@@ -196,7 +290,36 @@ static int launch(const float* A, const float* W, const float* bias, const float
   return launch_bm<MODE, 32>(A, W, bias, dres, mask_src, Y, T, KR, NOUT, ldw, relu, st);
 }
 
+template <int BM>
+static int launch_ln_bm(const float* X, const float* W, const float* bias, const float* res, const float* bscale,
+                        const float* gamma, const float* beta, float* y, float* z, float* mean, float* rstd, int64_t T,
+                        int in, float eps, cudaStream_t st) {
+  const size_t smem = ((size_t)BM * (in + 4) + (size_t)kBN * (in + 4)) * 4;
+  static std::atomic<int> granted{0};
+  if ((int)smem > granted.load(std::memory_order_relaxed)) {
+    FETA_CUDA(cudaFuncSetAttribute(linear_simt_ln_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    granted.store((int)smem, std::memory_order_relaxed);
+  }
+  FETA_CUDA(launch_chain(linear_simt_ln_kernel<BM>, dim3((unsigned)ceil_div(T, BM)), dim3(kThreads), smem, st, X, W,
+                         bias, res, bscale, gamma, beta, y, z, mean, rstd, T, in, eps));
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+
 }  // namespace lsimt
+
+// y = LayerNorm(res + bscale * (X . W^T + b)); returns 1 when the shape is not eligible (out must be 64)
+int linear_simt_ln_try(const float* X, const float* W, const float* bias, const float* res, const float* bscale,
+                       const float* gamma, const float* beta, float* y, float* z, float* mean, float* rstd, int64_t T,
+                       int in, int out, float eps, cudaStream_t st) {
+  if (out != lsimt::kBN || in < 4 || in % 4 != 0 || in > 256 || T < 1) return 1;
+  const uintptr_t ptrs = (uintptr_t)X | (uintptr_t)W | (uintptr_t)res | (uintptr_t)y | (uintptr_t)z;
+  if (ptrs % 16) return 1;
+  // 16-row tiles while 32-row tiles would leave SMs idle (one column tile per row block: T / 32 CTAs)
+  if (ceil_div(T, 32) < kNumSMs)
+    return lsimt::launch_ln_bm<16>(X, W, bias, res, bscale, gamma, beta, y, z, mean, rstd, T, in, eps, st);
+  return lsimt::launch_ln_bm<32>(X, W, bias, res, bscale, gamma, beta, y, z, mean, rstd, T, in, eps, st);
+}
 
 // Y[T, out] = act(X[T, in] . W[out, in]^T + b); returns 1 when the shape is not eligible
 int linear_simt_fwd_try(const float* X, const float* W, const float* bias, float* Y, int64_t T, int in, int out, int relu,
@@ -213,6 +336,10 @@ int linear_simt_dx_try(const float* dY, const float* W, const float* dres, const
 }
 
 }  // namespace feta
+
+extern "C" int feta_linear_layernorm_simt_supported(int in, int out) {
+  return out == 64 && in >= 64 && in % 64 == 0 && in <= 256;
+}
 
 extern "C" int feta_linear_simt_supported(int in, int out) {
   return in >= 64 && out >= 64 && in % 64 == 0 && out % 64 == 0 && in <= 256 && out <= 256;

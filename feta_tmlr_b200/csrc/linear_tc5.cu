@@ -569,15 +569,38 @@ extern "C" int feta_linear_layernorm_supported(int in, int out) {
   return out == 64 && in >= 64 && in % 64 == 0 && in <= 1024 && getenv("FETA_LINEAR_NO_TC5") == nullptr;
 }
 
-extern "C" int feta_linear_layernorm_fwd(const float* X, const float* W, const float* bias, const float* res,
-                                         const float* bscale, const float* gamma, const float* beta, float* y, float* z,
-                                         float* mean, float* rstd, int64_t T, int in, int out, float eps, void* stream_) {
+namespace feta {
+int linear_simt_ln_try(const float* X, const float* W, const float* bias, const float* res, const float* bscale,
+                       const float* gamma, const float* beta, float* y, float* z, float* mean, float* rstd, int64_t T,
+                       int in, int out, float eps, cudaStream_t st);
+}
+extern "C" int feta_linear_layernorm_simt_supported(int in, int out);
+
+// impl: FETA_LINEAR_AUTO (SIMT kernel when eligible, else tcgen05), FETA_LINEAR_SIMT, FETA_LINEAR_TC5
+extern "C" int feta_linear_layernorm_fwd_ex(const float* X, const float* W, const float* bias, const float* res,
+                                            const float* bscale, const float* gamma, const float* beta, float* y,
+                                            float* z, float* mean, float* rstd, int64_t T, int in, int out, float eps,
+                                            int impl, void* stream_) {
   using namespace feta;
-  FETA_REQUIRE(T >= 0 && feta_linear_layernorm_supported(in, out), "linear_layernorm_fwd: unsupported in=%d out=%d", in,
-               out);
+  const bool simt_ok = feta_linear_layernorm_simt_supported(in, out) != 0;
+  const bool tc5_ok = feta_linear_layernorm_supported(in, out) != 0;
+  FETA_REQUIRE(T >= 0 && (simt_ok || tc5_ok), "linear_layernorm_fwd: unsupported in=%d out=%d", in, out);
   if (T == 0) return FETA_OK;
   FETA_REQUIRE(X && W && res && gamma && beta && y && z && mean && rstd, "linear_layernorm_fwd: NULL pointer");
   const uintptr_t ptrs = (uintptr_t)X | (uintptr_t)W | (uintptr_t)res | (uintptr_t)y | (uintptr_t)z | (uintptr_t)bias;
   FETA_REQUIRE((ptrs % 16) == 0, "linear_layernorm_fwd: pointers must be 16-byte aligned");
+  if (simt_ok && (impl == FETA_LINEAR_AUTO || impl == FETA_LINEAR_SIMT)) {
+    const int rc = linear_simt_ln_try(X, W, bias, res, bscale, gamma, beta, y, z, mean, rstd, T, in, out, eps,
+                                      (cudaStream_t)stream_);
+    if (rc <= 0) return rc;
+  }
+  FETA_REQUIRE(tc5_ok, "linear_layernorm_fwd: in=%d out=%d not eligible for the tcgen05 kernel", in, out);
   return lin5::launch_ln(X, W, bias, res, bscale, gamma, beta, y, z, mean, rstd, T, in, eps, (cudaStream_t)stream_);
+}
+
+extern "C" int feta_linear_layernorm_fwd(const float* X, const float* W, const float* bias, const float* res,
+                                         const float* bscale, const float* gamma, const float* beta, float* y, float* z,
+                                         float* mean, float* rstd, int64_t T, int in, int out, float eps, void* stream_) {
+  return feta_linear_layernorm_fwd_ex(X, W, bias, res, bscale, gamma, beta, y, z, mean, rstd, T, in, out, eps,
+                                      FETA_LINEAR_AUTO, stream_);
 }

@@ -869,6 +869,9 @@ LINEAR_TC5 = _os.environ.get("FETA_LINEAR_TC5", "0") == "1"
 # (csrc/linear_simt.cu) whenever (in, out) are multiples of 64 up to 256 -- every projection of every BASELINE
 # config; FETA_LINEAR_SIMT=0 returns them to the library GEMM.
 LINEAR_SIMT = _os.environ.get("FETA_LINEAR_SIMT", "1") == "1"
+# out_proj -> norm1 and linear2 -> norm2 as ONE launch each (projection with the degree scale, residual add and
+# LayerNorm in its epilogue, csrc/linear_simt.cu); FETA_LINEAR_LN_FUSED=0: projection launch + add_layernorm launch
+LINEAR_LN_FUSED = _os.environ.get("FETA_LINEAR_LN_FUSED", "1") == "1"
 _IMPL_SIMT, _IMPL_TC5, _IMPL_MMA = 1, 2, 3
 
 
@@ -1096,9 +1099,10 @@ def add_layer_norm(a, b, gamma, beta, eps=1e-5, bscale=None):
 
 
 class LinearAddLayerNormFn(torch.autograd.Function):
-    """y = LayerNorm(res + bscale * (x W^T + b)) * gamma + beta in ONE launch (csrc/linear_tc5.cu: tcgen05 GEMM with
-    the degree scale, residual add and LayerNorm in its epilogue); backward = LayerNorm backward, then the Linear's
-    dX (tcgen05, optional ReLU mask of its input) and its weight gradients (side stream when opted in)."""
+    """y = LayerNorm(res + bscale * (x W^T + b)) * gamma + beta in ONE launch: the projection with the degree scale,
+    residual add and LayerNorm in its epilogue (default csrc/linear_simt.cu, exact fp32; FETA_LINEAR_TC5=1:
+    csrc/linear_tc5.cu, tcgen05 3xTF32); backward = LayerNorm backward, then the Linear's dX (optional ReLU mask of
+    its input) and its weight gradients (side stream when opted in)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, res, bscale, gamma, beta, eps, mask_input_grad):
@@ -1116,9 +1120,10 @@ class LinearAddLayerNormFn(torch.autograd.Function):
         z = torch.empty(res.shape, dtype=torch.float32, device=x.device)
         mean = torch.empty(T, dtype=torch.float32, device=x.device)
         rstd = torch.empty(T, dtype=torch.float32, device=x.device)
-        check(lib.feta_linear_layernorm_fwd(_ptr(x2), _ptr(w), _ptr(bc), _ptr(res2), _ptr(bscale), _ptr(gamma),
-                                            _ptr(beta), _ptr(y), _ptr(z), _ptr(mean), _ptr(rstd), T, in_f, out_f,
-                                            float(eps), _stream()), "feta_linear_layernorm_fwd")
+        check(lib.feta_linear_layernorm_fwd_ex(_ptr(x2), _ptr(w), _ptr(bc), _ptr(res2), _ptr(bscale), _ptr(gamma),
+                                               _ptr(beta), _ptr(y), _ptr(z), _ptr(mean), _ptr(rstd), T, in_f, out_f,
+                                               float(eps), linear_layernorm_impl(in_f, out_f), _stream()),
+              "feta_linear_layernorm_fwd")
         ctx.save_for_backward(x, w, z, mean, rstd, gamma, bscale)
         ctx.has_bias = bias is not None
         ctx.mask_in = bool(mask_input_grad)
@@ -1143,8 +1148,18 @@ class LinearAddLayerNormFn(torch.autograd.Function):
         return dx, dw, db, dz.view(z.shape), None, dg, dbeta, None, None
 
 
+def linear_layernorm_impl(in_f, out_f):
+    """0: separate projection + add_layer_norm launches; else the kernel family of the fused launch."""
+    lib = _lib.load()
+    if LINEAR_TC5 and lib.feta_linear_layernorm_supported(int(in_f), int(out_f)):
+        return _IMPL_TC5
+    if LINEAR_SIMT and LINEAR_LN_FUSED and lib.feta_linear_layernorm_simt_supported(int(in_f), int(out_f)):
+        return _IMPL_SIMT
+    return 0
+
+
 def linear_layernorm_enabled(in_f, out_f):
-    return bool(LINEAR_TC5 and _lib.load().feta_linear_layernorm_supported(int(in_f), int(out_f)))
+    return linear_layernorm_impl(in_f, out_f) != 0
 
 
 def linear_add_layer_norm(x, weight, bias, res, gamma, beta, eps=1e-5, bscale=None, mask_input_grad=False):

@@ -287,6 +287,13 @@ int feta_add_layernorm_bwd_fold(const float* partial, int64_t T, int D, float* d
  * of 64):  z = res + bscale[row] * (X . W^T + b)  (bscale, b may be NULL);  y = LayerNorm(z) * gamma + beta.
  * z, mean, rstd are what feta_add_layernorm_bwd takes; the Linear's own backward is feta_linear_dx / feta_linear_wgrad. */
 int feta_linear_layernorm_supported(int in, int out);
+/* The same fused launch on the fp32 CUDA-core kernel (csrc/linear_simt.cu: a CTA owns whole 64-wide output rows, the
+ * LayerNorm is two half-warp shuffle folds in the projection's epilogue; exact fp32): out = 64, in a multiple of 64
+ * up to 256.  feta_linear_layernorm_fwd = impl FETA_LINEAR_AUTO (this kernel when eligible, else tcgen05). */
+int feta_linear_layernorm_simt_supported(int in, int out);
+int feta_linear_layernorm_fwd_ex(const float* X, const float* W, const float* bias, const float* res,
+                                 const float* bscale, const float* gamma, const float* beta, float* y, float* z,
+                                 float* mean, float* rstd, int64_t T, int in, int out, float eps, int impl, void* stream);
 int feta_linear_layernorm_fwd(const float* X, const float* W, const float* bias, const float* res, const float* bscale,
                               const float* gamma, const float* beta, float* y, float* z, float* mean, float* rstd,
                               int64_t T, int in, int out, float eps, void* stream);
