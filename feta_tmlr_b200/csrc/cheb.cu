@@ -369,20 +369,26 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
     out[threadIdx.x] = t;
   }
 }
-// any C (un-tuned shapes)
-__global__ void colsum_partial_any_kernel(const float* __restrict__ x, int64_t R, int C, float* __restrict__ partial) {
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.0f;
-    for (int64_t r = blockIdx.x; r < R; r += gridDim.x) s += x[r * C + c];
-    partial[(int64_t)blockIdx.x * C + c] = s;
-  }
+// any other C (e.g. the 1024-wide coefficient GCN of the dh = 16 configs): thread per column (coalesced across
+// columns), grid (column tiles, row slices); the final pass folds the slices of a column in order
+__global__ void __launch_bounds__(256) colsum_partial_any_kernel(const float* __restrict__ x, int64_t R, int C,
+                                                                 float* __restrict__ partial) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s0 = 0.0f, s1 = 0.0f;
+  int64_t r = blockIdx.y;
+  for (; r + gridDim.y < R; r += 2 * (int64_t)gridDim.y) s0 += x[r * C + c], s1 += x[(r + gridDim.y) * C + c];
+  if (r < R) s0 += x[r * C + c];
+  partial[(int64_t)blockIdx.y * C + c] = s0 + s1;
 }
-__global__ void colsum_final_any_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
-    float s = 0.0f;
-    for (int b = 0; b < nblk; ++b) s += partial[(int64_t)b * C + c];
-    out[c] = s;
-  }
+__global__ void __launch_bounds__(256) colsum_final_any_kernel(const float* __restrict__ partial, int nsl, int C,
+                                                               float* __restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.0f;
+#pragma unroll 8
+  for (int b = 0; b < nsl; ++b) s += partial[(int64_t)b * C + c];
+  out[c] = s;
 }
 
 constexpr int kColsumBlocks = 256;
@@ -398,10 +404,11 @@ int colsum_launch(const float* x, int64_t R, int C, float* out, float* partial, 
     FETA_LAUNCH_CHECK();
     return FETA_OK;
   }
-  const int nblk = (int)(R < kColsumBlocks ? (R > 0 ? R : 1) : kColsumBlocks);
-  colsum_partial_any_kernel<<<nblk, 64, 0, st>>>(x, R, C, partial);
+  const int tiles = (int)ceil_div(C, 256);
+  int nsl = (int)(R < 32 ? (R > 0 ? R : 1) : 32);                 // nsl * C <= kColsumBlocks * C floats of `partial`
+  colsum_partial_any_kernel<<<dim3(tiles, nsl), 256, 0, st>>>(x, R, C, partial);
   FETA_LAUNCH_CHECK();
-  colsum_final_any_kernel<<<1, 64, 0, st>>>(partial, R > 0 ? nblk : 0, C, out);
+  colsum_final_any_kernel<<<tiles, 256, 0, st>>>(partial, R > 0 ? nsl : 0, C, out);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }

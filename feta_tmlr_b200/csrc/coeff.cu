@@ -15,7 +15,7 @@ namespace feta {
 constexpr int kCoeffThreads = 256;
 
 // one CTA per (graph b, head h)
-__global__ void __launch_bounds__(kCoeffThreads) coeff_scalar_kernel(const float* __restrict__ attn,
+__global__ void __launch_bounds__(1024) coeff_scalar_kernel(const float* __restrict__ attn,
                                                                     const uint8_t* __restrict__ mask,
                                                                     const int32_t* __restrict__ node_ptr,
                                                                     float* __restrict__ s, int H, int nmax,
@@ -171,11 +171,14 @@ extern "C" int feta_coeff_scalar(const float* attn, const uint8_t* mask, const i
   FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && N >= 0, "coeff_scalar: bad sizes");
   if (B == 0 || nmax == 0 || N == 0) return FETA_OK;
   FETA_REQUIRE(attn && mask && node_ptr && s, "coeff_scalar: NULL pointer argument");
-  const size_t smem = ((size_t)nmax * 3 + kCoeffThreads) * sizeof(float);
+  // graphs wider than 64 nodes: 1024 threads, i.e. several row slices per column (PATTERN: 5 x 192) -- the kernel is
+  // a chain of dependent loads per thread, nmax / slices long
+  const int threads = nmax > 64 ? 1024 : kCoeffThreads;
+  const size_t smem = ((size_t)nmax * 3 + threads) * sizeof(float);
   FETA_REQUIRE(smem <= 200 * 1024, "coeff_scalar: nmax=%d too large", nmax);
   if (smem > 48 * 1024)
     FETA_CUDA(cudaFuncSetAttribute(coeff_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  coeff_scalar_kernel<<<(unsigned)(B * H), kCoeffThreads, smem, st>>>(attn, mask, node_ptr, s, H, nmax, N);
+  coeff_scalar_kernel<<<(unsigned)(B * H), threads, smem, st>>>(attn, mask, node_ptr, s, H, nmax, N);
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
