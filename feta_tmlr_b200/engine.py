@@ -123,9 +123,13 @@ class GraphedTrainStep(object):
                 self._body(0)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # optimizer steps taken on the example batch before the graphs exist (a training script that must reproduce
+        # a single-process run counts them; tests/ddp_two_rank_check.py does)
+        self.uncaptured_steps = int(warmup)
         if self.comm_slices:
             self._setup_comm_slices()
             side.wait_stream(torch.cuda.current_stream(dev))
+            self.uncaptured_steps += 1
             with torch.cuda.stream(side):                            # one sliced step outside capture (NCCL warm-up)
                 self._body(0)
             torch.cuda.current_stream(dev).wait_stream(side)

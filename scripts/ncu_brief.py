@@ -1,7 +1,8 @@
 """Print the handful of ncu metrics that decide what bounds a kernel.  usage: ncu_brief.py report.ncu-rep"""
 import subprocess, sys, csv, io
 rep = sys.argv[1]
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units = rows[0], rows[1]
 want = ["Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",

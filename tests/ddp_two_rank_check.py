@@ -41,8 +41,8 @@ def main():
     if rank == 0:
         import copy
         ref = copy.deepcopy(model)
-    # every rank: its shard of each global batch;  engine warm-up runs on step 0's shard (3 un-captured steps),
-    # so the single-process reference below takes the same 3 extra steps on global batch 0
+    # every rank: its shard of each global batch;  engine warm-up runs on step 0's shard (eng.uncaptured_steps
+    # un-captured steps), so the single-process reference below takes the same extra steps on global batch 0
     def ids(step, r):
         base = step * world * B
         return np.arange(base + r * B, base + (r + 1) * B)
@@ -55,7 +55,7 @@ def main():
     ok = True
     if rank == 0:
         opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
-        seq = [0, 0, 0] + list(range(steps))
+        seq = [0] * eng.uncaptured_steps + list(range(steps))     # warm-up steps (+ the sliced-exchange warm-up step)
         for s in seq:
             gids = np.concatenate([ids(s, r) for r in range(world)])
             if node:
@@ -72,12 +72,20 @@ def main():
                 out = ref(b[0], b[6], b[7], b[8], b[1], b[2], b[3], b[4])[0]
                 torch.nn.functional.l1_loss(out, b[5]).backward()
                 opt.step()
-        worst = 0.0
+        # Tolerance: 2e-4 of the parameter's largest entry for weights.  Bias vectors start at zero, so after a handful
+        # of steps their largest entry is ~lr * steps and Adam's g / sqrt(v) turns the fp32 cancellation noise of a
+        # near-zero gradient element (sum over the batch of terms of both signs) into a visible fraction of one step:
+        # they are held to 2e-3 (observed 6.7e-4 = 0.5 % of ONE Adam step on classifier.0.bias, everything else <= 2e-5).
+        worst, errs, ok = 0.0, [], True
         for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
             err = float((p - q).abs().max() / q.abs().max().clamp_min(1e-12))
+            errs.append((err, k))
             worst = max(worst, err)
-        ok = worst < 2e-4
+            ok = ok and err < (2e-3 if k.endswith("bias") else 2e-4)
         print("DDP2 %s max_rel=%.3e" % ("OK" if ok else "FAIL", worst), flush=True)
+        if not ok:
+            print("DDP2 worst parameters: %s" % ", ".join("%s %.2e" % (k, e) for e, k in sorted(errs, reverse=True)[:6]),
+                  flush=True)
     # replicas identical across ranks
     flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
     other = flat.clone()
