@@ -56,6 +56,9 @@ SIGNATURES = {
     "feta_layer_tail_fwd": (c_int, [_P] * 22 + [c_int64, c_int, c_int, c_float, c_float, _P]),
     "feta_linear_layernorm_supported": (c_int, [c_int, c_int]),
     "feta_linear_layernorm_simt_supported": (c_int, [c_int, c_int]),
+    "feta_lnbwd_linear_dx_blocks": (c_int, [c_int64]),
+    "feta_lnbwd_linear_dx": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "feta_ln_fold": (c_int, [_P, c_int, c_int, _P, _P, _P]),
     "feta_linear_layernorm_fwd_ex": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float,
                                              c_int, _P]),
     "feta_linear_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _P]),

@@ -364,3 +364,12 @@ extern "C" int feta_add_layernorm_bwd_fold(const float* partial, int64_t T, int 
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
+
+// the same fold over an explicit number of per-CTA partials (feta_lnbwd_linear_dx writes one per 32-row tile)
+extern "C" int feta_ln_fold(const float* partial, int nblk, int D, float* dgamma, float* dbeta, void* stream_) {
+  FETA_REQUIRE(partial && dgamma && dbeta && nblk >= 0 && D >= 1 && D <= kLnMaxPerLane * 32, "ln_fold: bad argument");
+  ln_fold_kernel<<<(unsigned)ceil_div(2 * D, 8), 256, 0, (cudaStream_t)stream_>>>(partial, nblk, D, dgamma, dbeta);
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+

@@ -255,6 +255,136 @@ __global__ void __launch_bounds__(kThreads) linear_simt_ln_kernel(
   }
 }
 
+// Backward of the fused launch above, first half: LayerNorm backward over the 64-wide rows as the PROLOGUE of the
+// projection's input gradient --
+//   dz = rstd (g - mean(g) - xhat mean(g xhat)),  g = dy gamma,  xhat = (z - mean) rstd         (gradient of the residual)
+//   dlin = bscale dz                                                            (gradient of the projection's output)
+//   dX = (dlin . W) [mask > 0]
+// A CTA's A tile holds whole rows, so dz is computed in registers (a row = 16 lanes x 4 columns, two shuffle folds),
+// written to shared memory as the GEMM operand and -- by the first column tile only -- to global memory together with
+// the per-CTA partial sums of dgamma / dbeta (folded by ln_fold_kernel on the side stream).  Replaces the
+// add_layernorm_bwd launch in front of the dX launch of out_proj and linear2.
+constexpr int kLnBM = 32;
+__global__ void __launch_bounds__(kThreads) lnbwd_dx_kernel(
+    const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ bscale,
+    const float* __restrict__ W, const float* __restrict__ mask_src, float* __restrict__ dz, float* __restrict__ dlin,
+    float* __restrict__ dX, float* __restrict__ partial, int64_t T, int NOUT) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int KR = kBN, lda = KR + 4, RT = kLnBM / 8;
+  float* As = smem;                              // [kLnBM][lda]  dlin tile
+  float* Ws = As + kLnBM * lda;                  // [KR][kBN + 4]
+  float* red = Ws + KR * (kBN + 4);              // [2][8][64] column partials of dgamma / dbeta
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)blockIdx.x * kLnBM;
+  const int n0 = blockIdx.y * kBN;
+  const bool first = blockIdx.y == 0;
+  pdl_trigger();
+  {
+    constexpr int NQ = kBN / 4;
+    for (int i = tid; i < KR * NQ; i += kThreads) {
+      const int k = i / NQ, q = i - k * NQ;
+      cp_async16(Ws + k * (kBN + 4) + 4 * q, W + (int64_t)k * NOUT + n0 + 4 * q);
+    }
+  }
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + tx);
+  pdl_wait();
+  float dg[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < RT; ++i) {
+    const int r = ty + 8 * i;
+    const int64_t row = row0 + r;
+    const bool live = row < T;
+    float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f), z4 = d4;
+    float mu = 0.0f, rs = 0.0f, bs = 1.0f;
+    if (live) {
+      d4 = __ldg(reinterpret_cast<const float4*>(dy + row * KR) + tx);
+      z4 = __ldg(reinterpret_cast<const float4*>(z + row * KR) + tx);
+      mu = __ldg(mean + row), rs = __ldg(rstd + row);
+      if (bscale) bs = __ldg(bscale + row);
+    }
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float xh[4] = {(z4.x - mu) * rs, (z4.y - mu) * rs, (z4.z - mu) * rs, (z4.w - mu) * rs};
+    const float g[4] = {d4.x * gm.x, d4.y * gm.y, d4.z * gm.z, d4.w * gm.w};
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s1 += g[j];
+      s2 = fmaf(g[j], xh[j], s2);
+      dg[j] = fmaf(d[j], xh[j], dg[j]);
+      db[j] += d[j];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 *= (1.0f / KR), s2 *= (1.0f / KR);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = rs * (g[j] - s1 - xh[j] * s2);
+    const float4 dl = make_float4(v[0] * bs, v[1] * bs, v[2] * bs, v[3] * bs);
+    *reinterpret_cast<float4*>(As + r * lda + 4 * tx) = dl;
+    if (first && live) {
+      reinterpret_cast<float4*>(dz + row * KR)[tx] = make_float4(v[0], v[1], v[2], v[3]);
+      if (dlin) reinterpret_cast<float4*>(dlin + row * KR)[tx] = dl;
+    }
+  }
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[ty * 64 + 4 * tx + j] = dg[j];
+      red[512 + ty * 64 + 4 * tx + j] = db[j];
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (first) {                                   // tid < 64: dgamma column tid; 64..127: dbeta column tid - 64
+    const int which = tid >> 6, c = tid & 63;
+    float a = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[which * 512 + w * 64 + c];
+    partial[((size_t)blockIdx.x * 2 + which) * 64 + c] = a;
+  }
+
+  float2 p[RT][2];
+#pragma unroll
+  for (int i = 0; i < RT; ++i) p[i][0] = p[i][1] = make_float2(0.f, 0.f);
+  const float* a0 = As + ty * lda;
+  const float* w0 = Ws + 4 * tx;
+#pragma unroll 4
+  for (int kk = 0; kk < KR; kk += 4) {
+    float4 a[RT], b[4];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + (8 * i) * lda + kk);
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) b[s4] = *reinterpret_cast<const float4*>(w0 + (kk + s4) * (kBN + 4));
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+      const float as[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        const float2 aa = make_float2(as[s2], as[s2]);
+        p[i][0] = __ffma2_rn(aa, make_float2(b[s2].x, b[s2].y), p[i][0]);
+        p[i][1] = __ffma2_rn(aa, make_float2(b[s2].z, b[s2].w), p[i][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RT; ++i) {
+    const int64_t row = row0 + ty + 8 * i;
+    if (row >= T) continue;
+    const int col = n0 + 4 * tx;
+    float4 o = make_float4(p[i][0].x, p[i][0].y, p[i][1].x, p[i][1].y);
+    if (mask_src) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mask_src + row * NOUT + col));
+      o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f;
+      o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
+    }
+    *reinterpret_cast<float4*>(dX + row * NOUT + col) = o;
+  }
+}
+
 static bool eligible(int64_t T, int KR, int NOUT, const void* a, const void* w, const void* y, const void* p1,
                      const void* p2) {
   const uintptr_t ptrs = (uintptr_t)a | (uintptr_t)w | (uintptr_t)y | (uintptr_t)p1 | (uintptr_t)p2;
@@ -336,6 +466,34 @@ int linear_simt_dx_try(const float* dY, const float* W, const float* dres, const
 }
 
 }  // namespace feta
+
+extern "C" int feta_lnbwd_linear_dx_blocks(int64_t T) { return (int)feta::ceil_div(T > 0 ? T : 1, feta::lsimt::kLnBM); }
+
+extern "C" int feta_lnbwd_linear_dx(const float* dy, const float* z, const float* mean, const float* rstd,
+                                    const float* gamma, const float* bscale, const float* W, const float* mask_src,
+                                    float* dz, float* dlin, float* dX, float* partial, int64_t T, int in, int out,
+                                    void* stream_) {
+  using namespace feta;
+  FETA_REQUIRE(T >= 0 && out == lsimt::kBN && in >= 64 && in % 64 == 0 && in <= 1024,
+               "lnbwd_linear_dx: unsupported in=%d out=%d (out must be 64, in a multiple of 64)", in, out);
+  if (T == 0) return FETA_OK;
+  FETA_REQUIRE(dy && z && mean && rstd && gamma && W && dz && dX && partial && ((bscale == nullptr) == (dlin == nullptr)),
+               "lnbwd_linear_dx: NULL pointer argument (dlin goes with bscale)");
+  const uintptr_t ptrs = (uintptr_t)dy | (uintptr_t)z | (uintptr_t)gamma | (uintptr_t)W | (uintptr_t)mask_src |
+                         (uintptr_t)dz | (uintptr_t)dlin | (uintptr_t)dX;
+  FETA_REQUIRE((ptrs % 16) == 0, "lnbwd_linear_dx: pointers must be 16-byte aligned");
+  const size_t smem = ((size_t)lsimt::kLnBM * (lsimt::kBN + 4) + (size_t)lsimt::kBN * (lsimt::kBN + 4) + 1024) * 4;
+  static std::atomic<int> granted{0};
+  if ((int)smem > granted.load(std::memory_order_relaxed)) {
+    FETA_CUDA(cudaFuncSetAttribute(lsimt::lnbwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    granted.store((int)smem, std::memory_order_relaxed);
+  }
+  dim3 grid((unsigned)ceil_div(T, lsimt::kLnBM), (unsigned)(in / lsimt::kBN));
+  FETA_CUDA(launch_chain(lsimt::lnbwd_dx_kernel, grid, dim3(lsimt::kThreads), smem, (cudaStream_t)stream_, dy, z, mean,
+                         rstd, gamma, bscale, W, mask_src, dz, dlin, dX, partial, T, in));
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
 
 extern "C" int feta_linear_layernorm_simt_supported(int in, int out) {
   return out == 64 && in >= 64 && in % 64 == 0 && in <= 256;

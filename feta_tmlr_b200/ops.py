@@ -872,6 +872,9 @@ LINEAR_SIMT = _os.environ.get("FETA_LINEAR_SIMT", "1") == "1"
 # out_proj -> norm1 and linear2 -> norm2 as ONE launch each (projection with the degree scale, residual add and
 # LayerNorm in its epilogue, csrc/linear_simt.cu); FETA_LINEAR_LN_FUSED=0: projection launch + add_layernorm launch
 LINEAR_LN_FUSED = _os.environ.get("FETA_LINEAR_LN_FUSED", "1") == "1"
+# ... and their backward: LayerNorm backward as the prologue of the projection's dX launch (FETA_LINEAR_LN_BWD_FUSED=0:
+# add_layernorm_bwd launch + dX launch)
+LINEAR_LN_BWD_FUSED = _os.environ.get("FETA_LINEAR_LN_BWD_FUSED", "1") == "1"
 _IMPL_SIMT, _IMPL_TC5, _IMPL_MMA = 1, 2, 3
 
 
@@ -1127,6 +1130,8 @@ class LinearAddLayerNormFn(torch.autograd.Function):
         ctx.save_for_backward(x, w, z, mean, rstd, gamma, bscale)
         ctx.has_bias = bias is not None
         ctx.mask_in = bool(mask_input_grad)
+        ctx.fused_bwd = bool(LINEAR_LN_BWD_FUSED and linear_layernorm_impl(in_f, out_f) == _IMPL_SIMT
+                             and out_f == 64 and in_f % 64 == 0)
         return y
 
     @staticmethod
@@ -1134,9 +1139,40 @@ class LinearAddLayerNormFn(torch.autograd.Function):
         lib = _lib.load()
         x, w, z, mean, rstd, gamma, bscale = ctx.saved_tensors
         out_f, in_f = w.shape
+        dx = dw = db = None
+        if ctx.fused_bwd and ctx.needs_input_grad[0]:
+            # LayerNorm backward as the prologue of the projection's dX: one launch (csrc/linear_simt.cu)
+            dy = _f32c(dy)
+            T = z.numel() // out_f
+            dz = torch.empty_like(z)
+            dlin = torch.empty_like(z) if bscale is not None else None
+            dx = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+            nblk = lib.feta_lnbwd_linear_dx_blocks(T)
+            partial = torch.empty(nblk * 2 * out_f, dtype=torch.float32, device=z.device)
+            dg = torch.empty(out_f, dtype=torch.float32, device=z.device)
+            dbeta = torch.empty(out_f, dtype=torch.float32, device=z.device)
+            x2 = _f32c(x.reshape(-1, in_f)) if ctx.mask_in else None
+            check(lib.feta_lnbwd_linear_dx(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(bscale), _ptr(w),
+                                           _ptr(x2), _ptr(dz), _ptr(dlin), _ptr(dx), _ptr(partial), T, in_f, out_f,
+                                           _stream()), "feta_lnbwd_linear_dx")
+            if WGRAD_SIDE_STREAM:                               # the dgamma / dbeta fold leaves the critical path
+                main = torch.cuda.current_stream(z.device)
+                side = _side_stream(z.device)
+                side.wait_stream(main)
+                check(lib.feta_ln_fold(_ptr(partial), nblk, out_f, _ptr(dg), _ptr(dbeta), side.cuda_stream),
+                      "feta_ln_fold")
+                for t in (partial, dg, dbeta):
+                    t.record_stream(side)
+                _queue_side_join(z.device)
+            else:
+                check(lib.feta_ln_fold(_ptr(partial), nblk, out_f, _ptr(dg), _ptr(dbeta), _stream()), "feta_ln_fold")
+            if dlin is None:
+                dlin = dz
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                dw, db = _linear_wgrad(dlin, x, out_f, in_f, ctx.has_bias)
+            return dx, dw, db, dz.view(z.shape), None, dg, dbeta, None, None
         dz, dbs, dg, dbeta = _layernorm_backward(dy, z, mean, rstd, gamma, bscale, bscale is not None)
         dlin = dbs if dbs is not None else dz                   # gradient of the Linear's output
-        dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dl2 = _f32c(dlin.reshape(-1, out_f))
             x2 = _f32c(x.reshape(-1, in_f)) if ctx.mask_in else None

@@ -291,6 +291,17 @@ int feta_linear_layernorm_supported(int in, int out);
  * LayerNorm is two half-warp shuffle folds in the projection's epilogue; exact fp32): out = 64, in a multiple of 64
  * up to 256.  feta_linear_layernorm_fwd = impl FETA_LINEAR_AUTO (this kernel when eligible, else tcgen05). */
 int feta_linear_layernorm_simt_supported(int in, int out);
+/* Backward of that launch, input-gradient half, in ONE launch (csrc/linear_simt.cu): LayerNorm backward over the
+ * 64-wide rows (dz = gradient of `res`; dlin = bscale * dz = gradient of the projection's output, written only when
+ * bscale != NULL -- otherwise dlin == dz) as the prologue of dX = (dlin . W) * [mask_src > 0]; `partial` receives
+ * feta_lnbwd_linear_dx_blocks(T) * 2 * 64 floats (per-CTA sums of dgamma / dbeta) for feta_ln_fold.  out must be 64, in a
+ * multiple of 64.  W is the projection's weight [out = 64, in]. */
+int feta_lnbwd_linear_dx_blocks(int64_t T);
+int feta_lnbwd_linear_dx(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                         const float* bscale, const float* W, const float* mask_src, float* dz, float* dlin, float* dX,
+                         float* partial, int64_t T, int in, int out, void* stream);
+/* dgamma[c] = sum_k partial[k, 0, c], dbeta[c] = sum_k partial[k, 1, c] over nblk per-CTA partials (deterministic). */
+int feta_ln_fold(const float* partial, int nblk, int D, float* dgamma, float* dbeta, void* stream);
 int feta_linear_layernorm_fwd_ex(const float* X, const float* W, const float* bias, const float* res,
                                  const float* bscale, const float* gamma, const float* beta, float* y, float* z,
                                  float* mean, float* rstd, int64_t T, int in, int out, float eps, int impl, void* stream);
