@@ -635,12 +635,14 @@ def main():
                  "timed as CUDA-graph replays of the kernel ALONE on one of the step's batches (random q/k/v), not "
                  "inside the step graph")
         from feta_tmlr_b200 import ops as _ops
-        rows_on = bool(_ops.attn_rows_enabled(nm, dh)) and L > 1
+        rows_on = bool(_ops.attn_rows_enabled(nm, dh))
         # the dominant kernel = the largest (time per launch x launches per step) among this repo's kernels
         lin_us = kern_us.pop("linear_fwd_layer")
         lin_dx_us = kern_us.pop("linear_dx_layer")
         lin_bytes = kern_us.pop("linear_bytes_layer")
-        n_rows_layers = (L - 1) if rows_on else 0
+        # static (CUDA-graph) step: every layer runs the matrix-free kernels, the coefficient scalar of the last layer
+        # is recomputed from q / k (ops.LazyAttention); eager reference-API forward(): the last layer writes its matrix
+        n_rows_layers = (L if res["use_graph"] else L - 1) if rows_on else 0
         rows_bytes = attn_bytes - res["attn_matrix_bytes"]
         cands = {
             "linear_fwd": (lin_us / 4.0, 4 * L, lin_bytes / 4.0, "lsimt::linear_simt_kernel<0> (the layer's four "

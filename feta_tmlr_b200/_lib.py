@@ -44,6 +44,8 @@ SIGNATURES = {
     "feta_colsum_partial_floats": (c_int64, [c_int]),
     "feta_colsum": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
     "feta_attn_rows_supported": (c_int, [c_int, c_int]),
+    "feta_attn_rows_coeff": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float,
+                                     c_int64, _P]),
     "feta_attn_rows_fwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, c_int64, c_int64, _P,
                                    c_int, c_int, c_int, c_int, c_float, _P]),
     "feta_attn_rows_bwd": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P,

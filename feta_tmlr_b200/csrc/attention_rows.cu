@@ -402,6 +402,104 @@ __global__ void __launch_bounds__(kMaxN) attn_rows_bwd_kernel(
   }
 }
 
+// ------------------------------------------------------------------ coefficient scalar (N1) ------------
+// The filter-coefficient path (transformer/models.py:240-283) runs a GCN over an all-ones feature matrix on the
+// complete graph weighted by the (detached) attention matrix; with x == 1 its output at node j collapses to
+// s_j * colsum(W) + b (csrc/coeff.cu) with
+//   loop_j = a_jj != 0 ? a_jj : 1,  deg_j = sum_{i != j} a_ij + loop_j,  dis = deg^-1/2,
+//   s_j = dis_j (sum_{i != j} dis_i a_ij + dis_j loop_j).
+// Both sums run over a COLUMN of the attention matrix, i.e. over query rows for a fixed key: exactly the key-owning
+// thread mapping of the backward pass above.  This kernel recomputes a_ij = 2^(s_ij - m_i) pe_ij inv_i from q, k,
+// the position-encoding kernel and the forward pass's row statistics -- twice, once per sum -- so the layer that feeds
+// the coefficients needs no attention matrix either (no gradient flows here: the reference detaches it, :282).
+template <int DH, bool PE>
+__global__ void __launch_bounds__(kMaxN) attn_rows_coeff_kernel(
+    const float* __restrict__ q, const float* __restrict__ k, int64_t sn, int64_t sb, const float* __restrict__ pe,
+    const uint8_t* __restrict__ mask, const float4* __restrict__ stats, const int32_t* __restrict__ node_ptr,
+    float* __restrict__ s_out, int H, int nmax, float scale, int64_t N) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int C4 = DH / 4;
+  const int bh = blockIdx.x, b = bh / H, h = bh - b * H;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  float* Qs = smem;                                  // [nmax][DH]  q * scale * log2(e)
+  float2* sts = reinterpret_cast<float2*>(Qs + (size_t)nmax * DH);    // [nmax] (m, inv); inv = 0: not a real row
+  float* dis = reinterpret_cast<float*>(sts + nmax);                  // [nmax]
+  int* wcnt = reinterpret_cast<int*>(dis + nmax);                     // [8] real positions per warp
+  const int64_t hb = (int64_t)b * sb + h * DH;
+  pdl_trigger();
+  pdl_wait();
+  const bool valid = t < nmax && mask[(size_t)b * nmax + t] == 0;
+  float kr[DH];
+#pragma unroll
+  for (int c = 0; c < DH; ++c) kr[c] = 0.0f;
+  if (valid) {
+    float qr[DH];
+    ldg_row<DH>(kr, k + hb + (int64_t)t * sn);
+    ldg_row<DH>(qr, q + hb + (int64_t)t * sn);
+    const float f = scale * kLog2e;
+#pragma unroll
+    for (int c = 0; c < C4; ++c)
+      reinterpret_cast<float4*>(Qs + t * DH)[c] =
+          make_float4(qr[4 * c] * f, qr[4 * c + 1] * f, qr[4 * c + 2] * f, qr[4 * c + 3] * f);
+    const float4 s4 = __ldg(stats + ((size_t)b * H + h) * nmax + t);
+    sts[t] = make_float2(s4.x, s4.w != 0.0f ? s4.y : 0.0f);
+  } else if (t < nmax) {
+    sts[t] = make_float2(0.0f, 0.0f);
+  }
+  // packed index of a real position = number of real positions before it
+  const unsigned bal = __ballot_sync(0xffffffffu, valid);
+  if (lane == 0) wcnt[warp] = __popc(bal);
+  int generic;
+  const int n = analyse_mask(valid, t, nmax, &generic);          // barriers: Qs / sts / wcnt published
+  int rank = __popc(bal & ((1u << lane) - 1u));
+  for (int w = 0; w < warp; ++w) rank += wcnt[w];
+  const bool live = 32 * warp < n;                               // (no early return: one more barrier follows)
+  const float* peb = PE ? pe + (size_t)b * nmax * nmax : nullptr;
+
+  float deg = 0.0f, pjj = 0.0f;
+  if (live) {
+    for (int ic = 0; ic < n; ic += kCW) {
+      float per[kCW];
+      if (PE) load_tile_b(per, peb, nmax, n, ic, t);
+#pragma unroll
+      for (int ii = 0; ii < kCW; ++ii) {
+        if (ic + ii >= n) break;
+        const float2 st = sts[ic + ii];
+        if (st.y == 0.0f) continue;                   // padded / masked query row: its matrix row is zero
+        float qi[DH];
+        ld_row<DH>(qi, Qs + (ic + ii) * DH);
+        float p = exp2f(dot<DH>(qi, kr) - st.x) * st.y;
+        if (PE) p *= per[ii];
+        if (ic + ii == t) pjj = p;
+        else deg += p;
+      }
+    }
+  }
+  const float lw = pjj != 0.0f ? pjj : 1.0f;          // add_remaining_self_loops keeps an existing loop weight
+  deg += lw;
+  const float d = (valid && deg > 0.0f) ? 1.0f / sqrtf(deg) : 0.0f;
+  if (t < nmax) dis[t] = d;
+  __syncthreads();
+  if (!live || !valid) return;
+  float acc = 0.0f;
+  for (int ic = 0; ic < n; ic += kCW) {
+    float per[kCW];
+    if (PE) load_tile_b(per, peb, nmax, n, ic, t);
+#pragma unroll
+    for (int ii = 0; ii < kCW; ++ii) {
+      if (ic + ii >= n) break;
+      const float2 st = sts[ic + ii];
+      if (st.y == 0.0f || ic + ii == t) continue;
+      float qi[DH];
+      ld_row<DH>(qi, Qs + (ic + ii) * DH);
+      float p = exp2f(dot<DH>(qi, kr) - st.x) * st.y;
+      if (PE) p *= per[ii];
+      acc = fmaf(dis[ic + ii], p, acc);
+    }
+  }
+  s_out[(int64_t)h * N + __ldg(node_ptr + b) + rank] = d * (acc + d * lw);
+}
+
 static size_t fwd_smem(int dh, int nmax, bool has_pe) {
   const int nr4 = (nmax + 3) & ~3, warps = (nmax + 31) / 32;
   return (2 * (size_t)nmax * dh + nr4 + (has_pe ? (size_t)warps * kTile : 0)) * sizeof(float);
@@ -447,6 +545,21 @@ static int launch_bwd(const float* q, const float* k, const float* v, int64_t sn
   FETA_CUDA(launch_chain(attn_rows_bwd_kernel<DH, PE>, dim3((unsigned)(B * H)), dim3(32 * ((nmax + 31) / 32)), smem, st,
                          q, k, v, sn, sb, pe, mask, reinterpret_cast<const float4*>(stats), o_heads, d_o, osn, osb, dq,
                          dk, dv, dsn, dsb, H, nmax, scale));
+  FETA_LAUNCH_CHECK();
+  return FETA_OK;
+}
+
+template <int DH, bool PE>
+static int launch_coeff(const float* q, const float* k, int64_t sn, int64_t sb, const float* pe, const uint8_t* mask,
+                        const float* stats, const int32_t* node_ptr, float* s_out, int B, int H, int nmax, float scale,
+                        int64_t N, cudaStream_t st) {
+  const size_t smem = ((size_t)nmax * DH + 3 * (size_t)nmax + 8) * sizeof(float);
+  static std::atomic<int> granted{48 * 1024};
+  const int rc = grant_smem(attn_rows_coeff_kernel<DH, PE>, granted, smem);
+  if (rc != FETA_OK) return rc;
+  FETA_CUDA(launch_chain(attn_rows_coeff_kernel<DH, PE>, dim3((unsigned)(B * H)), dim3(32 * ((nmax + 31) / 32)), smem, st,
+                         q, k, sn, sb, pe, mask, reinterpret_cast<const float4*>(stats), node_ptr, s_out, H, nmax,
+                         scale, N));
   FETA_LAUNCH_CHECK();
   return FETA_OK;
 }
@@ -513,3 +626,20 @@ extern "C" int feta_attn_rows_bwd(const float* q, const float* k, const float* v
                       dsn, dsb, B, H, nmax, scale, st);
   return FETA_EUNSUPPORTED;
 }
+
+extern "C" int feta_attn_rows_coeff(const float* q, const float* k, int64_t sn, int64_t sb, const float* pe,
+                                    const uint8_t* mask, const float* stats, const int32_t* node_ptr, float* s_out,
+                                    int B, int H, int nmax, int dh, float scale, int64_t N, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  FETA_REQUIRE(B >= 0 && H >= 1 && nmax >= 0 && dh >= 1 && N >= 0, "attn_rows_coeff: bad sizes");
+  if (B == 0 || nmax == 0 || N == 0) return FETA_OK;
+  FETA_REQUIRE(q && k && mask && stats && node_ptr && s_out, "attn_rows_coeff: NULL pointer argument");
+  if (!feta_attn_rows_supported(nmax, dh) || !arows::aligned16({q, k, stats}, {sn, sb})) {
+    set_last_error("attn_rows_coeff: needs nmax <= %d, dh in {4,8,16,32}, 16-byte aligned head slices (nmax=%d dh=%d)",
+                   arows::kMaxN, nmax, dh);
+    return FETA_EUNSUPPORTED;
+  }
+  FETA_AROWS_DISPATCH(arows::launch_coeff, q, k, sn, sb, pe, mask, stats, node_ptr, s_out, B, H, nmax, scale, N, st);
+  return FETA_EUNSUPPORTED;
+}
+

@@ -251,10 +251,13 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         attn = None
         rowscale = None if degree is None else degree.transpose(0, 1).contiguous()
         for layer_num, mod in enumerate(self.layers):
+            # layers that feed the coefficients hand out a LazyAttention (ops.py): the coefficient scalar is
+            # recomputed from q / k, so no layer of the static step materialises its attention matrix; the matrix
+            # this method returns is therefore a LazyAttention too (``.materialize()`` for whoever wants to look)
             last = layer_num + 1 == num_layers
             output, attn, out_each_head = mod(output, pe=pe, degree=degree, src_key_padding_mask=masks,
                                               need_heads=True, rowscale=rowscale, bn_rows=bn_rows,
-                                              need_attn=last or not self.last_layer_filter)
+                                              need_attn='coeff' if (last or not self.last_layer_filter) else False)
             if self.last_layer_filter and layer_num + 1 != num_layers:
                 continue
             if ctx is None:

@@ -470,10 +470,11 @@ class DiffAttentionRowsFn(torch.autograd.Function):
                                          _ptr(stats), B, H, N, dh, float(scale), _stream()), "feta_attn_rows_fwd")
         ctx.save_for_backward(qkv, pec, mask_u8, stats, o_heads)
         ctx.cfg = (H, float(scale), bool(share_qk))
-        return o_heads
+        ctx.mark_non_differentiable(stats)
+        return o_heads, stats
 
     @staticmethod
-    def backward(ctx, d_o_heads):
+    def backward(ctx, d_o_heads, _unused=None):
         lib = _lib.load()
         qkv, pec, mask_u8, stats, o_heads = ctx.saved_tensors
         H, scale, share_qk = ctx.cfg
@@ -501,14 +502,52 @@ def dropout_multiplier(shape, p, device, generator=None):
     return keep.to(torch.float32) * (1.0 / (1.0 - p))
 
 
+class LazyAttention(object):
+    """What a layer hands out in place of its attention matrix when the caller only wants the filter-coefficient
+    scalar from it (``need_attn='coeff'``): q/k (detached), the position-encoding kernel, the mask and the row
+    statistics of the matrix-free forward pass.  ``coeff_scalar`` recomputes the matrix entries on the fly
+    (feta_attn_rows_coeff); ``materialize`` writes the [B, H, Nmax, Nmax] matrix for a caller that wants to look at it."""
+
+    def __init__(self, qkv, pe, mask_u8, stats, num_heads, scale, share_qk):
+        self.qkv, self.pe, self.mask_u8, self.stats = qkv.detach(), pe, mask_u8, stats
+        self.num_heads, self.scale, self.share_qk = int(num_heads), float(scale), bool(share_qk)
+
+    def coeff_scalar(self, node_ptr, num_nodes, zero_fill=False):
+        lib = _lib.load()
+        qkv = self.qkv
+        N, B, d3 = qkv.shape
+        d = d3 // 3
+        H = self.num_heads
+        alloc = torch.zeros if zero_fill else torch.empty
+        s = alloc(H * int(num_nodes), dtype=torch.float32, device=qkv.device)
+        base = qkv.data_ptr()
+        kp = base + (0 if self.share_qk else d * 4)
+        check(lib.feta_attn_rows_coeff(base, kp, B * d3, d3, _ptr(self.pe), _ptr(self.mask_u8), _ptr(self.stats),
+                                       _ptr(node_ptr), _ptr(s), B, H, N, d // H, self.scale, int(num_nodes), _stream()),
+              "feta_attn_rows_coeff")
+        return s
+
+    def materialize(self):
+        with torch.no_grad():
+            attn, _, _ = DiffAttentionFn.apply(self.qkv, self.pe, self.mask_u8, self.num_heads, self.scale,
+                                               self.share_qk, None)
+        return attn
+
+
 def diff_attention(qkv, pe, key_padding_mask, num_heads, scale, share_qk=False, drop=None, need_attn=True):
     """``drop`` (optional, [B, H, Nmax, Nmax]): attention-weight dropout multipliers; the returned attention is the
     dropped one (``F.dropout(P)``), the saved one the un-dropped P.  ``need_attn=False``: the caller does not read
-    the attention matrix -- it is returned as None when the matrix-free kernels cover the shape."""
+    the attention matrix -- it is returned as None when the matrix-free kernels cover the shape.
+    ``need_attn='coeff'``: the caller only needs ``coeff_scalar`` of this layer's matrix -- a ``LazyAttention`` comes
+    back in its place (falls back to the matrix when the matrix-free kernels do not cover the shape / dropout)."""
     N, B, d3 = qkv.shape
     mask_u8 = _mask_u8(key_padding_mask, B, N, qkv.device)
-    if not need_attn and drop is None and qkv.is_cuda and attn_rows_enabled(N, d3 // 3 // num_heads):
-        return None, DiffAttentionRowsFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk)
+    if need_attn is not True and drop is None and qkv.is_cuda and attn_rows_enabled(N, d3 // 3 // num_heads):
+        o_sf, stats = DiffAttentionRowsFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk)
+        if need_attn == 'coeff':           # the caller wants the coefficient scalar of this layer, not the matrix
+            pec = None if pe is None else _f32c(pe)
+            return LazyAttention(_f32c(qkv), pec, mask_u8, stats, num_heads, scale, share_qk), o_sf
+        return None, o_sf
     attn, o_sf, _ = DiffAttentionFn.apply(qkv, pe, mask_u8, num_heads, scale, share_qk, drop)
     return attn, o_sf            # o_sf [Nmax, B, H, dh]; out_each_head = o_sf.permute(1, 0, 2, 3)
 
@@ -520,6 +559,8 @@ def coeff_scalar(attn, key_padding_mask, node_ptr, num_nodes, zero_fill=False):
     """s [H*N]: the per-node scalar the all-ones GCN of models.py:280-282 reduces to.
     Not differentiable (the reference detaches the attention, models.py:282).
     ``zero_fill``: start from zeros (padded layouts, where masked positions own a slot)."""
+    if isinstance(attn, LazyAttention):
+        return attn.coeff_scalar(node_ptr, num_nodes, zero_fill=zero_fill)
     _need_cuda(attn, node_ptr)
     lib = _lib.load()
     attn = _f32c(attn.detach())

@@ -237,6 +237,14 @@ int feta_attn_rows_supported(int nmax, int dh);
 int feta_attn_rows_fwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
                        const float* pe, const uint8_t* mask, float* o_heads, int64_t o_stride_n, int64_t o_stride_b,
                        float* stats, int B, int H, int nmax, int dh, float scale, void* stream);
+/* N1: the per-node scalar of the collapsed filter-coefficient path (see feta_coeff_scalar) WITHOUT the attention matrix:
+ * a_ij is recomputed from q, k, `pe` and the `stats` feta_attn_rows_fwd left behind (one thread per key row, two sweeps
+ * over the query rows: degrees, then the normalised sums).  s_out [H * N] is indexed h*N + node_ptr[b] + rank, rank =
+ * packed index of the real position, like feta_coeff_scalar.  Not differentiable (the reference detaches the matrix,
+ * transformer/models.py:282). */
+int feta_attn_rows_coeff(const float* q, const float* k, int64_t stride_n, int64_t stride_b, const float* pe,
+                         const uint8_t* mask, const float* stats, const int32_t* node_ptr, float* s_out, int B, int H,
+                         int nmax, int dh, float scale, int64_t N, void* stream);
 int feta_attn_rows_bwd(const float* q, const float* k, const float* v, int64_t stride_n, int64_t stride_b,
                        const float* pe, const uint8_t* mask, const float* stats, const float* o_heads,
                        const float* d_o_heads, int64_t o_stride_n, int64_t o_stride_b, float* dq, float* dk, float* dv,

@@ -298,3 +298,47 @@ def test_attention_rows_switch_off(cuda, monkeypatch):
     go, ga = m(src.to(cuda), pe=pe.to(cuda), degree=degree.to(cuda), src_key_padding_mask=mask.to(cuda),
                need_attn=False)
     assert ga is not None                                   # falls back to the matrix-writing kernels
+
+
+@pytest.mark.parametrize("B,N,H,dh,with_pe", [(4, 37, 8, 8, True), (3, 150, 4, 16, False), (5, 20, 2, 32, True),
+                                               (2, 256, 1, 16, True)])
+@pytest.mark.parametrize("layout", ["packed", "padded_slots", "interior_mask"])
+def test_lazy_attention_coeff_scalar_matches_matrix_path(cuda, B, N, H, dh, with_pe, layout):
+    """N1: the coefficient scalar recomputed from q / k (feta_attn_rows_coeff) == feta_coeff_scalar over the
+    materialised attention matrix -- packed output (reference layout), padded slots (static layout), a mask that is
+    not a suffix, exact zeros on the diagonal of the kernel (loop weight 1, PyG add_remaining_self_loops)."""
+    from feta_tmlr_b200 import ops
+    g = torch.Generator().manual_seed(B * N + H)
+    d = H * dh
+    qkv = torch.randn(N, B, 3 * d, generator=g).to(cuda)
+    lens = torch.randint(1, N + 1, (B,), generator=g)
+    lens[0] = N
+    mask = torch.arange(N)[None, :] >= lens[:, None]
+    if layout == "interior_mask":
+        mask[0, 1] = True
+        mask[B - 1, 0] = True
+    pe = None
+    if with_pe:
+        a = torch.rand(B, N, N, generator=g)
+        pe = (a + a.transpose(1, 2)) * 0.5 * (torch.rand(B, N, N, generator=g) > 0.2)
+        idx = torch.arange(0, N, 3)
+        pe[:, idx, idx] = 0.0                                      # zero self weights: loop weight falls back to 1
+        pe = (pe * ((~mask)[:, :, None] & (~mask)[:, None, :])).to(cuda)
+    mask = mask.to(cuda)
+    scale = dh ** -0.5
+    lazy, o1 = ops.diff_attention(qkv, pe, mask, H, scale, need_attn='coeff')
+    assert isinstance(lazy, ops.LazyAttention)
+    attn, o2 = ops.diff_attention(qkv, pe, mask, H, scale, need_attn=True)
+    assert rel_err(o1, o2) < 1e-5
+    assert rel_err(lazy.materialize(), attn) == 0.0
+    real = (~mask).sum(dim=1)
+    if layout == "padded_slots":
+        node_ptr = (torch.arange(B, device=cuda) * N).to(torch.int32)
+        total, zero_fill = B * N, True
+    else:
+        node_ptr = (torch.cumsum(real, 0) - real).to(torch.int32)
+        total, zero_fill = int(real.sum()), False
+    s_lazy = ops.coeff_scalar(lazy, mask, node_ptr, total, zero_fill=zero_fill)
+    s_mat = ops.coeff_scalar(attn, mask, node_ptr, total, zero_fill=zero_fill)
+    assert s_lazy.shape == s_mat.shape
+    assert rel_err(s_lazy, s_mat) < 1e-5
