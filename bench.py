@@ -696,7 +696,8 @@ def main():
                 "warmup": args.warmup, "ms_per_step": round(res["ms"] / args.steps, 4), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "graphs_per_step": world * B,
-                           "parallelism": "dp%d (graphs sharded, one flat-bucket NCCL all-reduce of %d B/step)"
+                           "parallelism": "dp%d (graphs sharded; flat gradient bucket of %d B/step all-reduced over NCCL in slices "
+                                          "overlapped with the backward pass)"
                                           % (world, res["bucket_bytes"]) if world > 1 else "single GPU",
                            "l2": "inputs rotate through a pool of %d distinct device-resident batches "
                                  "(%.0f MB > 126 MB L2)" % (res["n_pool"], res["n_pool"] * res["per_batch"] / 1e6),

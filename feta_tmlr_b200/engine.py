@@ -99,6 +99,8 @@ class GraphedTrainStep(object):
         # post-accumulate hooks) the slice is copied into the flat buffer and all-reduced on a communication stream
         # (forked from the main stream and from the weight-gradient side stream) while the rest of the backward
         # pass runs; only the first slice's all-reduce (embedding + first layers) is exposed before Adam.
+        import os
+        comm_slices = int(os.environ.get("FETA_COMM_SLICES", comm_slices))
         self.comm_slices = int(comm_slices) if (self.world > 1 and self.flat_adam) else 0
         self.comm_stream = torch.cuda.Stream(device=dev) if self.comm_slices else None
         self._slices, self._hooks, self._works = [], [], []
