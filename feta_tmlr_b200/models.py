@@ -20,6 +20,11 @@ from . import ops
 from .ChebNetDynamic import ARMAConvDynamic, ChebConvDynamic
 from .layers import DiffTransformerEncoderLayer, Linear
 
+import os as _os
+# forward_static builds the batch's padded-domain context + Laplacian plan on the side stream, concurrently with the
+# encoder layers (FETA_STATIC_CONTEXT_SIDE_STREAM=0: on the main stream, where the first filtering layer needs them)
+STATIC_CONTEXT_SIDE_STREAM = _os.environ.get("FETA_STATIC_CONTEXT_SIDE_STREAM", "1") == "1"
+
 
 # Every Linear of the heads / encoder glue is ``layers.Linear``: an ``nn.Linear`` (same parameters and state_dict keys)
 # whose weight / bias gradients are reduced over the token axis by csrc/dense.cu -- the library's SIMT sgemm needs
@@ -250,6 +255,17 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
         ctx = None
         attn = None
         rowscale = None if degree is None else degree.transpose(0, 1).contiguous()
+        # The padded-domain context and the Laplacian plan depend on the batch's mask and edge list only: they are
+        # built on the side stream while the encoder layers run (a parallel branch of the captured graph, ~15 launches
+        # off the critical chain -- at the PATTERN shape the plan of 449k edges alone is ~100 us) and joined where the
+        # first filtering layer needs them.  Every later use is ordered behind that join.
+        side = None
+        if src.is_cuda and STATIC_CONTEXT_SIDE_STREAM and num_layers > 0:
+            main = torch.cuda.current_stream(src.device)
+            side = ops._side_stream(src.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ctx = self.static_context(edge_index, masks, nmax)
         for layer_num, mod in enumerate(self.layers):
             # layers that feed the coefficients hand out a LazyAttention (ops.py): the coefficient scalar is
             # recomputed from q / k, so no layer of the static step materialises its attention matrix; the matrix
@@ -260,6 +276,9 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
                                               need_attn='coeff' if (last or not self.last_layer_filter) else False)
             if self.last_layer_filter and layer_num + 1 != num_layers:
                 continue
+            if side is not None:
+                torch.cuda.current_stream(src.device).wait_stream(side)
+                side = None
             if ctx is None:
                 ctx = self.static_context(edge_index, masks, nmax)
             s = ops.coeff_scalar(attn, masks, ctx.node_ptr, B * nmax, zero_fill=True)
@@ -276,6 +295,8 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
             else:
                 allout_filtered = out_filtered
                 output = allout_filtered
+        if side is not None:                         # (no layer filtered: the branch still has to rejoin)
+            torch.cuda.current_stream(src.device).wait_stream(side)
         if self.use_skip_conn:
             if allout_filtered is not None:
                 output = self.linear_cat(torch.cat((output, allout_filtered), dim=-1))
