@@ -24,6 +24,10 @@ import os as _os
 # forward_static builds the batch's padded-domain context + Laplacian plan on the side stream, concurrently with the
 # encoder layers (FETA_STATIC_CONTEXT_SIDE_STREAM=0: on the main stream, where the first filtering layer needs them)
 STATIC_CONTEXT_SIDE_STREAM = _os.environ.get("FETA_STATIC_CONTEXT_SIDE_STREAM", "1") == "1"
+# ... and issues the filter-coefficient branch on its own stream so that its backward (parameter gradients only) runs
+# beside the layers' backward chain (FETA_COEFF_BRANCH_STREAM=0: on the main stream)
+COEFF_BRANCH_STREAM = _os.environ.get("FETA_COEFF_BRANCH_STREAM", "1") == "1"
+import contextlib
 
 
 # Every Linear of the heads / encoder glue is ``layers.Linear``: an ``nn.Linear`` (same parameters and state_dict keys)
@@ -281,9 +285,20 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
                 side = None
             if ctx is None:
                 ctx = self.static_context(edge_index, masks, nmax)
-            s = ops.coeff_scalar(attn, masks, ctx.node_ptr, B * nmax, zero_fill=True)
-            pooled = ops.coeff_pool(s, ctx.seg_lo, ops.colsum(self.gcn.weight), self.gcn.bias, seg_hi=ctx.seg_hi)
-            coeff_all_heads = self.linear(pooled).reshape((H, B, -1))
+            # The coefficient branch (attention -> scalar -> tanh/mean pool -> Linear) ends in parameters only -- the
+            # reference detaches the attention (:282) -- so its BACKWARD is off the layers' gradient chain.  Autograd
+            # runs a node's backward on the stream its forward ran on: issuing the branch on its own stream makes its
+            # backward a parallel branch of the captured graph (the forward gains nothing: the filter needs `coeff`).
+            branch = ops._side_stream(src.device, 1) if (src.is_cuda and COEFF_BRANCH_STREAM) else None
+            if branch is not None:
+                main = torch.cuda.current_stream(src.device)
+                branch.wait_stream(main)
+            with (torch.cuda.stream(branch) if branch is not None else contextlib.nullcontext()):
+                s = ops.coeff_scalar(attn, masks, ctx.node_ptr, B * nmax, zero_fill=True)
+                pooled = ops.coeff_pool(s, ctx.seg_lo, ops.colsum(self.gcn.weight), self.gcn.bias, seg_hi=ctx.seg_hi)
+                coeff_all_heads = self.linear(pooled).reshape((H, B, -1))
+            if branch is not None:
+                main.wait_stream(branch)
             coeff = coeff_all_heads.reshape((H * B, coeff_all_heads.shape[2]))
             x = out_each_head.permute(2, 0, 1, 3).reshape(H * B * nmax, -1)          # padded-domain stacking
             filtered = self.filter(coeff, None, ctx.edge_index, None, ctx.batch_all_heads,

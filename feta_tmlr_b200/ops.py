@@ -937,11 +937,13 @@ _SIDE = {}
 _JOIN_TASK = {}          # device -> id of the autograd graph task that already queued its join
 
 
-def _side_stream(device):
-    st = _SIDE.get(device)
+def _side_stream(device, index=0):
+    """index 0: the weight-gradient side stream; 1: the coefficient-branch stream of forward_static."""
+    key = device if index == 0 else (device, index)
+    st = _SIDE.get(key)
     if st is None:
         st = torch.cuda.Stream(device=device)
-        _SIDE[device] = st
+        _SIDE[key] = st
     return st
 
 
