@@ -98,12 +98,15 @@ class DiffTransformerEncoderLayer(nn.Module):
         self.scaling = None
 
     def forward(self, src, pe=None, degree=None, src_mask=None, src_key_padding_mask=None,
-                need_heads=False, rowscale=None, bn_rows=None, need_attn=True):
+                need_heads=False, rowscale=None, bn_rows=None, need_attn=True, after_attention=None):
         """``rowscale`` (extension): the seq-first ``degree.t().contiguous()`` precomputed once per forward by
         the encoder instead of once per layer.  ``bn_rows`` (extension, BatchNorm variant): 0/1 weight per
         flattened row ``[Nmax * B]``; rows with 0 stay out of the batch statistics (static-shape batches).
         ``need_attn=False`` (extension): the caller does not read the attention matrix of this layer; it comes back as
-        None and is never materialised (matrix-free attention kernels)."""
+        None and is never materialised (matrix-free attention kernels).
+        ``after_attention`` (extension): ``callback(attn, out_each_head)`` invoked as soon as the attention core has
+        been issued, before the layer's token-wise tail -- the encoder starts the filter branch there (on another
+        stream), which depends on the attention outputs only."""
         if src_mask is not None:
             raise NotImplementedError("src_mask (attn_mask) is never passed by the reference "
                                       "(models.py:166) and is not implemented")
@@ -118,6 +121,8 @@ class DiffTransformerEncoderLayer(nn.Module):
         else:
             src2, attn, heads = self.self_attn(src, pe=pe, key_padding_mask=src_key_padding_mask,
                                                need_attn=need_attn)
+        if after_attention is not None:
+            after_attention(attn, heads)
         if rowscale is not None:
             pass
         elif degree is not None:

@@ -270,41 +270,55 @@ class DiffTransformerEncoderGenGCN(nn.TransformerEncoder):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 ctx = self.static_context(edge_index, masks, nmax)
+        dev = src.device
+        use_branch = bool(src.is_cuda and COEFF_BRANCH_STREAM)
         for layer_num, mod in enumerate(self.layers):
             # layers that feed the coefficients hand out a LazyAttention (ops.py): the coefficient scalar is
             # recomputed from q / k, so no layer of the static step materialises its attention matrix; the matrix
             # this method returns is therefore a LazyAttention too (``.materialize()`` for whoever wants to look)
             last = layer_num + 1 == num_layers
+            filters = last or not self.last_layer_filter
+            got = {}
+
+            def filter_branch(attn_l, out_each_head):
+                # The filter branch -- attention -> coefficient scalar -> tanh/mean pool -> Linear -> Chebyshev filter of
+                # the stacked heads -- needs the attention outputs only, not the layer's token-wise tail (out_proj,
+                # FFN, norms), and the two meet again at `linear_cat` / the skip sum.  It is issued on its own stream
+                # right after the attention core: a parallel branch of the captured graph in the forward pass, and --
+                # autograd runs a node's backward on the stream its forward ran on -- in the backward pass too.
+                nonlocal side, ctx
+                main = torch.cuda.current_stream(dev) if src.is_cuda else None
+                if side is not None:                     # the context / plan branch joins here
+                    main.wait_stream(side)
+                    side = None
+                if ctx is None:
+                    ctx = self.static_context(edge_index, masks, nmax)
+                branch = ops._side_stream(dev, 1) if use_branch else None
+                if branch is not None:
+                    branch.wait_stream(main)
+                with (torch.cuda.stream(branch) if branch is not None else contextlib.nullcontext()):
+                    s = ops.coeff_scalar(attn_l, masks, ctx.node_ptr, B * nmax, zero_fill=True)
+                    pooled = ops.coeff_pool(s, ctx.seg_lo, ops.colsum(self.gcn.weight), self.gcn.bias,
+                                            seg_hi=ctx.seg_hi)
+                    coeff_all_heads = self.linear(pooled).reshape((H, B, -1))
+                    coeff = coeff_all_heads.reshape((H * B, coeff_all_heads.shape[2]))
+                    x = out_each_head.permute(2, 0, 1, 3).reshape(H * B * nmax, -1)      # padded-domain stacking
+                    filtered = self.filter(coeff, None, ctx.edge_index, None, ctx.batch_all_heads,
+                                           self.spectral_gnns, x=x, plan=ctx.plan)
+                    got['out'] = filtered.reshape(H, B, nmax, -1).permute(2, 1, 0, 3).reshape(nmax, B, d) * ctx.real
+                got['coeff'] = coeff_all_heads
+                got['branch'] = branch
+
             output, attn, out_each_head = mod(output, pe=pe, degree=degree, src_key_padding_mask=masks,
                                               need_heads=True, rowscale=rowscale, bn_rows=bn_rows,
-                                              need_attn='coeff' if (last or not self.last_layer_filter) else False)
-            if self.last_layer_filter and layer_num + 1 != num_layers:
+                                              need_attn='coeff' if filters else False,
+                                              after_attention=filter_branch if filters else None)
+            if not filters:
                 continue
-            if side is not None:
-                torch.cuda.current_stream(src.device).wait_stream(side)
-                side = None
-            if ctx is None:
-                ctx = self.static_context(edge_index, masks, nmax)
-            # The coefficient branch (attention -> scalar -> tanh/mean pool -> Linear) ends in parameters only -- the
-            # reference detaches the attention (:282) -- so its BACKWARD is off the layers' gradient chain.  Autograd
-            # runs a node's backward on the stream its forward ran on: issuing the branch on its own stream makes its
-            # backward a parallel branch of the captured graph (the forward gains nothing: the filter needs `coeff`).
-            branch = ops._side_stream(src.device, 1) if (src.is_cuda and COEFF_BRANCH_STREAM) else None
-            if branch is not None:
-                main = torch.cuda.current_stream(src.device)
-                branch.wait_stream(main)
-            with (torch.cuda.stream(branch) if branch is not None else contextlib.nullcontext()):
-                s = ops.coeff_scalar(attn, masks, ctx.node_ptr, B * nmax, zero_fill=True)
-                pooled = ops.coeff_pool(s, ctx.seg_lo, ops.colsum(self.gcn.weight), self.gcn.bias, seg_hi=ctx.seg_hi)
-                coeff_all_heads = self.linear(pooled).reshape((H, B, -1))
-            if branch is not None:
-                main.wait_stream(branch)
-            coeff = coeff_all_heads.reshape((H * B, coeff_all_heads.shape[2]))
-            x = out_each_head.permute(2, 0, 1, 3).reshape(H * B * nmax, -1)          # padded-domain stacking
-            filtered = self.filter(coeff, None, ctx.edge_index, None, ctx.batch_all_heads,
-                                   self.spectral_gnns, x=x, plan=ctx.plan)
-            coefficients.append(coeff_all_heads)
-            out_filtered = filtered.reshape(H, B, nmax, -1).permute(2, 1, 0, 3).reshape(nmax, B, d) * ctx.real
+            if got['branch'] is not None:
+                torch.cuda.current_stream(dev).wait_stream(got['branch'])
+            coefficients.append(got['coeff'])
+            out_filtered = got['out']
             if self.use_skip_conn:
                 allout_filtered = out_filtered if allout_filtered is None else allout_filtered + out_filtered
             else:
