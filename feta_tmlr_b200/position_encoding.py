@@ -12,9 +12,15 @@ a ``[G, n, n]`` batch (<= 256 MB) and decomposed with one batched symmetric eige
                                  (I - beta L)^p = U diag((1 - beta w)^p) U^T     (PStepRWEncoding)
                                  columns 1..dim of U (ascending w)               (LapEncoding)
 
-``'sym'`` and ``None`` normalisations are symmetric and take the batched path; ``'rw'`` (not
-symmetric) falls back to the per-graph dense formulas.  Graphs are dicts / objects with
-``edge_index`` and ``num_nodes`` (``x.shape[0]``), as produced by ``synthetic`` or PyG.
+``'sym'`` and ``None`` normalisations are symmetric and take the batched path directly.  ``'rw'`` is not
+symmetric but, for an undirected edge list, similar to ``'sym'``:  ``L_rw = S^-1 L_sym S`` with
+``S = diag(sqrt(deg))`` (1 for isolated nodes, which are decoupled 1x1 blocks), so
+
+    f(L_rw) = S^-1 U f(w) U^T S        and the eigenvectors of L_rw are  S^-1 u / |S^-1 u|
+
+ride on the same batched ``eigh``.  A directed edge list (non-symmetric adjacency) takes the general per-graph
+dense formula instead.  Graphs are dicts / objects with ``edge_index`` and ``num_nodes`` (``x.shape[0]``), as
+produced by ``synthetic`` or PyG.
 """
 import os
 import pickle
@@ -34,9 +40,9 @@ def _edge_index(g):
     return np.asarray(ei.cpu() if torch.is_tensor(ei) else ei, dtype=np.int64)
 
 
-def dense_laplacians(graphs, normalization, device='cpu', dtype=torch.float64):
+def dense_laplacians(graphs, normalization, device='cpu', dtype=torch.float64, return_deg=False):
     """Padded batch ``[G, nmax, nmax]`` of PyG ``get_laplacian`` matrices (self loops removed,
-    multi-edges summed, degree over the source index) + the node counts."""
+    multi-edges summed, degree over the source index) + the node counts (+ the degrees)."""
     ns = np.array([_num_nodes(g) for g in graphs], dtype=np.int64)
     nmax = int(ns.max())
     A = np.zeros((len(graphs), nmax, nmax), dtype=np.float64)
@@ -59,6 +65,8 @@ def dense_laplacians(graphs, normalization, device='cpu', dtype=torch.float64):
         L = eye * real2 - di.unsqueeze(2) * A
     else:
         raise ValueError("normalization must be None, 'sym' or 'rw'")
+    if return_deg:
+        return L, ns, deg
     return L, ns
 
 
@@ -83,19 +91,34 @@ def _is_symmetric(L):
     return (L == L.transpose(1, 2)).flatten(1).all(dim=1)
 
 
+def _rw_scale(deg):
+    """S of ``L_rw = S^-1 L_sym S``: sqrt(deg), 1 where the degree is 0 (isolated and padded nodes)."""
+    return torch.where(deg > 0, deg.clamp(min=1e-300).sqrt(), torch.ones_like(deg))
+
+
 def _spectral_map(graphs, normalization, fn, device, fallback):
-    """U f(w) U^T per graph, one batched eigh per size-sorted chunk (symmetric normalisations).  A graph whose
-    Laplacian is NOT symmetric (directed edge list) takes ``fallback(L)`` -- the general dense formula the
-    reference's scipy ``expm`` / matrix power computes -- instead of a silently wrong ``eigh``."""
+    """U f(w) U^T per graph, one batched eigh per size-sorted chunk (``'rw'``: the similarity transform of the
+    module docstring around the ``'sym'`` decomposition).  A graph whose adjacency is NOT symmetric (directed edge
+    list) takes ``fallback(L)`` -- the general dense formula the reference's scipy ``expm`` / matrix power
+    computes -- instead of a silently wrong ``eigh``."""
     out = [None] * len(graphs)
+    rw = normalization == 'rw'
     for idx in _size_sorted_chunks(graphs):
-        L, ns = dense_laplacians([graphs[i] for i in idx], normalization, device=device)
+        sub = [graphs[i] for i in idx]
+        L, ns, deg = dense_laplacians(sub, 'sym' if rw else normalization, device=device, return_deg=True)
         sym = _is_symmetric(L).cpu().numpy()
         # padded rows/cols are zero: they add zero eigenvalues whose eigenvectors live in the padding
         w, U = torch.linalg.eigh(L)
         M = (U * fn(w).unsqueeze(1)) @ U.transpose(1, 2)
+        if rw:
+            s = _rw_scale(deg)
+            M = M * s.unsqueeze(1) / s.unsqueeze(2)
         for j, (i, n) in enumerate(zip(idx, ns)):
-            out[i] = (M[j, :n, :n] if sym[j] else fallback(L[j, :n, :n])).to(torch.float32).cpu()
+            if sym[j]:
+                out[i] = M[j, :n, :n].to(torch.float32).cpu()
+            else:
+                Lj = dense_laplacians([sub[j]], normalization, device=device)[0][0] if rw else L[j, :n, :n]
+                out[i] = fallback(Lj).to(torch.float32).cpu()
     return out
 
 
@@ -153,12 +176,6 @@ class DiffusionEncoding(PositionEncoding):
         self.beta, self.normalization = beta, normalization
 
     def compute_all(self, graphs):
-        if self.normalization == 'rw':
-            out = []
-            for g in graphs:
-                L, ns = dense_laplacians([g], 'rw')
-                out.append(torch.matrix_exp(-self.beta * L[0]).to(torch.float32))
-            return out
         return _spectral_map(graphs, self.normalization, lambda w: torch.exp(-self.beta * w), self.device,
                              fallback=lambda L: torch.matrix_exp(-self.beta * L))
 
@@ -174,13 +191,6 @@ class PStepRWEncoding(PositionEncoding):
         self.p, self.beta, self.normalization = p, beta, normalization
 
     def compute_all(self, graphs):
-        if self.normalization == 'rw':
-            out = []
-            for g in graphs:
-                L, ns = dense_laplacians([g], 'rw')
-                M = torch.eye(L.shape[1], dtype=L.dtype) - self.beta * L[0]
-                out.append(torch.linalg.matrix_power(M, self.p).to(torch.float32))
-            return out
         return _spectral_map(graphs, self.normalization, lambda w: (1.0 - self.beta * w) ** self.p, self.device,
                              fallback=lambda L: torch.linalg.matrix_power(
                                  torch.eye(L.shape[0], dtype=L.dtype, device=L.device) - self.beta * L, self.p))
@@ -216,7 +226,7 @@ class FullEncoding(PositionEncoding):
 
 class LapEncoding(PositionEncoding):
     """:118-168 -- first ``dim`` non-trivial Laplacian eigenvectors (ascending eigenvalue), zero padded.
-    The reference uses ``np.linalg.eig`` on a symmetric matrix; eigenvector signs (and bases of
+    The reference uses ``np.linalg.eig`` (unit-norm eigenvectors); eigenvector signs (and bases of
     repeated eigenvalues) are not unique -- the drivers randomise the sign anyway
     (run_transformer_gengcn_SBM_cv.py:159-164)."""
 
@@ -227,11 +237,11 @@ class LapEncoding(PositionEncoding):
         self.pos_enc_dim, self.normalization = dim, normalization
 
     def compute_all(self, graphs):
-        if self.normalization == 'rw':
-            raise NotImplementedError("LapEncoding with 'rw' normalisation (non-symmetric) is not implemented")
+        rw = self.normalization == 'rw'      # eigenvectors of L_rw = S^-1 (eigenvectors of L_sym), renormalised
         out = [None] * len(graphs)
         for idx in _size_sorted_chunks(graphs):
-            L, ns = dense_laplacians([graphs[i] for i in idx], self.normalization, device=self.device)
+            L, ns, deg = dense_laplacians([graphs[i] for i in idx], 'sym' if rw else self.normalization,
+                                          device=self.device, return_deg=True)
             if not bool(_is_symmetric(L).all()):
                 raise NotImplementedError("LapEncoding: a graph's Laplacian is not symmetric (directed edge list); "
                                           "the batched symmetric eigendecomposition does not apply")
@@ -240,6 +250,9 @@ class LapEncoding(PositionEncoding):
             pad = (torch.arange(nmax, device=L.device).unsqueeze(0)
                    >= torch.from_numpy(ns).to(L.device).unsqueeze(1))
             w, U = torch.linalg.eigh(L + torch.diag_embed(pad.to(L.dtype) * 1e6))
+            if rw:
+                U = U / _rw_scale(deg).unsqueeze(2)
+                U = U / torch.linalg.vector_norm(U, dim=1, keepdim=True)      # np.linalg.eig returns unit vectors
             for j, (i, n) in enumerate(zip(idx, ns)):
                 pe = U[j, :n, 1:self.pos_enc_dim + 1]
                 pe = pe[:, :max(0, min(self.pos_enc_dim, n - 1))]

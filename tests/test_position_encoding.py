@@ -35,15 +35,16 @@ def test_pstep_matches_matrix_power(norm, p):
         assert torch.allclose(m, ref.float(), atol=1e-5)
 
 
-def test_lap_encoding_spans_reference_eigenvectors():
+@pytest.mark.parametrize("norm", ['sym', None, 'rw'])
+def test_lap_encoding_spans_reference_eigenvectors(norm):
     gs = _graphs(8, shape='PATTERN')
     dim = 4
-    out = pe.LapEncoding(dim, normalization='sym', device='cpu').compute_all(gs)
+    out = pe.LapEncoding(dim, normalization=norm, device='cpu').compute_all(gs)
     for g, m in zip(gs, out):
         n = g['x'].shape[0]
         assert m.shape == (n, dim)
-        L = od._dense_laplacian(torch.from_numpy(g['edge_index']), n, 'sym').astype(np.float64)
-        w = np.sort(np.linalg.eigvalsh(L))
+        L = od._dense_laplacian(torch.from_numpy(g['edge_index']), n, norm).astype(np.float64)
+        w = np.sort(np.linalg.eigvals(L).real)           # 'rw' is not symmetric: the reference's general eig
         # each column is a unit eigenvector of L for the matching (ascending, non-trivial) eigenvalue
         for c in range(dim):
             v = m[:, c].double().numpy()
@@ -68,6 +69,25 @@ def test_cache_format_and_zero_diag(tmp_path):
     full = pe.FullEncoding(None).compute_all(gs)
     assert full[0].shape == (gs[0]['x'].shape[0],) * 2
     assert pe.AdjEncoding(None).compute_all(gs)[0].shape[0] == 1
+
+
+def test_rw_with_isolated_nodes_and_directed_edges():
+    """'rw' rides on the 'sym' decomposition through L_rw = S^-1 L_sym S; isolated nodes (degree 0) are decoupled
+    1x1 blocks, and a directed edge list must take the general per-graph formula."""
+    g = dict(_graphs(1)[0])
+    n = g['x'].shape[0]
+    ei = g['edge_index']
+    g['edge_index'] = ei[:, (ei[0] != 0) & (ei[1] != 0)]                 # node 0 isolated
+    d = dict(g)
+    d['edge_index'] = np.concatenate([g['edge_index'], np.array([[1], [n - 1]])], axis=1)   # + a one-way edge
+    for gg in (g, d):
+        e = torch.from_numpy(gg['edge_index'])
+        m = pe.DiffusionEncoding(None, beta=1.0, normalization='rw', device='cpu').compute_all([gg])[0]
+        assert torch.allclose(m, od.diffusion_pe(e, n, 1.0, 'rw').float(), atol=2e-6)
+        m = pe.PStepRWEncoding(None, p=3, beta=0.5, normalization='rw', device='cpu').compute_all([gg])[0]
+        assert torch.allclose(m, od.pstep_pe(e, n, 3, 0.5, 'rw').float(), atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        pe.LapEncoding(4, normalization='rw', device='cpu').compute_all([d])
 
 
 def test_synthetic_diffusion_pe_is_the_same_kernel():
