@@ -12,24 +12,48 @@
 namespace feta {
 
 constexpr int kWgTile = 64, kWgTT = 32, kWgThreads = 256;
+constexpr int kWgPitch = kWgTile + 8;   // smem row pitch: fragment loads (4 token rows x 8 columns per warp) hit 32 banks
 
+// 3xTF32 (hi.hi + hi.lo + lo.hi, fp32-grade): the tensor core reads the top 19 bits of an operand, so "hi" is the
+// value itself and the remainder is exact in fp32 (same scheme as csrc/cheb_lane.cu)
+__device__ __forceinline__ void wg_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
+}
+__device__ __forceinline__ void wg_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// One CTA = one 64 x 64 tile of dW over one slice of `t_per_cta` tokens.  The contraction runs over tokens on the
+// tensor cores: M = output channel (A[m][k] = dY[t][o], read transposed out of the token-major staging tile),
+// N = input channel (B[k][n] = X[t][i]), K = 8 tokens per step; warp w owns output rows 16 (w & 3) .. + 15 and input
+// columns 32 (w >> 2) .. + 31.  The round-2 launch list had the CUDA-core version of this kernel (16 FFMA per two
+// LDS.128, 3840 warp instructions per slice) as the largest single share of the step's GPU time, competing for issue
+// slots with the layer chain it runs beside; this one issues ~1200.  db rides along as one more accumulator tile
+// against an all-ones B fragment.
 __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float* __restrict__ dY,
                                                                   const float* __restrict__ X,
                                                                   float* __restrict__ partial,
                                                                   float* __restrict__ partial_db, int T, int out,
                                                                   int in, int t_per_cta, int in_tiles) {
-  __shared__ __align__(16) float sA[kWgTT][kWgTile];
-  __shared__ __align__(16) float sB[kWgTT][kWgTile];
+  __shared__ __align__(16) float sA[kWgTT][kWgPitch];
+  __shared__ __align__(16) float sB[kWgTT][kWgPitch];
   const int tile = blockIdx.x, s = blockIdx.y;
   const int o0 = (tile / in_tiles) * kWgTile, i0 = (tile % in_tiles) * kWgTile;
   const int t0 = s * t_per_cta, t1 = min(T, t0 + t_per_cta);
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const int mo = (warp & 3) * 16, nb = (warp >> 2) * 32;
+  const bool want_db = partial_db != nullptr && i0 == 0 && nb == 0;   // warp-uniform
   float acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
   float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t one = __float_as_uint(1.0f);
   // register-staged prefetch: the next 32-token tile is in flight while the current one is consumed
   float4 ra[2], rb[2];
   auto fetch = [&](int tt0) {
@@ -56,29 +80,45 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_partial_kernel(const float* 
     }
     __syncthreads();
     if (tt0 + kWgTT < t1) fetch(tt0 + kWgTT);
-#pragma unroll 8
-    for (int tt = 0; tt < kWgTT; ++tt) {
-      const float4 a = *reinterpret_cast<const float4*>(&sA[tt][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&sB[tt][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        dbacc[p] += av[p];
+    for (int ks = 0; ks < kWgTT / 8; ++ks) {
+      const float* pa = &sA[8 * ks + tq][mo + g];      // A[m][k]: rows g, g + 8 <-> channels, k = tq, tq + 4 <-> tokens
+      uint32_t ah[4], al[4];
+      wg_split(pa[0], ah[0], al[0]);
+      wg_split(pa[8], ah[1], al[1]);
+      wg_split(pa[4 * kWgPitch], ah[2], al[2]);
+      wg_split(pa[4 * kWgPitch + 8], ah[3], al[3]);
+      const float* pb = &sB[8 * ks + tq][nb + g];      // B[k][n]: k = tq, tq + 4 <-> tokens, n = g <-> channel
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t bh0, bl0, bh1, bl1;
+        wg_split(pb[8 * nt], bh0, bl0);
+        wg_split(pb[4 * kWgPitch + 8 * nt], bh1, bl1);
+        wg_mma(acc[nt], ah, bh0, bh1);
+        wg_mma(acc[nt], ah, bl0, bl1);
+        wg_mma(acc[nt], al, bh0, bh1);
+      }
+      if (want_db) {
+        wg_mma(dbacc, ah, one, one);
+        wg_mma(dbacc, al, one, one);
       }
     }
     __syncthreads();
   }
+  // C fragment: (row g, cols 2 tq, 2 tq + 1), (row g + 8, same cols)
   float* pt = partial + (size_t)s * out * in;
+  const int oa = o0 + mo + g, ob = oa + 8;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int o = o0 + ty * 4 + p;
-    if (o >= out) continue;
-    if (i0 + tx * 4 < in)
-      *reinterpret_cast<float4*>(pt + (size_t)o * in + i0 + tx * 4) =
-          make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
-    if (partial_db != nullptr && i0 == 0 && tx == 0) partial_db[(size_t)s * out + o] = dbacc[p];
+  for (int nt = 0; nt < 4; ++nt) {
+    const int i = i0 + nb + 8 * nt + 2 * tq;
+    if (i < in) {
+      if (oa < out) *reinterpret_cast<float2*>(pt + (size_t)oa * in + i) = make_float2(acc[nt][0], acc[nt][1]);
+      if (ob < out) *reinterpret_cast<float2*>(pt + (size_t)ob * in + i) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+  }
+  if (want_db && tq == 0) {     // every column of the ones-product holds sum_t dY[t][o]
+    if (oa < out) partial_db[(size_t)s * out + oa] = dbacc[0];
+    if (ob < out) partial_db[(size_t)s * out + ob] = dbacc[2];
   }
 }
 
@@ -272,8 +312,11 @@ __global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ 
 
 using namespace feta;
 
-constexpr int kWgTokensPerCta = 192;
-extern "C" int feta_linear_wgrad_slices(int64_t T) { return (int)ceil_div(T > 0 ? T : 1, kWgTokensPerCta); }
+// tokens per CTA (= per slice of the token axis).  Measured in the step (round 2, tensor-core kernel): ZINC shape
+// (T = 4.7k) 128 tokens 101.9k graphs/s, 192 99.3k, 256 94.2k; PATTERN shape (T = 12k) 192 54.1k, 128 53.0k -- short
+// slices put more CTAs on a small batch, long ones keep the second pass short on a large one
+static inline int wg_tokens(int64_t T) { return T <= 8192 ? 128 : 192; }
+extern "C" int feta_linear_wgrad_slices(int64_t T) { return (int)ceil_div(T > 0 ? T : 1, wg_tokens(T)); }
 
 extern "C" int feta_linear_wgrad(const float* dY, const float* X, float* dW, float* db, float* partial,
                                  size_t partial_floats, int32_t* counters, int64_t T, int out, int in,
@@ -295,7 +338,7 @@ extern "C" int feta_linear_wgrad(const float* dY, const float* X, float* dW, flo
   float* pdb = db ? partial + (size_t)S * out * in : nullptr;
   const int out_tiles = (int)ceil_div(out, kWgTile), in_tiles = (int)ceil_div(in, kWgTile);
   dim3 grid((unsigned)(out_tiles * in_tiles), (unsigned)S);
-  wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(dY, X, partial, pdb, (int)T, out, in, kWgTokensPerCta, in_tiles);
+  wgrad_partial_kernel<<<grid, kWgThreads, 0, st>>>(dY, X, partial, pdb, (int)T, out, in, wg_tokens(T), in_tiles);
   FETA_LAUNCH_CHECK();
   const int64_t n4 = (int64_t)out * in / 4, n4b = db ? out / 4 : 0;
   slices_reduce4_kernel<<<(unsigned)ceil_div(n4 + n4b, 128), 128, 0, st>>>(

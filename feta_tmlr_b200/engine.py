@@ -182,7 +182,8 @@ class GraphedTrainStep(object):
         dev = self.device
         main, cs = torch.cuda.current_stream(dev), self.comm_stream
         cs.wait_stream(main)
-        cs.wait_stream(ops._side_stream(dev))                      # weight gradients are produced there
+        for st in ops.side_streams_in_use(dev):                    # weight gradients are produced there
+            cs.wait_stream(st)
         with torch.cuda.stream(cs):
             torch._foreach_copy_([self.bucket.views[i] for i in sl["idx"]], [self.params[i].grad for i in sl["idx"]])
             self._works.append(torch.distributed.all_reduce(self.bucket.flat[sl["lo"]:sl["hi"]],
