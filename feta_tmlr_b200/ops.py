@@ -975,7 +975,9 @@ def side_streams_in_use(device):
 
 def _queue_side_join(device):
     """Once per backward pass (keyed by the engine's graph-task id, so a pass that died with an exception cannot
-    leave a stale 'already queued' mark): main waits on every side stream the pass used when the pass completes."""
+    leave a stale 'already queued' mark): main waits on every side stream the pass used when the pass completes.
+    The join is the only place that forgets a stream or rewinds the round-robin, so a nested pass (its own task id,
+    its own join) can only join MORE than it launched, never less, and every captured step deals the same streams."""
     task = torch._C._current_graph_task_id()
     if task >= 0 and _JOIN_TASK.get(device) == task:
         return
@@ -989,15 +991,6 @@ def _queue_side_join(device):
         _WG_NEXT[device] = 0
 
     torch.autograd.Variable._execution_engine.queue_callback(_join)
-
-
-def _begin_side_pass(device):
-    """Called before the first side-stream launch of a call site: a new backward pass (new graph task) starts with no
-    join targets and the round-robin at stream 0, so the captured graph's branch structure is the same every step."""
-    task = torch._C._current_graph_task_id()
-    if task < 0 or _JOIN_TASK.get(device) != task:
-        _WG_USED[device] = []
-        _WG_NEXT[device] = 0
 
 
 def _linear_wgrad(dy, x, out_f, in_f, has_bias):
@@ -1017,7 +1010,6 @@ def _linear_wgrad(dy, x, out_f, in_f, has_bias):
     cnt = _counters(dy.device)
     if WGRAD_SIDE_STREAM:
         main = torch.cuda.current_stream(dy.device)
-        _begin_side_pass(dy.device)
         side = _wgrad_stream(dy.device)
         side.wait_stream(main)                      # dy, x (and the buffers above) are ready
         check(lib.feta_linear_wgrad(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), _ptr(partial), n_part,
@@ -1050,7 +1042,6 @@ def _layernorm_backward(dy, z, mean, rstd, gamma, bscale, want_dbs):
                                          _ptr(dz), _ptr(dbs), None, None, _ptr(partial), None, T, D, _stream()),
               "feta_add_layernorm_bwd")
         main = torch.cuda.current_stream(z.device)
-        _begin_side_pass(z.device)
         side = _wgrad_stream(z.device)
         side.wait_stream(main)
         check(lib.feta_add_layernorm_bwd_fold(_ptr(partial), T, D, _ptr(dg), _ptr(db), side.cuda_stream),
@@ -1241,7 +1232,6 @@ class LinearAddLayerNormFn(torch.autograd.Function):
                                            _stream()), "feta_lnbwd_linear_dx")
             if WGRAD_SIDE_STREAM:                               # the dgamma / dbeta fold leaves the critical path
                 main = torch.cuda.current_stream(z.device)
-                _begin_side_pass(z.device)
                 side = _wgrad_stream(z.device)
                 side.wait_stream(main)
                 check(lib.feta_ln_fold(_ptr(partial), nblk, out_f, _ptr(dg), _ptr(dbeta), side.cuda_stream),
