@@ -122,6 +122,30 @@ def test_sass_is_blackwell_native():
     # tcgen05 attention forward: tensor-core MMA (UTC*MMA), TMEM loads / stores
     sass = sass_of("attn_fwd_tc_kernelILi16E")
     assert "UTCHMMA" in sass and "LDTM" in sass and "STTM" in sass
+    # weight gradients: the token-axis contraction runs on the tensor cores (3xTF32), 48 + 8 (db) MMAs per 32 tokens
+    sass = sass_of("wgrad_partial_kernel")
+    assert sass.count("HMMA.1688.F32.TF32") == 56 and "FFMA" not in sass
+
+
+def test_weight_gradient_launches_are_dealt_over_the_side_streams(monkeypatch):
+    """ops._wgrad_stream: round-robin over WGRAD_STREAMS side streams starting at the device's side stream 0; every
+    stream that received work is a join target (ops.side_streams_in_use) until the end-of-pass join forgets it."""
+    from feta_tmlr_b200 import ops
+    made = {}
+    monkeypatch.setattr(ops, "_side_stream", lambda device, index=0: made.setdefault((device, index), object()))
+    monkeypatch.setattr(ops, "WGRAD_STREAMS", 3)
+    monkeypatch.setattr(ops, "_WG_USED", {})
+    monkeypatch.setattr(ops, "_WG_NEXT", {})
+    dev = "cuda:0"
+    assert ops.side_streams_in_use(dev) == []
+    dealt = [ops._wgrad_stream(dev) for _ in range(7)]
+    assert dealt[0] is made[(dev, 0)]                                  # the stream engine / models already know
+    assert len({id(s) for s in dealt}) == 3 and dealt[:3] == dealt[3:6] and dealt[6] is dealt[0]
+    assert ops.side_streams_in_use(dev) == dealt[:3]
+    assert ops.side_streams_in_use("cuda:1") == []
+    monkeypatch.setattr(ops, "WGRAD_STREAMS", 1)
+    monkeypatch.setattr(ops, "_WG_NEXT", {})
+    assert all(ops._wgrad_stream(dev) is made[(dev, 0)] for _ in range(3))
 
 
 def test_no_cpu_fallback():
