@@ -322,7 +322,8 @@ def kernel_times(cfg, B, model, bq, dev, use_graph):
     # the layer's four projections (forward and input gradient), csrc/linear_simt.cu
     T_ = nm * B
     lin_bytes = 0
-    us["linear_fwd_layer"] = us["linear_dx_layer"] = 0.0
+    us["linear_fwd_layer"] = us["linear_dx_layer"] = us["linear_wgrad_layer"] = 0.0
+    wg_ok = True
     for (fi, fo, relu) in ((d_, 3 * d_, False), (d_, d_, False), (d_, 2 * d_, True), (2 * d_, d_, False)):
         xl = torch.randn(T_, fi, device=dev, generator=gq)
         wl = torch.randn(fo, fi, device=dev, generator=gq) * 0.1
@@ -336,6 +337,18 @@ def kernel_times(cfg, B, model, bq, dev, use_graph):
         us["linear_fwd_layer"] += tf
         us["linear_dx_layer"] += time_graphed(lin_fb, dev) - tf
         lin_bytes += 4 * (T_ * fi + fi * fo + T_ * fo)
+        # the weight-gradient pair of the same projection (csrc/dense.cu: wgrad_partial_kernel on the tensor cores +
+        # slices_reduce4_kernel); in the step it runs on the side streams beside the chain, so it is reported, not
+        # ranked with the chain's kernels.  Never allowed to break the line.
+        if wg_ok:
+            try:
+                def lin_wb():
+                    w_, b_ = wl.detach().requires_grad_(), bl.detach().requires_grad_()
+                    torch.autograd.grad(ops.linear(xl, w_, b_, relu=relu), (w_, b_), gl)
+                us["linear_wgrad_layer"] += max(time_graphed(lin_wb, dev) - tf, 0.0)
+            except Exception as e:                       # noqa: BLE001 -- informational measurement only
+                sys.stderr.write("bench.py: weight-gradient timing skipped (%s)\n" % str(e)[:120])
+                us["linear_wgrad_layer"], wg_ok = 0.0, False
     us["linear_bytes_layer"] = float(lin_bytes)
     if use_graph:
         ctx_t = model.encoder.static_context(bq[6], mask_b, nm)
@@ -640,6 +653,7 @@ def main():
         lin_us = kern_us.pop("linear_fwd_layer")
         lin_dx_us = kern_us.pop("linear_dx_layer")
         lin_bytes = kern_us.pop("linear_bytes_layer")
+        lin_wg_us = kern_us.pop("linear_wgrad_layer", None)
         # static (CUDA-graph) step: every layer runs the matrix-free kernels, the coefficient scalar of the last layer
         # is recomputed from q / k (ops.LazyAttention); eager reference-API forward(): the last layer writes its matrix
         n_rows_layers = (L if res["use_graph"] else L - 1) if rows_on else 0
@@ -669,6 +683,8 @@ def main():
         roofline["attn_matrix_bwd_us_per_launch"] = round(kern_us["attn_matrix_bwd"], 2)
         roofline["linear_fwd_us_per_layer"] = round(lin_us, 2)
         roofline["linear_dx_us_per_layer"] = round(lin_dx_us, 2)
+        if lin_wg_us:          # weight-gradient pairs of the four projections (side streams; profiles/r2_launches_final.md)
+            roofline["linear_wgrad_us_per_layer"] = round(lin_wg_us, 2)
         roofline_cheb = roof("cheb_fwd_%s_kernel<%d>" % ("lane" if nm <= 64 else "graph", dh), cheb_bytes,
                              kern_us["cheb_fwd"], 1,
                              small % (cheb_bytes / 1e6) + "; roofline_sweep is the same kernel family on an HBM-sized "
