@@ -256,9 +256,10 @@ int feta_attn_rows_bwd(const float* q, const float* k, const float* v, int64_t s
  * reference's upstream).  T = Nmax*B tokens.
  *   feta_linear_wgrad:  dW[out,in] = sum_t dY[t,out] X[t,in],  db[out] = sum_t dY[t,out] (db may be
  *     NULL).  dY [T,out], X [T,in] contiguous, 16-byte aligned, out/in multiples of 4.  `partial`
- *     needs feta_linear_wgrad_slices(T) * (out*in + out) floats.  The token axis is split over CTAs,
- *     a second pass folds the slices in slice order (deterministic).  `counters` is reserved (may be
- *     NULL).
+ *     needs feta_linear_wgrad_slices(T) * (out*in + out) floats.  The token axis is split over CTAs
+ *     (each contracts its slice on the tensor cores, 3xTF32: fp32-grade), a second pass folds the slices
+ *     in slice order (deterministic).  No shared scratch: calls on different streams may overlap.
+ *     `counters` is reserved (may be NULL).
  *   feta_add_layernorm_fwd:  z = a + bscale[row] * b (b, bscale may be NULL), y = LayerNorm(z)*gamma + beta;
  *     saves z, mean, rstd [T] for the backward.  D <= 256.  bscale is the per-node `degree` factor the
  *     layer applies to the attention branch before the residual.
