@@ -59,6 +59,10 @@ def test_model_forward_backward_parity(cuda, name, B, over):
         scale = float(po[k].grad.abs().max())
         if scale < 1e-9:
             continue
+        # 1e-3, not north_star's 1e-4: BOTH sides of this comparison are fp32 (the oracle on the CPU, the kernels on
+        # the GPU) and each carries its own rounding through up to 10 layers, so their difference is not an error of
+        # either.  The 1e-4 bar is held where the reference is exact: tests/test_gpu_reference_pin.py compares the
+        # same models' outputs, losses and every parameter gradient with the fp64 run of the reference's own code.
         assert rel_err(pg[k].grad, po[k].grad) < 1e-3, (k, rel_err(pg[k].grad, po[k].grad))
     plan = next(iter(m.encoder.spectral_gnns._plans.values()))
     assert plan.validate()[7] == 0                                         # device-side guard never tripped
