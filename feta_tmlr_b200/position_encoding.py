@@ -242,9 +242,7 @@ class LapEncoding(PositionEncoding):
         for idx in _size_sorted_chunks(graphs):
             L, ns, deg = dense_laplacians([graphs[i] for i in idx], 'sym' if rw else self.normalization,
                                           device=self.device, return_deg=True)
-            if not bool(_is_symmetric(L).all()):
-                raise NotImplementedError("LapEncoding: a graph's Laplacian is not symmetric (directed edge list); "
-                                          "the batched symmetric eigendecomposition does not apply")
+            sym = _is_symmetric(L).cpu().numpy()
             nmax = L.shape[1]
             # push the padding's zero eigenvalues to the top so real eigenpairs come first, ascending
             pad = (torch.arange(nmax, device=L.device).unsqueeze(0)
@@ -254,8 +252,13 @@ class LapEncoding(PositionEncoding):
                 U = U / _rw_scale(deg).unsqueeze(2)
                 U = U / torch.linalg.vector_norm(U, dim=1, keepdim=True)      # np.linalg.eig returns unit vectors
             for j, (i, n) in enumerate(zip(idx, ns)):
-                pe = U[j, :n, 1:self.pos_enc_dim + 1]
-                pe = pe[:, :max(0, min(self.pos_enc_dim, n - 1))]
+                if not sym[j]:      # directed edge list: the general eigendecomposition the reference calls (:137-139)
+                    Lj = dense_laplacians([graphs[i]], self.normalization)[0][0].numpy()
+                    val, vec = np.linalg.eig(Lj)
+                    pe = torch.from_numpy(np.real(vec[:, val.argsort()])[:, 1:self.pos_enc_dim + 1])
+                else:
+                    pe = U[j, :n, 1:self.pos_enc_dim + 1]
+                    pe = pe[:, :max(0, min(self.pos_enc_dim, n - 1))]
                 full = torch.zeros((n, self.pos_enc_dim), dtype=torch.float32)
                 full[:, :pe.shape[1]] = pe.to(torch.float32).cpu()
                 out[i] = full
