@@ -40,16 +40,23 @@ def _edge_index(g):
     return np.asarray(ei.cpu() if torch.is_tensor(ei) else ei, dtype=np.int64)
 
 
-def dense_laplacians(graphs, normalization, device='cpu', dtype=torch.float64, return_deg=False):
+def _edge_weight(g):
+    """``graph.edge_attr`` as the 1-D edge weight PyG ``get_laplacian`` takes (``use_edge_attr=True``, :66)."""
+    ea = g['edge_attr'] if isinstance(g, dict) else g.edge_attr
+    return np.asarray(ea.cpu() if torch.is_tensor(ea) else ea, dtype=np.float64).reshape(-1)
+
+
+def dense_laplacians(graphs, normalization, device='cpu', dtype=torch.float64, return_deg=False, weighted=False):
     """Padded batch ``[G, nmax, nmax]`` of PyG ``get_laplacian`` matrices (self loops removed,
-    multi-edges summed, degree over the source index) + the node counts (+ the degrees)."""
+    multi-edges summed, degree over the source index; ``weighted``: edge weights from ``edge_attr``, assumed
+    positive) + the node counts (+ the degrees)."""
     ns = np.array([_num_nodes(g) for g in graphs], dtype=np.int64)
     nmax = int(ns.max())
     A = np.zeros((len(graphs), nmax, nmax), dtype=np.float64)
     for i, g in enumerate(graphs):
         s, t = _edge_index(g)
         keep = s != t
-        np.add.at(A[i], (s[keep], t[keep]), 1.0)
+        np.add.at(A[i], (s[keep], t[keep]), _edge_weight(g)[keep] if weighted else 1.0)
     A = torch.from_numpy(A).to(device=device, dtype=dtype)
     deg = A.sum(dim=2)
     eye = torch.eye(nmax, device=device, dtype=dtype).unsqueeze(0)
@@ -96,7 +103,7 @@ def _rw_scale(deg):
     return torch.where(deg > 0, deg.clamp(min=1e-300).sqrt(), torch.ones_like(deg))
 
 
-def _spectral_map(graphs, normalization, fn, device, fallback):
+def _spectral_map(graphs, normalization, fn, device, fallback, weighted=False):
     """U f(w) U^T per graph, one batched eigh per size-sorted chunk (``'rw'``: the similarity transform of the
     module docstring around the ``'sym'`` decomposition).  A graph whose adjacency is NOT symmetric (directed edge
     list) takes ``fallback(L)`` -- the general dense formula the reference's scipy ``expm`` / matrix power
@@ -105,7 +112,8 @@ def _spectral_map(graphs, normalization, fn, device, fallback):
     rw = normalization == 'rw'
     for idx in _size_sorted_chunks(graphs):
         sub = [graphs[i] for i in idx]
-        L, ns, deg = dense_laplacians(sub, 'sym' if rw else normalization, device=device, return_deg=True)
+        L, ns, deg = dense_laplacians(sub, 'sym' if rw else normalization, device=device, return_deg=True,
+                                      weighted=weighted)
         sym = _is_symmetric(L).cpu().numpy()
         # padded rows/cols are zero: they add zero eigenvalues whose eigenvectors live in the padding
         w, U = torch.linalg.eigh(L)
@@ -117,7 +125,8 @@ def _spectral_map(graphs, normalization, fn, device, fallback):
             if sym[j]:
                 out[i] = M[j, :n, :n].to(torch.float32).cpu()
             else:
-                Lj = dense_laplacians([sub[j]], normalization, device=device)[0][0] if rw else L[j, :n, :n]
+                Lj = dense_laplacians([sub[j]], normalization, device=device, weighted=weighted)[0][0] if rw \
+                    else L[j, :n, :n]
                 out[i] = fallback(Lj).to(torch.float32).cpu()
     return out
 
@@ -171,13 +180,11 @@ class DiffusionEncoding(PositionEncoding):
 
     def __init__(self, savepath, beta=1., use_edge_attr=False, normalization=None, zero_diag=False, device=None):
         super().__init__(savepath, zero_diag, device)
-        if use_edge_attr:
-            raise NotImplementedError("use_edge_attr is never set by the reference drivers")
-        self.beta, self.normalization = beta, normalization
+        self.beta, self.normalization, self.use_edge_attr = beta, normalization, use_edge_attr
 
     def compute_all(self, graphs):
         return _spectral_map(graphs, self.normalization, lambda w: torch.exp(-self.beta * w), self.device,
-                             fallback=lambda L: torch.matrix_exp(-self.beta * L))
+                             fallback=lambda L: torch.matrix_exp(-self.beta * L), weighted=self.use_edge_attr)
 
 
 class PStepRWEncoding(PositionEncoding):
@@ -186,14 +193,13 @@ class PStepRWEncoding(PositionEncoding):
     def __init__(self, savepath, p=1, beta=0.5, use_edge_attr=False, normalization=None, zero_diag=False,
                  device=None):
         super().__init__(savepath, zero_diag, device)
-        if use_edge_attr:
-            raise NotImplementedError("use_edge_attr is never set by the reference drivers")
-        self.p, self.beta, self.normalization = p, beta, normalization
+        self.p, self.beta, self.normalization, self.use_edge_attr = p, beta, normalization, use_edge_attr
 
     def compute_all(self, graphs):
         return _spectral_map(graphs, self.normalization, lambda w: (1.0 - self.beta * w) ** self.p, self.device,
                              fallback=lambda L: torch.linalg.matrix_power(
-                                 torch.eye(L.shape[0], dtype=L.dtype, device=L.device) - self.beta * L, self.p))
+                                 torch.eye(L.shape[0], dtype=L.dtype, device=L.device) - self.beta * L, self.p),
+                             weighted=self.use_edge_attr)
 
 
 class AdjEncoding(PositionEncoding):
@@ -232,16 +238,14 @@ class LapEncoding(PositionEncoding):
 
     def __init__(self, dim, use_edge_attr=False, normalization=None, device=None):
         super().__init__(None, False, device)
-        if use_edge_attr:
-            raise NotImplementedError("use_edge_attr is never set by the reference drivers")
-        self.pos_enc_dim, self.normalization = dim, normalization
+        self.pos_enc_dim, self.normalization, self.use_edge_attr = dim, normalization, use_edge_attr
 
     def compute_all(self, graphs):
         rw = self.normalization == 'rw'      # eigenvectors of L_rw = S^-1 (eigenvectors of L_sym), renormalised
         out = [None] * len(graphs)
         for idx in _size_sorted_chunks(graphs):
             L, ns, deg = dense_laplacians([graphs[i] for i in idx], 'sym' if rw else self.normalization,
-                                          device=self.device, return_deg=True)
+                                          device=self.device, return_deg=True, weighted=self.use_edge_attr)
             sym = _is_symmetric(L).cpu().numpy()
             nmax = L.shape[1]
             # push the padding's zero eigenvalues to the top so real eigenpairs come first, ascending
@@ -253,7 +257,7 @@ class LapEncoding(PositionEncoding):
                 U = U / torch.linalg.vector_norm(U, dim=1, keepdim=True)      # np.linalg.eig returns unit vectors
             for j, (i, n) in enumerate(zip(idx, ns)):
                 if not sym[j]:      # directed edge list: the general eigendecomposition the reference calls (:137-139)
-                    Lj = dense_laplacians([graphs[i]], self.normalization)[0][0].numpy()
+                    Lj = dense_laplacians([graphs[i]], self.normalization, weighted=self.use_edge_attr)[0][0].numpy()
                     val, vec = np.linalg.eig(Lj)
                     pe = torch.from_numpy(np.real(vec[:, val.argsort()])[:, 1:self.pos_enc_dim + 1])
                 else:

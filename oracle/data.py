@@ -108,24 +108,24 @@ def collate_ogb(batch, n_tags=None, n_features=None):
     return _collate_common(batch, n_tags, n_features, 'ogb')
 
 
-def _dense_laplacian(edge_index, num_nodes, normalization):
-    ei, ew = pyg17.get_laplacian(edge_index, None, normalization=normalization,
+def _dense_laplacian(edge_index, num_nodes, normalization, edge_weight=None):
+    ei, ew = pyg17.get_laplacian(edge_index, edge_weight, normalization=normalization,
                                  dtype=torch.float32, num_nodes=num_nodes)
     L = np.zeros((num_nodes, num_nodes), dtype=np.float32)
     np.add.at(L, (ei[0].numpy(), ei[1].numpy()), ew.numpy())      # to_scipy_sparse_matrix sums dups
     return L
 
 
-def diffusion_pe(edge_index, num_nodes, beta=1.0, normalization=None):
+def diffusion_pe(edge_index, num_nodes, beta=1.0, normalization=None, edge_weight=None):
     """DiffusionEncoding.compute_pe -- position_encoding.py:65-72: ``expm(-beta L)``."""
     from scipy.linalg import expm
-    L = _dense_laplacian(edge_index, num_nodes, normalization)
+    L = _dense_laplacian(edge_index, num_nodes, normalization, edge_weight)   # use_edge_attr: :66, :81, :129
     return torch.from_numpy(expm(-beta * L))
 
 
-def pstep_pe(edge_index, num_nodes, p=1, beta=0.5, normalization=None):
+def pstep_pe(edge_index, num_nodes, p=1, beta=0.5, normalization=None, edge_weight=None):
     """PStepRWEncoding.compute_pe -- position_encoding.py:83-93: ``(I - beta L)^p``."""
-    L = _dense_laplacian(edge_index, num_nodes, normalization)
+    L = _dense_laplacian(edge_index, num_nodes, normalization, edge_weight)   # use_edge_attr: :66, :81, :129
     M = np.eye(num_nodes, dtype=L.dtype) - beta * L
     tmp = M
     for _ in range(p - 1):
@@ -133,10 +133,10 @@ def pstep_pe(edge_index, num_nodes, p=1, beta=0.5, normalization=None):
     return torch.from_numpy(tmp)
 
 
-def lap_pe(edge_index, num_nodes, dim, normalization=None):
+def lap_pe(edge_index, num_nodes, dim, normalization=None, edge_weight=None):
     """LapEncoding.compute_pe -- position_encoding.py:127-161 (np.linalg.eig, ascending
     eigenvalues, drop the first eigenvector, zero-pad to ``dim`` columns)."""
-    L = _dense_laplacian(edge_index, num_nodes, normalization)
+    L = _dense_laplacian(edge_index, num_nodes, normalization, edge_weight)   # use_edge_attr: :66, :81, :129
     EigVal, EigVec = np.linalg.eig(L)
     idx = EigVal.argsort()
     EigVal, EigVec = EigVal[idx], np.real(EigVec[:, idx])

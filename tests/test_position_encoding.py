@@ -90,6 +90,33 @@ def test_rw_with_isolated_nodes_and_directed_edges():
     assert got.shape == (n, 4) and bool(torch.isfinite(got).all())
 
 
+@pytest.mark.parametrize("norm", [None, 'sym', 'rw'])
+def test_use_edge_attr_weights_the_laplacian(norm):
+    """``use_edge_attr=True`` (position_encoding.py:66, :81, :129): ``graph.edge_attr`` is the edge weight of PyG
+    ``get_laplacian``.  Symmetric positive weights (one per undirected edge) keep the batched path."""
+    gs = _graphs(5)
+    rng = np.random.default_rng(7)
+    for g in gs:
+        s, t = g['edge_index']
+        key = np.minimum(s, t) * 1000 + np.maximum(s, t)
+        w = {k: rng.uniform(0.5, 2.0) for k in np.unique(key)}
+        g['edge_attr'] = np.array([w[k] for k in key])
+    for g in gs:
+        e, n, w = torch.from_numpy(g['edge_index']), g['x'].shape[0], torch.from_numpy(g['edge_attr']).float()
+        m = pe.DiffusionEncoding(None, beta=1.0, use_edge_attr=True, normalization=norm, device='cpu').compute_all([g])[0]
+        assert torch.allclose(m, od.diffusion_pe(e, n, 1.0, norm, edge_weight=w).float(), atol=5e-6)
+        unweighted = pe.DiffusionEncoding(None, beta=1.0, normalization=norm, device='cpu').compute_all([g])[0]
+        assert not torch.allclose(m, unweighted, atol=1e-3)
+        m = pe.PStepRWEncoding(None, p=2, beta=0.5, use_edge_attr=True, normalization=norm, device='cpu').compute_all([g])[0]
+        assert torch.allclose(m, od.pstep_pe(e, n, 2, 0.5, norm, edge_weight=w).float(), atol=1e-5)
+        m = pe.LapEncoding(3, use_edge_attr=True, normalization=norm, device='cpu').compute_all([g])[0]
+        L = od._dense_laplacian(e, n, norm, w).astype(np.float64)
+        ev = np.sort(np.linalg.eigvals(L).real)
+        for c in range(3):
+            v = m[:, c].double().numpy()
+            assert abs(np.linalg.norm(v) - 1.0) < 1e-5 and np.allclose(L @ v, ev[c + 1] * v, atol=1e-4)
+
+
 def test_synthetic_diffusion_pe_is_the_same_kernel():
     g = _graphs(1)[0]
     a = synthetic.diffusion_pe(g['edge_index'], g['x'].shape[0], 1.0)
