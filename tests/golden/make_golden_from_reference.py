@@ -264,8 +264,63 @@ def model_case(name, B, seed, tag=None, **over):
           [g['x'].shape[0] for g in graphs], float(loss), float(out.abs().max())))
 
 
+# ---------------------------------------------------------------------------------------------------
+# N3: position encodings -- transformer/position_encoding.py:55-161 executed by the reference (scipy expm,
+# sparse matrix powers, np.linalg.eig); fp64 where the reference computes in fp64 (it builds fp32 Laplacians:
+# get_laplacian's default dtype), stored as the reference returns them
+# ---------------------------------------------------------------------------------------------------
+def pe_graphs():
+    """5 molecule-shape + 2 small dense SBM graphs (the fixture stores dense [n, n] kernels: kept small); #1 gets an
+    isolated node, #2 a one-way (directed) edge; every graph also carries symmetric positive edge weights for the
+    ``use_edge_attr`` cases."""
+    rng = np.random.default_rng(61)
+    gs = [synthetic.make_graph(rng, 'ZINC') for _ in range(5)]
+    gs = [dict(x=g['x'], edge_index=np.asarray(g['edge_index'])) for g in gs]
+    for sizes, p, q in (([7, 9, 8], 0.5, 0.35), ([6, 5, 9, 7], 0.55, 0.25)):
+        ei, block = synthetic.sbm_graph(rng, sizes, p, q)
+        gs.append(dict(x=block.reshape(-1, 1), edge_index=np.asarray(ei)))
+    ei = gs[1]['edge_index']
+    gs[1]['edge_index'] = ei[:, (ei[0] != 0) & (ei[1] != 0)]
+    n2 = gs[2]['x'].shape[0]
+    gs[2]['edge_index'] = np.concatenate([gs[2]['edge_index'], np.array([[0], [n2 - 1]])], axis=1)
+    for g in gs:
+        s, t = g['edge_index']
+        key = np.minimum(s, t) * 100000 + np.maximum(s, t)
+        w = {k: rng.uniform(0.5, 2.0) for k in np.unique(key)}
+        g['edge_attr'] = np.array([w[k] for k in key], dtype=np.float32)
+    return gs
+
+
+def pe_cases():
+    P = REF.pe
+    gs = pe_graphs()
+    datas = [REF.Data(torch.from_numpy(np.asarray(g['x'])), torch.from_numpy(g['edge_index']).long(), None,
+                      torch.from_numpy(g['edge_attr'])) for g in gs]
+    encs = {}
+    for norm in (None, 'sym', 'rw'):
+        tag = str(norm)
+        encs['diffusion_' + tag] = P.DiffusionEncoding(None, beta=1.0, normalization=norm)
+        encs['diffusion_w_' + tag] = P.DiffusionEncoding(None, beta=0.5, use_edge_attr=True, normalization=norm)
+        encs['pstep_' + tag] = P.PStepRWEncoding(None, p=3, beta=0.5, normalization=norm)
+        encs['pstep_w_' + tag] = P.PStepRWEncoding(None, p=2, beta=0.25, use_edge_attr=True, normalization=norm)
+        encs['lap_' + tag] = P.LapEncoding(4, normalization=norm)
+        encs['lap_w_' + tag] = P.LapEncoding(3, use_edge_attr=True, normalization=norm)
+    encs['adj'] = P.AdjEncoding(None)
+    encs['full'] = P.FullEncoding(None)
+    out = dict(graphs=[dict(x=torch.from_numpy(np.asarray(g['x'])), edge_index=torch.from_numpy(g['edge_index']),
+                            edge_attr=torch.from_numpy(g['edge_attr'])) for g in gs], pe={})
+    for k, enc in encs.items():
+        out['pe'][k] = [enc.compute_pe(d) for d in datas]
+    return out
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "needs the reference tree at %s" % ref_shim.REFERENCE_ROOT
+    if sys.argv[1:] == ["pe"]:                       # only the position-encoding fixture
+        save_fixture(pe_cases(), os.path.join(HERE, "ref_pe.pt.gz"))
+        print("ref_pe.pt.gz %d bytes" % os.path.getsize(os.path.join(HERE, "ref_pe.pt.gz")))
+        sys.exit(0)
+    save_fixture(pe_cases(), os.path.join(HERE, "ref_pe.pt.gz"))
     coeff, gavg = coeff_cases()
     save_fixture(dict(cheb=cheb_cases(), arma=arma_cases(), coeff=coeff, global_avg=gavg),
                  os.path.join(HERE, "ref_ops.pt.gz"))

@@ -20,8 +20,10 @@ own, unmodified op sequence:
     models.py           DiffTransformerEncoderGenGCN (+ get_filter_coefficients, filter), the three heads,
                         GlobalAvg1D                                                   -- reference code
     data.py             GraphDataset_v2 / _sbm / _ogb  collate_fn                     -- reference code
+    position_encoding.py  Diffusion / PStepRW / Adj / Full / Lap encodings (compute_pe)  -- reference code
     MessagePassing.propagate, get_laplacian, remove/add_self_loops, gcn_norm,
-    GCNConv, global_mean_pool, degree, AtomEncoder, BondEncoder                      -- this shim
+    GCNConv, global_mean_pool, degree, to_scipy_sparse_matrix, to_dense_adj,
+    AtomEncoder, BondEncoder                                                         -- this shim
     DiffTransformerEncoderLayer                                                      -- oracle/layers.py (F1)
 """
 import inspect
@@ -109,6 +111,30 @@ def _get_laplacian(edge_index, edge_weight=None, normalization=None, dtype=None,
         edge_weight = di[row] * edge_weight
         edge_index, edge_weight = _add_self_loops(edge_index, -edge_weight, fill_value=1., num_nodes=N)
     return edge_index, edge_weight
+
+
+def _to_scipy_sparse_matrix(edge_index, edge_attr=None, num_nodes=None):
+    """``torch_geometric.utils.to_scipy_sparse_matrix`` (call sites position_encoding.py:69,85,133): COO matrix,
+    ones when no attribute is given; duplicates are summed when the caller converts (``.tocsc()``)."""
+    import scipy.sparse
+    row, col = edge_index.cpu()
+    if edge_attr is None:
+        edge_attr = torch.ones(row.size(0))
+    else:
+        edge_attr = edge_attr.view(-1).cpu()
+        assert edge_attr.size(0) == row.size(0)
+    N = _maybe_num_nodes(edge_index, num_nodes)
+    return scipy.sparse.coo_matrix((edge_attr.numpy(), (row.numpy(), col.numpy())), (N, N))
+
+
+def _to_dense_adj(edge_index, batch=None, edge_attr=None, max_num_nodes=None):
+    """``torch_geometric.utils.to_dense_adj`` for a single graph (call site position_encoding.py:105): ``[1, N, N]``,
+    duplicate edges summed."""
+    assert batch is None and edge_attr is None
+    N = max_num_nodes if max_num_nodes is not None else _maybe_num_nodes(edge_index)
+    adj = torch.zeros(N * N)
+    adj.scatter_add_(0, edge_index[0] * N + edge_index[1], torch.ones(edge_index.size(1)))
+    return adj.view(1, N, N)
 
 
 def _degree(index, num_nodes=None, dtype=None):
@@ -284,7 +310,7 @@ def install(layer_cls=None):
     _module('torch_geometric.typing', OptTensor=Opt, Adj=Opt, PairTensor=Opt, Size=Opt)
     utils = _module('torch_geometric.utils', remove_self_loops=_remove_self_loops, add_self_loops=_add_self_loops,
                     add_remaining_self_loops=_add_remaining_self_loops, get_laplacian=_get_laplacian,
-                    degree=_degree)
+                    degree=_degree, to_scipy_sparse_matrix=_to_scipy_sparse_matrix, to_dense_adj=_to_dense_adj)
     _module('torch_geometric.utils.num_nodes', maybe_num_nodes=_maybe_num_nodes)
     nn_mod = _module('torch_geometric.nn', global_mean_pool=_global_mean_pool, global_max_pool=_global_max_pool,
                      GCNConv=GCNConv, ChebConv=_Unavailable, MessagePassing=MessagePassing)
@@ -324,6 +350,7 @@ def install(layer_cls=None):
         cheb=importlib.import_module('transformer.ChebNetDynamic'),
         models=importlib.import_module('transformer.models'),
         data=importlib.import_module('transformer.data'),
+        pe=importlib.import_module('transformer.position_encoding'),
         Data=Data)
     _INSTALLED['ns'] = ns
     return ns

@@ -240,3 +240,75 @@ def test_live_reference_model_matches_fixture():
         m.train()
         out = m(px.double(), ei, bi, fi, mask, None, None, deg.double())[0]
     assert rel_err(out, fx['out']) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------
+# N3: position encodings -- the reference's own position_encoding.py (scipy expm / sparse powers / np.linalg.eig on
+# fp32 Laplacians) vs the oracle restatement and vs the product's batched eigendecomposition (CPU here, the device
+# path is tests/test_position_encoding.py::test_position_encodings_on_cuda)
+# ---------------------------------------------------------------------------------------------------
+PE_FIX = load_fixture("ref_pe.pt.gz")
+_NORMS = {'None': None, 'sym': 'sym', 'rw': 'rw'}
+
+
+def _pe_graph_dicts():
+    return [dict(x=g['x'].numpy(), edge_index=g['edge_index'].numpy(), edge_attr=g['edge_attr'].numpy())
+            for g in PE_FIX['graphs']]
+
+
+def _same_eigvecs(got, ref, L, what):
+    """Columns agree up to sign wherever the eigenvalue is simple (a repeated eigenvalue leaves the basis free)."""
+    ev = np.sort(np.linalg.eigvals(L.astype(np.float64)).real)
+    for c in range(ref.shape[1]):
+        if c + 1 >= len(ev):
+            assert float(got[:, c].abs().max()) == 0.0 and float(ref[:, c].abs().max()) == 0.0, what
+            continue
+        gap = min(abs(ev[c + 1] - ev[c]), abs(ev[c + 2] - ev[c + 1]) if c + 2 < len(ev) else 1.0)
+        if gap < 1e-3:
+            continue
+        d = min(float((got[:, c] - ref[:, c]).abs().max()), float((got[:, c] + ref[:, c]).abs().max()))
+        assert d < 2e-4, (what, c, d)
+
+
+@pytest.mark.parametrize("norm", ['None', 'sym', 'rw'])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_position_encodings_equal_reference_run(norm, weighted):
+    from feta_tmlr_b200 import position_encoding as fpe
+    nz, w_ = _NORMS[norm], ('_w_' if weighted else '_')
+    beta_d, (p, beta_p), dim = (0.5, (2, 0.25), 3) if weighted else (1.0, (3, 0.5), 4)
+    gs = _pe_graph_dicts()
+    mine_d = fpe.DiffusionEncoding(None, beta=beta_d, use_edge_attr=weighted, normalization=nz, device='cpu').compute_all(gs)
+    mine_p = fpe.PStepRWEncoding(None, p=p, beta=beta_p, use_edge_attr=weighted, normalization=nz, device='cpu').compute_all(gs)
+    mine_l = fpe.LapEncoding(dim, use_edge_attr=weighted, normalization=nz, device='cpu').compute_all(gs)
+    for i, g in enumerate(PE_FIX['graphs']):
+        n, ei = g['x'].shape[0], g['edge_index']
+        w = g['edge_attr'] if weighted else None
+        rd, rp, rl = (PE_FIX['pe'][k + w_ + norm][i] for k in ('diffusion', 'pstep', 'lap'))
+        # the oracle restatement (dense scipy expm on the same fp32 Laplacian) and the product (fp64 eigh -> fp32)
+        assert torch.allclose(od.diffusion_pe(ei, n, beta_d, nz, edge_weight=w).float(), rd.float(), atol=5e-6)
+        assert torch.allclose(od.pstep_pe(ei, n, p, beta_p, nz, edge_weight=w).float(), rp.float(), atol=2e-5)
+        assert mine_d[i].dtype == torch.float32 and torch.allclose(mine_d[i], rd.float(), atol=5e-6), (i, norm)
+        assert torch.allclose(mine_p[i], rp.float(), atol=2e-5), (i, norm)
+        L = od._dense_laplacian(ei, n, nz, w)
+        assert rl.shape == (n, dim) and mine_l[i].shape == (n, dim)
+        _same_eigvecs(od.lap_pe(ei, n, dim, nz, edge_weight=w), rl, L, ("oracle", i, norm))
+        _same_eigvecs(mine_l[i], rl, L, ("product", i, norm))
+
+
+def test_adjacency_and_full_encodings_equal_reference_run():
+    from feta_tmlr_b200 import position_encoding as fpe
+    gs = _pe_graph_dicts()
+    for a, b in zip(fpe.AdjEncoding(None).compute_all(gs), PE_FIX['pe']['adj']):
+        assert a.shape == b.shape and torch.equal(a, b.float())
+    for a, b in zip(fpe.FullEncoding(None).compute_all(gs), PE_FIX['pe']['full']):
+        assert torch.equal(a, b.float())
+
+
+def test_live_reference_position_encoding_matches_fixture():
+    REF = _ref()
+    g = PE_FIX['graphs'][3]
+    d = REF.Data(g['x'], g['edge_index'].long(), None, g['edge_attr'])
+    assert torch.equal(REF.pe.DiffusionEncoding(None, beta=1.0, normalization='sym').compute_pe(d),
+                       PE_FIX['pe']['diffusion_sym'][3])
+    assert torch.equal(REF.pe.PStepRWEncoding(None, p=2, beta=0.25, use_edge_attr=True, normalization='rw').compute_pe(d),
+                       PE_FIX['pe']['pstep_w_rw'][3])
