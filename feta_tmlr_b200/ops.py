@@ -956,8 +956,17 @@ _WG_USED = {}            # device -> side streams that carry work of the running
 _WG_NEXT = {}            # device -> round-robin position
 
 
+def _dev_key(device):
+    """One dictionary key per physical device: ``'cuda'`` / ``torch.device('cuda')`` mean the current device."""
+    d = torch.device(device)
+    if d.type == 'cuda' and d.index is None:
+        d = torch.device('cuda', torch.cuda.current_device())
+    return d
+
+
 def _wgrad_stream(device):
     """The side stream the next weight-gradient (or gamma / beta fold) launch goes to; marks it as a join target."""
+    device = _dev_key(device)
     i = _WG_NEXT.get(device, 0)
     _WG_NEXT[device] = (i + 1) % WGRAD_STREAMS
     st = _side_stream(device) if i == 0 else _side_stream(device, ('wgrad', i))
@@ -970,7 +979,7 @@ def _wgrad_stream(device):
 def side_streams_in_use(device):
     """Side streams holding weight-gradient work of the running backward pass (engine: the gradient exchange of a
     slice waits on them)."""
-    return list(_WG_USED.get(device, ()))
+    return list(_WG_USED.get(_dev_key(device), ()))
 
 
 def _queue_side_join(device):
@@ -984,11 +993,12 @@ def _queue_side_join(device):
     _JOIN_TASK[device] = task
 
     def _join():
+        key = _dev_key(device)
         main = torch.cuda.current_stream(device)
-        for st in _WG_USED.get(device, ()):
+        for st in _WG_USED.get(key, ()):
             main.wait_stream(st)
-        _WG_USED[device] = []
-        _WG_NEXT[device] = 0
+        _WG_USED[key] = []
+        _WG_NEXT[key] = 0
 
     torch.autograd.Variable._execution_engine.queue_callback(_join)
 

@@ -139,13 +139,14 @@ def test_weight_gradient_launches_are_dealt_over_the_side_streams(monkeypatch):
     dev = "cuda:0"
     assert ops.side_streams_in_use(dev) == []
     dealt = [ops._wgrad_stream(dev) for _ in range(7)]
-    assert dealt[0] is made[(dev, 0)]                                  # the stream engine / models already know
+    assert dealt[0] is made[(torch.device(dev), 0)]                    # the stream engine / models already know
     assert len({id(s) for s in dealt}) == 3 and dealt[:3] == dealt[3:6] and dealt[6] is dealt[0]
     assert ops.side_streams_in_use(dev) == dealt[:3]
+    assert ops.side_streams_in_use(torch.device("cuda", 0)) == dealt[:3]          # one key per physical device
     assert ops.side_streams_in_use("cuda:1") == []
     monkeypatch.setattr(ops, "WGRAD_STREAMS", 1)
     monkeypatch.setattr(ops, "_WG_NEXT", {})
-    assert all(ops._wgrad_stream(dev) is made[(dev, 0)] for _ in range(3))
+    assert all(ops._wgrad_stream(dev) is made[(torch.device(dev), 0)] for _ in range(3))
 
 
 def test_no_cpu_fallback():
