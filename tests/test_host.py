@@ -93,6 +93,9 @@ def test_abi_header_ctypes_and_exports_agree():
     assert lib.feta_version() >= 100
     assert lib.feta_last_error_string() is not None
     assert lib.feta_cheb_plan_workspace_bytes(100, 1000) > 0 and lib.feta_cheb_workspace_bytes(100, 16, 16, 4) > 0
+    # token slices of the weight-gradient kernel: 128 tokens per CTA up to 8192 rows, 192 above (workspace sizing)
+    assert [lib.feta_linear_wgrad_slices(t) for t in (0, 1, 128, 129, 4736, 8192, 8193, 12032)] == \
+        [1, 1, 1, 2, 37, 64, 43, 63]
     # argument validation happens before any CUDA call: a NULL pointer is rejected with FETA_EINVAL
     assert lib.feta_cheb_fwd(*([0] * 7), 0, 0, 0, 0, 0, 10, 1, 4, 16, 16, 8, 1, 0, 0, 0) == -1
     assert b"NULL" in lib.feta_last_error_string()
