@@ -312,3 +312,38 @@ def test_live_reference_position_encoding_matches_fixture():
                        PE_FIX['pe']['diffusion_sym'][3])
     assert torch.equal(REF.pe.PStepRWEncoding(None, p=2, beta=0.25, use_edge_attr=True, normalization='rw').compute_pe(d),
                        PE_FIX['pe']['pstep_w_rw'][3])
+
+
+def test_position_encoders_drop_into_the_reference_dataset_flow(tmp_path):
+    """run_transformer_gengcn.py:258-272: ``pos_encoder.apply_to(train_dset, split='train')`` /
+    ``lap_pos_encoder.apply_to(train_dset)`` on the REFERENCE's ``GraphDataset_v2``, then the reference's own collate --
+    with this repo's encoders in place of the reference's, the padded ``pos_enc`` batch is the same, and a cache written
+    by either side is read by the other."""
+    REF = _ref()
+    from feta_tmlr_b200 import position_encoding as fpe
+    graphs = synthetic.make_dataset("ZINC", 5, seed=77)
+
+    def dataset():
+        datas = [REF.Data(torch.from_numpy(np.asarray(g['x'])),
+                          torch.from_numpy(np.asarray(g['edge_index'], dtype=np.int64)), torch.as_tensor(g['y']))
+                 for g in graphs]
+        return REF.data.GraphDataset_v2(datas, n_tags=synthetic.CONFIGS["ZINC"]['n_tags'], degree=True)
+
+    theirs, ours = dataset(), dataset()
+    cache_ref, cache_own = str(tmp_path / "ref_diffusion.pkl"), str(tmp_path / "own_diffusion.pkl")
+    REF.pe.DiffusionEncoding(cache_ref, beta=1.0, normalization='sym', zero_diag=False).apply_to(theirs, split='train')
+    REF.pe.LapEncoding(4, normalization='sym').apply_to(theirs)
+    fpe.DiffusionEncoding(cache_own, beta=1.0, normalization='sym', zero_diag=False, device='cpu').apply_to(ours, split='train')
+    fpe.LapEncoding(4, normalization='sym', device='cpu').apply_to(ours)
+    ids = [3, 0, 4]
+    bt = theirs.collate_fn()([theirs[i] for i in ids])
+    bo = ours.collate_fn()([ours[i] for i in ids])
+    assert torch.equal(bt[1], bo[1])                                            # mask
+    assert bt[2].shape == bo[2].shape and torch.allclose(bo[2].float(), bt[2].float(), atol=5e-6)   # pos_enc
+    assert bt[3].shape == bo[3].shape                                           # lap_pos_enc (sign / basis free)
+    # caches cross-load: the reference reads ours, we read the reference's
+    a, b = dataset(), dataset()
+    REF.pe.DiffusionEncoding(cache_own, beta=1.0, normalization='sym').apply_to(a, split='train')
+    fpe.DiffusionEncoding(cache_ref, beta=1.0, normalization='sym', device='cpu').apply_to(b, split='train')
+    for i in range(len(graphs)):
+        assert torch.equal(a.pe_list[i], ours.pe_list[i]) and torch.equal(b.pe_list[i], theirs.pe_list[i])
